@@ -1,0 +1,674 @@
+// mapf_b200.cu -- the C ABI of libmapf_b200.so (see include/mapf_b200.h) over the sm_100a kernels
+// of mapf_kernels.cuh.  Host side only: argument validation, map bit-packing, launch geometry,
+// state/IO buffer management.  There is no CPU implementation of the transition in here: every
+// entry point that computes launches a kernel, and fails with MAPF_ERR_CUDA if it cannot.
+#include "mapf_kernels.cuh"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                         \
+    do {                                                                                       \
+        cudaError_t e__ = (expr);                                                              \
+        if (e__ != cudaSuccess)                                                                \
+            return fail(MAPF_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), \
+                        __FILE__, __LINE__);                                                   \
+    } while (0)
+
+using KernelFn = void (*)(const mapf::KParams);
+
+template <int G>
+KernelFn step_for_sr(int sr) {
+    switch (sr) {
+        case 1: return mapf::mapf_step_kernel<G, 1>;
+        case 2: return mapf::mapf_step_kernel<G, 2>;
+        case 3: return mapf::mapf_step_kernel<G, 3>;
+    }
+    return nullptr;
+}
+template <int G>
+KernelFn reset_for_sr(int sr) {
+    switch (sr) {
+        case 1: return mapf::mapf_reset_kernel<G, 1>;
+        case 2: return mapf::mapf_reset_kernel<G, 2>;
+        case 3: return mapf::mapf_reset_kernel<G, 3>;
+    }
+    return nullptr;
+}
+KernelFn pick_step(int G, int sr) {
+    switch (G) {
+        case 4: return step_for_sr<4>(sr);
+        case 8: return step_for_sr<8>(sr);
+        case 16: return step_for_sr<16>(sr);
+        case 32: return step_for_sr<32>(sr);
+    }
+    return nullptr;
+}
+KernelFn pick_reset(int G, int sr) {
+    switch (G) {
+        case 4: return reset_for_sr<4>(sr);
+        case 8: return reset_for_sr<8>(sr);
+        case 16: return reset_for_sr<16>(sr);
+        case 32: return reset_for_sr<32>(sr);
+    }
+    return nullptr;
+}
+
+constexpr size_t kMaxSmem = 200 * 1024;
+
+}  // namespace
+
+struct mapf_handle {
+    mapf_config cfg;
+    int G, SR, V2, LW;
+    int wpr, map_words, fw;
+    int threads;
+    size_t smem_bytes;
+    KernelFn step_fn, reset_fn;
+    uint32_t *d_map_rows, *d_free_bits;
+    int32_t *d_num_free;
+    bool map_set;
+    uint32_t *d_err;
+    mapf_state st;
+    bool bound, owns_state;
+    int64_t launches;
+    // device mirrors of the *_host entry points' arguments (allocated on first use)
+    cudaStream_t hstream;
+    bool io_alloc;
+    int8_t *io_actions;
+    uint32_t *io_goal_override, *io_starts_override, *io_goals_override;
+    int32_t *io_goal_rank;
+    uint8_t *io_reset_mask;
+    mapf_outputs io_out;
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) return;
+        ok = (prev == dev) || cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (ok && prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+void state_sizes(const mapf_handle *h, int64_t n[10]) {
+    const int64_t B = h->cfg.num_envs, N = h->cfg.num_agents;
+    n[0] = B * N * 4;                      // positions  int16[B,N,2]
+    n[1] = B * N * 4;                      // goals
+    n[2] = B * N * 4;                      // starts
+    n[3] = B * N;                          // agent_flags
+    n[4] = B * N * 4;                      // lock_goal_progress
+    n[5] = B * N * 4;                      // lock_moved
+    n[6] = B * N * 4;                      // lock_failed_move
+    n[7] = B * (int64_t)h->LW * N * 2;     // lock_distance int16[B,LW,N]
+    n[8] = B * MAPF_ENV_WORDS * 4;         // env_words
+    n[9] = B * MAPF_METRIC_COUNT * 8;      // env_metrics
+}
+
+void **state_member(mapf_state *s, int i) {
+    switch (i) {
+        case 0: return reinterpret_cast<void **>(&s->positions);
+        case 1: return reinterpret_cast<void **>(&s->goals);
+        case 2: return reinterpret_cast<void **>(&s->starts);
+        case 3: return reinterpret_cast<void **>(&s->agent_flags);
+        case 4: return reinterpret_cast<void **>(&s->lock_goal_progress);
+        case 5: return reinterpret_cast<void **>(&s->lock_moved);
+        case 6: return reinterpret_cast<void **>(&s->lock_failed_move);
+        case 7: return reinterpret_cast<void **>(&s->lock_distance);
+        case 8: return reinterpret_cast<void **>(&s->env_words);
+        case 9: return reinterpret_cast<void **>(&s->env_metrics);
+    }
+    return nullptr;
+}
+
+void output_sizes(const mapf_handle *h, int64_t n[10]) {
+    const int64_t B = h->cfg.num_envs, N = h->cfg.num_agents;
+    n[0] = B * N * h->V2;           // local_obs
+    n[1] = B * N * 5;               // action_mask
+    n[2] = B * N * 8;               // goal_delta
+    n[3] = B * N;                   // blocking_prev
+    n[4] = B * N * 4;               // reward
+    n[5] = B;                       // terminated
+    n[6] = B;                       // truncated
+    n[7] = B;                       // step_flags
+    n[8] = B * N;                   // agent_step_flags
+    n[9] = B * MAPF_INFO_WORDS * 4; // info
+}
+
+void **output_member(mapf_outputs *o, int i) {
+    switch (i) {
+        case 0: return reinterpret_cast<void **>(&o->local_obs);
+        case 1: return reinterpret_cast<void **>(&o->action_mask);
+        case 2: return reinterpret_cast<void **>(&o->goal_delta);
+        case 3: return reinterpret_cast<void **>(&o->blocking_prev);
+        case 4: return reinterpret_cast<void **>(&o->reward);
+        case 5: return reinterpret_cast<void **>(&o->terminated);
+        case 6: return reinterpret_cast<void **>(&o->truncated);
+        case 7: return reinterpret_cast<void **>(&o->step_flags);
+        case 8: return reinterpret_cast<void **>(&o->agent_step_flags);
+        case 9: return reinterpret_cast<void **>(&o->info);
+    }
+    return nullptr;
+}
+
+int check_ready(const mapf_handle *h) {
+    if (!h) return fail(MAPF_ERR_INVALID_ARG, "null handle");
+    if (!h->map_set) return fail(MAPF_ERR_STATE, "mapf_set_map has not been called");
+    if (!h->bound) return fail(MAPF_ERR_STATE, "no state bound (mapf_bind_state / mapf_alloc_state)");
+    return MAPF_OK;
+}
+
+void fill_params(const mapf_handle *h, mapf::KParams &p) {
+    const mapf_config &c = h->cfg;
+    memset(&p, 0, sizeof(p));
+    p.B = c.num_envs; p.N = c.num_agents; p.R = c.rows; p.C = c.cols;
+    p.steps_per_episode = c.steps_per_episode;
+    p.lifelong = c.lifelong_mapf != 0;
+    p.lock_enabled = c.enable_lock_metrics != 0;
+    p.dw = c.deadlock_window_steps; p.lw = c.livelock_window_steps;
+    p.nearby = c.lock_nearby_manhattan; p.min_nb = c.lock_min_neighbors;
+    p.eps_floor = c.lock_progress_epsilon_floor;
+    p.normalize = c.normalize_goal_delta != 0;
+    p.deterministic = c.deterministic != 0;
+    p.per_env_maps = c.per_env_maps != 0;
+    p.env_id_base = c.env_id_base;
+    p.seed = c.seed;
+    p.den0 = (float)(c.rows - 1 > 1 ? c.rows - 1 : 1);  // ENV:152-155
+    p.den1 = (float)(c.cols - 1 > 1 ? c.cols - 1 : 1);
+    p.map_rows = h->d_map_rows; p.free_bits = h->d_free_bits; p.num_free = h->d_num_free;
+    p.wpr = h->wpr; p.map_words = h->map_words; p.fw = h->fw;
+    p.positions = reinterpret_cast<uint32_t *>(h->st.positions);
+    p.goals = reinterpret_cast<uint32_t *>(h->st.goals);
+    p.starts = reinterpret_cast<uint32_t *>(h->st.starts);
+    p.agent_flags = h->st.agent_flags;
+    p.lock_gp = h->st.lock_goal_progress; p.lock_mv = h->st.lock_moved; p.lock_fm = h->st.lock_failed_move;
+    p.lock_dist = h->st.lock_distance;
+    p.env_words = reinterpret_cast<int4 *>(h->st.env_words);
+    p.env_metrics = h->st.env_metrics;
+    p.err_bits = h->d_err;
+}
+
+void fill_outputs(mapf::KParams &p, const mapf_outputs *o) {
+    if (!o) return;
+    p.o_local_obs = o->local_obs; p.o_action_mask = o->action_mask;
+    p.o_goal_delta = reinterpret_cast<float2 *>(o->goal_delta);
+    p.o_blocking_prev = o->blocking_prev; p.o_reward = o->reward;
+    p.o_terminated = o->terminated; p.o_truncated = o->truncated;
+    p.o_step_flags = o->step_flags; p.o_agent_step_flags = o->agent_step_flags;
+    p.o_info = reinterpret_cast<int4 *>(o->info);
+}
+
+int launch(mapf_handle *h, KernelFn fn, const mapf::KParams &p, cudaStream_t s) {
+    const int groups = h->threads / h->G;
+    const unsigned grid = (unsigned)((h->cfg.num_envs + groups - 1) / groups);
+    fn<<<grid, h->threads, h->smem_bytes, s>>>(p);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    return MAPF_OK;
+}
+
+int ensure_io(mapf_handle *h) {
+    if (h->io_alloc) return MAPF_OK;
+    const int64_t B = h->cfg.num_envs, N = h->cfg.num_agents;
+    if (!h->hstream) CUDA_TRY(cudaStreamCreateWithFlags(&h->hstream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaMalloc(&h->io_actions, B * N));
+    CUDA_TRY(cudaMalloc(&h->io_goal_override, B * N * 4));
+    CUDA_TRY(cudaMalloc(&h->io_starts_override, B * N * 4));
+    CUDA_TRY(cudaMalloc(&h->io_goals_override, B * N * 4));
+    CUDA_TRY(cudaMalloc(&h->io_goal_rank, B * N * 4));
+    CUDA_TRY(cudaMalloc(&h->io_reset_mask, B));
+    int64_t n[10];
+    output_sizes(h, n);
+    for (int i = 0; i < 10; ++i) CUDA_TRY(cudaMalloc(output_member(&h->io_out, i), (size_t)n[i]));
+    h->io_alloc = true;
+    return MAPF_OK;
+}
+
+// device copies of the requested host outputs: only channels the caller asked for are computed
+void select_outputs(mapf_handle *h, const mapf_outputs *host, mapf_outputs *dev) {
+    memset(dev, 0, sizeof(*dev));
+    if (!host) return;
+    mapf_outputs tmp = *host;
+    for (int i = 0; i < 10; ++i)
+        if (*output_member(&tmp, i)) *output_member(dev, i) = *output_member(&h->io_out, i);
+}
+
+int copy_outputs_back(mapf_handle *h, const mapf_outputs *host) {
+    if (!host) return MAPF_OK;
+    int64_t n[10];
+    output_sizes(h, n);
+    mapf_outputs tmp = *host;
+    for (int i = 0; i < 10; ++i) {
+        void *dst = *output_member(&tmp, i);
+        if (dst)
+            CUDA_TRY(cudaMemcpyAsync(dst, *output_member(&h->io_out, i), (size_t)n[i],
+                                     cudaMemcpyDeviceToHost, h->hstream));
+    }
+    return MAPF_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *mapf_version(void) { return "mapf_b200 0.1.0 (sm_100a)"; }
+const char *mapf_last_error(void) { return g_err.c_str(); }
+
+int mapf_create(const mapf_config *cfg, mapf_handle **out) {
+    if (!cfg || !out) return fail(MAPF_ERR_INVALID_ARG, "null argument");
+    *out = nullptr;
+    const mapf_config &c = *cfg;
+    if (c.num_envs < 1) return fail(MAPF_ERR_INVALID_ARG, "num_envs must be >= 1");
+    if (c.num_agents < 1 || c.num_agents > MAPF_MAX_AGENTS)
+        return fail(MAPF_ERR_UNSUPPORTED, "num_agents=%d outside 1..%d", c.num_agents, MAPF_MAX_AGENTS);
+    if (c.rows < 1 || c.cols < 1 || c.rows > MAPF_MAX_DIM || c.cols > MAPF_MAX_DIM)
+        return fail(MAPF_ERR_UNSUPPORTED, "map %dx%d outside 1..%d", c.rows, c.cols, MAPF_MAX_DIM);
+    if (c.sensor_range < 1 || c.sensor_range > MAPF_MAX_SENSOR_RANGE)
+        return fail(MAPF_ERR_UNSUPPORTED, "sensor_range=%d outside 1..%d", c.sensor_range, MAPF_MAX_SENSOR_RANGE);
+    if (c.deadlock_window_steps < 1 || c.deadlock_window_steps > MAPF_MAX_LOCK_WINDOW ||
+        c.livelock_window_steps < 1 || c.livelock_window_steps > MAPF_MAX_LOCK_WINDOW)
+        return fail(MAPF_ERR_UNSUPPORTED, "lock windows must be in 1..%d", MAPF_MAX_LOCK_WINDOW);
+    if (c.lock_nearby_manhattan < 1 || c.lock_nearby_manhattan > 255 || c.lock_min_neighbors < 1)
+        return fail(MAPF_ERR_INVALID_ARG, "lock_nearby_manhattan / lock_min_neighbors must be >= 1");
+    if (c.steps_per_episode < 1) return fail(MAPF_ERR_INVALID_ARG, "steps_per_episode must be >= 1");
+
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev < 1)
+        return fail(MAPF_ERR_CUDA, "no CUDA device: %s (libmapf_b200 has no CPU fallback)",
+                    ce != cudaSuccess ? cudaGetErrorString(ce) : "device count is 0");
+    if (c.device < 0 || c.device >= ndev) return fail(MAPF_ERR_INVALID_ARG, "device %d of %d", c.device, ndev);
+    DeviceGuard guard(c.device);
+    if (!guard.ok) return fail(MAPF_ERR_CUDA, "cudaSetDevice(%d) failed", c.device);
+
+    mapf_handle *h = new (std::nothrow) mapf_handle();
+    if (!h) return fail(MAPF_ERR_STATE, "out of host memory");
+    memset(h, 0, sizeof(*h));
+    h->cfg = c;
+    h->G = c.num_agents <= 4 ? 4 : c.num_agents <= 8 ? 8 : c.num_agents <= 16 ? 16 : 32;
+    h->SR = c.sensor_range;
+    h->V2 = (2 * c.sensor_range + 1) * (2 * c.sensor_range + 1);
+    h->LW = c.livelock_window_steps;
+    // +1 word: the window extractor reads a 64-bit funnel (word, word + 1) of every padded row
+    h->wpr = (c.cols + 2 * mapf::PAD + 31) / 32 + 1;
+    h->map_words = (c.rows + 2 * mapf::PAD) * h->wpr;
+    h->fw = (c.rows * c.cols + 31) / 32;
+    h->step_fn = pick_step(h->G, h->SR);
+    h->reset_fn = pick_reset(h->G, h->SR);
+    h->threads = 0;
+    for (int t = 256; t >= 32; t >>= 1) {
+        mapf::SmemLayout L = mapf::make_layout(h->G, h->V2, c.num_agents, h->wpr, c.rows, h->fw,
+                                               c.per_env_maps != 0, t);
+        if ((size_t)L.total_words * 4 <= kMaxSmem) {
+            h->threads = t;
+            h->smem_bytes = (size_t)L.total_words * 4;
+            break;
+        }
+    }
+    if (!h->threads) {
+        delete h;
+        return fail(MAPF_ERR_UNSUPPORTED, "map %dx%d needs more shared memory than one SM has", c.rows, c.cols);
+    }
+    cudaError_t e1 = cudaFuncSetAttribute(reinterpret_cast<const void *>(h->step_fn),
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
+    cudaError_t e2 = cudaFuncSetAttribute(reinterpret_cast<const void *>(h->reset_fn),
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
+    cudaError_t e3 = cudaMalloc(&h->d_err, 4);
+    if (e3 == cudaSuccess) e3 = cudaMemset(h->d_err, 0, 4);
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
+        cudaError_t e = e1 != cudaSuccess ? e1 : e2 != cudaSuccess ? e2 : e3;
+        if (h->d_err) cudaFree(h->d_err);
+        delete h;
+        return fail(MAPF_ERR_CUDA, "kernel setup failed: %s (built for sm_100a only)", cudaGetErrorString(e));
+    }
+    *out = h;
+    return MAPF_OK;
+}
+
+int mapf_destroy(mapf_handle *h) {
+    if (!h) return MAPF_OK;
+    DeviceGuard guard(h->cfg.device);
+    cudaDeviceSynchronize();
+    if (h->owns_state)
+        for (int i = 0; i < 10; ++i) cudaFree(*state_member(&h->st, i));
+    if (h->io_alloc) {
+        cudaFree(h->io_actions); cudaFree(h->io_goal_override); cudaFree(h->io_starts_override);
+        cudaFree(h->io_goals_override); cudaFree(h->io_goal_rank); cudaFree(h->io_reset_mask);
+        for (int i = 0; i < 10; ++i) cudaFree(*output_member(&h->io_out, i));
+    }
+    if (h->hstream) cudaStreamDestroy(h->hstream);
+    cudaFree(h->d_map_rows); cudaFree(h->d_free_bits); cudaFree(h->d_num_free); cudaFree(h->d_err);
+    delete h;
+    return MAPF_OK;
+}
+
+int mapf_set_map(mapf_handle *h, const uint8_t *grid) {
+    if (!h || !grid) return fail(MAPF_ERR_INVALID_ARG, "null argument");
+    DeviceGuard guard(h->cfg.device);
+    const int R = h->cfg.rows, C = h->cfg.cols, N = h->cfg.num_agents;
+    const int64_t copies = h->cfg.per_env_maps ? h->cfg.num_envs : 1;
+    std::vector<uint32_t> rows((size_t)copies * h->map_words, 0xFFFFFFFFu);  // padding = obstacle (OOB -> 1, ENV:718)
+    std::vector<uint32_t> freeb((size_t)copies * h->fw, 0u);
+    std::vector<int32_t> nfree((size_t)copies, 0);
+    for (int64_t m = 0; m < copies; ++m) {
+        const uint8_t *g = grid + (size_t)m * R * C;
+        uint32_t *mr = rows.data() + (size_t)m * h->map_words;
+        uint32_t *fb = freeb.data() + (size_t)m * h->fw;
+        int F = 0;
+        for (int r = 0; r < R; ++r)
+            for (int c = 0; c < C; ++c) {
+                const uint8_t v = g[r * C + c];
+                if (v > 1) return fail(MAPF_ERR_INVALID_ARG, "grid cell (%d,%d) = %d, expected 0 or 1", r, c, v);
+                if (v == 0) {  // ENV:82 free cell
+                    const int bit = c + mapf::PAD;
+                    mr[(r + mapf::PAD) * h->wpr + (bit >> 5)] &= ~(1u << (bit & 31));
+                    const int cell = r * C + c;
+                    fb[cell >> 5] |= 1u << (cell & 31);
+                    ++F;
+                }
+            }
+        nfree[m] = F;
+        if (!h->cfg.deterministic && F < 2 * N)  // ENV:270-275
+            return fail(MAPF_ERR_INVALID_ARG, "Not enough free cells (%d) for %d agents (need %d)", F, N, 2 * N);
+    }
+    cudaFree(h->d_map_rows); cudaFree(h->d_free_bits); cudaFree(h->d_num_free);
+    h->d_map_rows = nullptr; h->d_free_bits = nullptr; h->d_num_free = nullptr;
+    h->map_set = false;
+    CUDA_TRY(cudaMalloc(&h->d_map_rows, rows.size() * 4));
+    CUDA_TRY(cudaMalloc(&h->d_free_bits, freeb.size() * 4));
+    CUDA_TRY(cudaMalloc(&h->d_num_free, nfree.size() * 4));
+    CUDA_TRY(cudaMemcpy(h->d_map_rows, rows.data(), rows.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(h->d_free_bits, freeb.data(), freeb.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(h->d_num_free, nfree.data(), nfree.size() * 4, cudaMemcpyHostToDevice));
+    h->map_set = true;
+    return MAPF_OK;
+}
+
+int mapf_state_nbytes(const mapf_handle *h, int64_t out_nbytes[10]) {
+    if (!h || !out_nbytes) return fail(MAPF_ERR_INVALID_ARG, "null argument");
+    state_sizes(h, out_nbytes);
+    return MAPF_OK;
+}
+
+int mapf_bind_state(mapf_handle *h, const mapf_state *state) {
+    if (!h || !state) return fail(MAPF_ERR_INVALID_ARG, "null argument");
+    mapf_state s = *state;
+    for (int i = 0; i < 10; ++i)
+        if (!*state_member(&s, i)) return fail(MAPF_ERR_INVALID_ARG, "mapf_state member %d is NULL", i);
+    if (h->owns_state) {
+        DeviceGuard guard(h->cfg.device);
+        for (int i = 0; i < 10; ++i) cudaFree(*state_member(&h->st, i));
+        h->owns_state = false;
+    }
+    h->st = s;
+    h->bound = true;
+    return MAPF_OK;
+}
+
+int mapf_alloc_state(mapf_handle *h) {
+    if (!h) return fail(MAPF_ERR_INVALID_ARG, "null handle");
+    if (h->owns_state) return MAPF_OK;
+    DeviceGuard guard(h->cfg.device);
+    int64_t n[10];
+    state_sizes(h, n);
+    mapf_state s;
+    memset(&s, 0, sizeof(s));
+    for (int i = 0; i < 10; ++i) {
+        CUDA_TRY(cudaMalloc(state_member(&s, i), (size_t)n[i]));
+        CUDA_TRY(cudaMemset(*state_member(&s, i), 0, (size_t)n[i]));
+    }
+    h->st = s;
+    h->bound = true;
+    h->owns_state = true;
+    return MAPF_OK;
+}
+
+int mapf_get_state_host(mapf_handle *h, const mapf_state *host) {
+    if (!h || !host) return fail(MAPF_ERR_INVALID_ARG, "null argument");
+    if (!h->bound) return fail(MAPF_ERR_STATE, "no state bound");
+    DeviceGuard guard(h->cfg.device);
+    int64_t n[10];
+    state_sizes(h, n);
+    mapf_state hs = *host;
+    CUDA_TRY(cudaDeviceSynchronize());
+    for (int i = 0; i < 10; ++i)
+        if (*state_member(&hs, i))
+            CUDA_TRY(cudaMemcpy(*state_member(&hs, i), *state_member(&h->st, i), (size_t)n[i], cudaMemcpyDeviceToHost));
+    return MAPF_OK;
+}
+
+int mapf_set_state_host(mapf_handle *h, const mapf_state *host) {
+    if (!h || !host) return fail(MAPF_ERR_INVALID_ARG, "null argument");
+    if (!h->bound) return fail(MAPF_ERR_STATE, "no state bound");
+    DeviceGuard guard(h->cfg.device);
+    int64_t n[10];
+    state_sizes(h, n);
+    mapf_state hs = *host;
+    CUDA_TRY(cudaDeviceSynchronize());
+    for (int i = 0; i < 10; ++i)
+        if (*state_member(&hs, i))
+            CUDA_TRY(cudaMemcpy(*state_member(&h->st, i), *state_member(&hs, i), (size_t)n[i], cudaMemcpyHostToDevice));
+    return MAPF_OK;
+}
+
+int mapf_reset(mapf_handle *h, const uint8_t *reset_mask, const int16_t *starts_override,
+               const int16_t *goals_override, const mapf_outputs *out, void *stream) {
+    int rc = check_ready(h);
+    if (rc) return rc;
+    if ((starts_override == nullptr) != (goals_override == nullptr))
+        return fail(MAPF_ERR_INVALID_ARG, "starts_override and goals_override must be given together");
+    DeviceGuard guard(h->cfg.device);
+    mapf::KParams p;
+    fill_params(h, p);
+    fill_outputs(p, out);
+    p.reset_mask = reset_mask;
+    p.starts_override = reinterpret_cast<const uint32_t *>(starts_override);
+    p.goals_override = reinterpret_cast<const uint32_t *>(goals_override);
+    return launch(h, h->reset_fn, p, static_cast<cudaStream_t>(stream));
+}
+
+int mapf_observe(mapf_handle *h, const mapf_outputs *out, void *stream) {
+    int rc = check_ready(h);
+    if (rc) return rc;
+    if (!out) return fail(MAPF_ERR_INVALID_ARG, "null outputs");
+    DeviceGuard guard(h->cfg.device);
+    mapf::KParams p;
+    fill_params(h, p);
+    fill_outputs(p, out);
+    p.o_reward = nullptr; p.o_terminated = nullptr; p.o_truncated = nullptr;
+    p.o_step_flags = nullptr; p.o_agent_step_flags = nullptr; p.o_info = nullptr;
+    p.observe_only = 1;
+    return launch(h, h->reset_fn, p, static_cast<cudaStream_t>(stream));
+}
+
+int mapf_observe_host(mapf_handle *h, const mapf_outputs *out_host) {
+    int rc = check_ready(h);
+    if (rc) return rc;
+    if (!out_host) return fail(MAPF_ERR_INVALID_ARG, "null outputs");
+    DeviceGuard guard(h->cfg.device);
+    rc = ensure_io(h);
+    if (rc) return rc;
+    mapf_outputs want;
+    memset(&want, 0, sizeof(want));
+    want.local_obs = out_host->local_obs; want.action_mask = out_host->action_mask;
+    want.goal_delta = out_host->goal_delta; want.blocking_prev = out_host->blocking_prev;
+    mapf_outputs dev;
+    select_outputs(h, &want, &dev);
+    rc = mapf_observe(h, &dev, h->hstream);
+    if (rc) return rc;
+    rc = copy_outputs_back(h, &want);
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(h->hstream));
+    return MAPF_OK;
+}
+
+int mapf_step(mapf_handle *h, const int8_t *actions, const int16_t *goal_override,
+              const int32_t *goal_rank, const mapf_outputs *out, int32_t auto_reset, void *stream) {
+    int rc = check_ready(h);
+    if (rc) return rc;
+    DeviceGuard guard(h->cfg.device);
+    mapf::KParams p;
+    fill_params(h, p);
+    fill_outputs(p, out);
+    p.actions = actions;
+    p.goal_override = reinterpret_cast<const uint32_t *>(goal_override);
+    p.goal_rank = goal_rank;
+    p.auto_reset = auto_reset != 0;
+    return launch(h, h->step_fn, p, static_cast<cudaStream_t>(stream));
+}
+
+int mapf_reset_host(mapf_handle *h, const uint8_t *reset_mask, const int16_t *starts_override,
+                    const int16_t *goals_override, const mapf_outputs *out_host) {
+    int rc = check_ready(h);
+    if (rc) return rc;
+    if ((starts_override == nullptr) != (goals_override == nullptr))
+        return fail(MAPF_ERR_INVALID_ARG, "starts_override and goals_override must be given together");
+    DeviceGuard guard(h->cfg.device);
+    rc = ensure_io(h);
+    if (rc) return rc;
+    const size_t B = h->cfg.num_envs, BN = B * h->cfg.num_agents;
+    if (reset_mask) CUDA_TRY(cudaMemcpyAsync(h->io_reset_mask, reset_mask, B, cudaMemcpyHostToDevice, h->hstream));
+    if (starts_override) {
+        CUDA_TRY(cudaMemcpyAsync(h->io_starts_override, starts_override, BN * 4, cudaMemcpyHostToDevice, h->hstream));
+        CUDA_TRY(cudaMemcpyAsync(h->io_goals_override, goals_override, BN * 4, cudaMemcpyHostToDevice, h->hstream));
+    }
+    mapf_outputs dev;
+    select_outputs(h, out_host, &dev);
+    rc = mapf_reset(h, reset_mask ? h->io_reset_mask : nullptr,
+                    starts_override ? reinterpret_cast<const int16_t *>(h->io_starts_override) : nullptr,
+                    starts_override ? reinterpret_cast<const int16_t *>(h->io_goals_override) : nullptr, &dev,
+                    h->hstream);
+    if (rc) return rc;
+    rc = copy_outputs_back(h, out_host);
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(h->hstream));
+    return MAPF_OK;
+}
+
+int mapf_step_host(mapf_handle *h, const int8_t *actions, const int16_t *goal_override,
+                   const int32_t *goal_rank, const mapf_outputs *out_host, int32_t auto_reset) {
+    int rc = check_ready(h);
+    if (rc) return rc;
+    DeviceGuard guard(h->cfg.device);
+    rc = ensure_io(h);
+    if (rc) return rc;
+    const size_t BN = (size_t)h->cfg.num_envs * h->cfg.num_agents;
+    if (actions) CUDA_TRY(cudaMemcpyAsync(h->io_actions, actions, BN, cudaMemcpyHostToDevice, h->hstream));
+    if (goal_override)
+        CUDA_TRY(cudaMemcpyAsync(h->io_goal_override, goal_override, BN * 4, cudaMemcpyHostToDevice, h->hstream));
+    if (goal_rank) CUDA_TRY(cudaMemcpyAsync(h->io_goal_rank, goal_rank, BN * 4, cudaMemcpyHostToDevice, h->hstream));
+    mapf_outputs dev;
+    select_outputs(h, out_host, &dev);
+    rc = mapf_step(h, actions ? h->io_actions : nullptr,
+                   goal_override ? reinterpret_cast<const int16_t *>(h->io_goal_override) : nullptr,
+                   goal_rank ? h->io_goal_rank : nullptr, &dev, auto_reset, h->hstream);
+    if (rc) return rc;
+    rc = copy_outputs_back(h, out_host);
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(h->hstream));
+    return MAPF_OK;
+}
+
+int mapf_flat_obs_dim(const mapf_handle *h, int32_t include_goal_distance, int32_t include_blocking_pressure,
+                      int32_t include_action_mask) {
+    if (!h) return fail(MAPF_ERR_INVALID_ARG, "null handle");
+    return h->V2 + 2 + (include_goal_distance ? 1 : 0) + (include_blocking_pressure ? 1 : 0) +
+           (include_action_mask ? 5 : 0);
+}
+
+int mapf_pack_flat_obs(mapf_handle *h, const mapf_outputs *ch, int32_t include_goal_distance,
+                       int32_t include_blocking_pressure, int32_t include_action_mask, float *flat,
+                       void *stream) {
+    if (!h || !ch || !flat) return fail(MAPF_ERR_INVALID_ARG, "null argument");
+    if (!ch->local_obs || !ch->goal_delta) return fail(MAPF_ERR_INVALID_ARG, "local_obs and goal_delta are required");
+    if (include_blocking_pressure && !ch->blocking_prev) return fail(MAPF_ERR_INVALID_ARG, "blocking_prev is required");
+    if (include_action_mask && !ch->action_mask) return fail(MAPF_ERR_INVALID_ARG, "action_mask is required");
+    DeviceGuard guard(h->cfg.device);
+    const int D = mapf_flat_obs_dim(h, include_goal_distance, include_blocking_pressure, include_action_mask);
+    const long long BN = (long long)h->cfg.num_envs * h->cfg.num_agents;
+    const long long total = BN * D;
+    const int threads = 256;
+    const unsigned grid = (unsigned)((total + threads - 1) / threads);
+    mapf::mapf_pack_flat_kernel<<<grid, threads, 0, static_cast<cudaStream_t>(stream)>>>(
+        ch->local_obs, reinterpret_cast<const float2 *>(ch->goal_delta), ch->blocking_prev, ch->action_mask, flat,
+        BN, h->V2, include_goal_distance ? 1 : 0, include_blocking_pressure ? 1 : 0, include_action_mask ? 1 : 0, D);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    return MAPF_OK;
+}
+
+static int sample_actions(mapf_handle *h, const int8_t *mask, int8_t *actions, uint64_t counter, void *stream) {
+    if (!h || !actions) return fail(MAPF_ERR_INVALID_ARG, "null argument");
+    DeviceGuard guard(h->cfg.device);
+    const long long BN = (long long)h->cfg.num_envs * h->cfg.num_agents;
+    const int threads = 256;
+    const unsigned grid = (unsigned)((BN + threads - 1) / threads);
+    mapf::mapf_sample_actions_kernel<<<grid, threads, 0, static_cast<cudaStream_t>(stream)>>>(
+        mask, actions, BN, h->cfg.num_agents, h->cfg.seed, h->cfg.env_id_base, counter);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    return MAPF_OK;
+}
+
+int mapf_sample_masked_actions(mapf_handle *h, const int8_t *action_mask, int8_t *actions, uint64_t counter,
+                               void *stream) {
+    if (!action_mask) return fail(MAPF_ERR_INVALID_ARG, "null action_mask");
+    return sample_actions(h, action_mask, actions, counter, stream);
+}
+
+int mapf_sample_random_actions(mapf_handle *h, int8_t *actions, uint64_t counter, void *stream) {
+    return sample_actions(h, nullptr, actions, counter, stream);
+}
+
+int mapf_metrics_reduce(mapf_handle *h, double *out_device, void *stream) {
+    int rc = check_ready(h);
+    if (rc) return rc;
+    if (!out_device) return fail(MAPF_ERR_INVALID_ARG, "null argument");
+    DeviceGuard guard(h->cfg.device);
+    mapf::mapf_metrics_reduce_kernel<<<MAPF_METRIC_COUNT, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        h->st.env_metrics, h->cfg.num_envs, out_device);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    return MAPF_OK;
+}
+
+int mapf_poll_errors(mapf_handle *h, uint32_t *bits, void *stream) {
+    if (!h || !bits) return fail(MAPF_ERR_INVALID_ARG, "null argument");
+    DeviceGuard guard(h->cfg.device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    CUDA_TRY(cudaMemcpyAsync(bits, h->d_err, 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemsetAsync(h->d_err, 0, 4, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    if (h->hstream && s != h->hstream) {
+        // the *_host entry points run on the handle's own stream and are synchronous, nothing pending
+    }
+    return MAPF_OK;
+}
+
+int64_t mapf_launch_count(const mapf_handle *h) { return h ? h->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,935 @@
+// mapf_kernels.cuh -- sm_100a kernels of the batched MAPF environment transition.
+//
+// Reference semantics: src/environments/reference_model_multi_agent.py ("ENV:line").
+// Mapping: one env per G-lane sub-warp group (G = 4/8/16/32 >= num_agents), one agent per lane.
+//  * move resolution (ENV:502-526) is the reference's sequential agent-index order, executed as
+//    an N-iteration shuffle/ballot chain inside the group;
+//  * staggered observations (ENV:528-536) use the snapshot identity: agent i sees
+//    agent a at new[a] if a <= i else old[a]; a step with a lifelong goal reassignment shows
+//    everybody the final state instead (ENV:565-575);
+//  * the lock heuristic (ENV:389-438) runs on three per-agent shift registers and ballots;
+//  * lifelong goal resampling (ENV:284-304) picks the k-th candidate of a shared-memory
+//    bitmap (free & ~occupied & ~goals), k from Philox4x32-10 or from a replay hook;
+//  * the wait-for graph (no reference counterpart) is resolved by pointer jumping.
+// No tensor cores: there is no dense contraction on this path; the kernels are integer/byte
+// work bounded by HBM traffic and instruction issue.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/mapf_b200.h"
+
+namespace mapf {
+
+constexpr int PAD = MAPF_MAX_SENSOR_RANGE;  // obstacle padding around the map in map_rows
+constexpr uint32_t NOCELL = 0x7FFF7FFFu;    // packed (row, col) that never matches a real cell
+constexpr uint32_t LFAR = 0x40000000u;      // linear code of an absent agent (far from any window)
+
+struct KParams {
+    int B, N, R, C;
+    int steps_per_episode, lifelong, lock_enabled, dw, lw, nearby, min_nb, eps_floor;
+    int normalize, deterministic, per_env_maps, auto_reset;
+    int observe_only;  // reset kernel: rebuild the observation channels from the current state, write nothing else
+    long long env_id_base;
+    unsigned long long seed;
+    float den0, den1;  // ENV:152-155
+    // map tables (device).  Shared map: one copy; per-env maps: B copies, strides below.
+    const uint32_t *map_rows;   // [(R+2*PAD) * wpr] bit (c+PAD) of padded row (r+PAD) = obstacle/OOB
+    const uint32_t *free_bits;  // [fw] bit (r*C+c) = free cell
+    const int32_t *num_free;    // [1] or [B]
+    int wpr, map_words, fw;
+    // state
+    uint32_t *positions, *goals, *starts;  // int16 pairs viewed as u32: row | col << 16
+    uint8_t *agent_flags;
+    uint32_t *lock_gp, *lock_mv, *lock_fm;
+    int16_t *lock_dist;
+    int4 *env_words;  // [B, 4] int4 = 16 words
+    double *env_metrics;
+    // step / reset inputs
+    const int8_t *actions;
+    const uint32_t *goal_override;  // int16 pairs
+    const int32_t *goal_rank;
+    const uint8_t *reset_mask;
+    const uint32_t *starts_override, *goals_override;
+    // outputs
+    uint8_t *o_local_obs;
+    int8_t *o_action_mask;
+    float2 *o_goal_delta;
+    uint8_t *o_blocking_prev;
+    float *o_reward;
+    uint8_t *o_terminated, *o_truncated, *o_step_flags, *o_agent_step_flags;
+    int4 *o_info;  // [B, 4] int4 = MAPF_INFO_WORDS int32
+    uint32_t *err_bits;
+};
+
+// ------------------------------------------------------------------ Philox4x32-10
+struct Philox {
+    uint32_t k0, k1;
+    __device__ __forceinline__ Philox(unsigned long long seed, long long stream) {
+        unsigned long long k = seed ^ (0x9E3779B97F4A7C15ull * (unsigned long long)(stream + 1));
+        k0 = (uint32_t)k;
+        k1 = (uint32_t)(k >> 32);
+    }
+    __device__ __forceinline__ uint4 operator()(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) const {
+        uint32_t a0 = k0, a1 = k1;
+#pragma unroll
+        for (int r = 0; r < 10; ++r) {
+            uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+            uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+            uint32_t n0 = hi1 ^ c1 ^ a0, n1 = lo1, n2 = hi0 ^ c3 ^ a1, n3 = lo0;
+            c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+            a0 += 0x9E3779B9u; a1 += 0xBB67AE85u;
+        }
+        return make_uint4(c0, c1, c2, c3);
+    }
+};
+
+// ------------------------------------------------------------------ small helpers
+__device__ __forceinline__ int prow(uint32_t p) { return (int)(short)(p & 0xFFFFu); }
+__device__ __forceinline__ int pcol(uint32_t p) { return (int)(short)(p >> 16); }
+__device__ __forceinline__ uint32_t pack_rc(int r, int c) {
+    return ((uint32_t)r & 0xFFFFu) | ((uint32_t)c << 16);
+}
+// linear code with a 1024-wide row pitch: windows become 1-D range tests
+__device__ __forceinline__ uint32_t lin(uint32_t p) { return (uint32_t)(prow(p) * 1024 + pcol(p)); }
+
+template <int V> struct WinBits { using type = uint32_t; };
+template <> struct WinBits<7> { using type = unsigned long long; };
+
+// obstacle/OOB bit of cell (r, c), valid for -PAD <= r < R+PAD, -PAD <= c < C+PAD
+__device__ __forceinline__ bool map_blocked(const uint32_t *rows, int wpr, int r, int c) {
+    int bit = c + PAD;
+    return (rows[(r + PAD) * wpr + (bit >> 5)] >> (bit & 31)) & 1u;
+}
+
+// k-th (0-based) set bit of a bitmap in shared memory; -1 if k >= popcount
+__device__ __forceinline__ int select_kth(const uint32_t *bm, int words, int k) {
+    for (int w = 0; w < words; ++w) {
+        uint32_t x = bm[w];
+        int c = __popc(x);
+        if (k < c) return w * 32 + (int)__fns(x, 0, k + 1);
+        k -= c;
+    }
+    return -1;
+}
+
+// Shared memory carve-up (32-bit words).  Per CTA: [shared map rows][shared free bitmap],
+// then per group: arrays for the pair loop, scratch bitmap, (per-env map copy), and per warp
+// the staging buffers for the byte outputs.
+struct SmemLayout {
+    int map_rows_off, free_off;    // CTA-wide (shared map)
+    int grp_off, grp_words;        // per group block
+    int g_new, g_snap, g_goal, g_int, g_delta, g_scratch, g_map, g_free;  // offsets inside a group block
+    int stage_off, stage_words;    // per warp staging (obs + mask), 16-byte aligned
+    int total_words;
+};
+
+__host__ __device__ inline SmemLayout make_layout(int G, int V2, int N, int wpr, int R, int fw,
+                                                  int per_env_maps, int threads) {
+    SmemLayout L;
+    int map_words = (R + 2 * PAD) * wpr;
+    int o = 0;
+    L.map_rows_off = o; o += per_env_maps ? 0 : map_words;
+    L.free_off = o; o += per_env_maps ? 0 : fw;
+    o = (o + 3) & ~3;
+    int g = 0;
+    int GA = G;  // arrays padded to G entries (G is a multiple of 4)
+    L.g_new = g; g += GA;
+    L.g_snap = g; g += GA;
+    L.g_goal = g; g += GA;
+    L.g_int = g; g += GA;
+    L.g_delta = g; g += GA;
+    L.g_scratch = g; g += fw;
+    L.g_map = g; g += per_env_maps ? map_words : 0;
+    L.g_free = g; g += per_env_maps ? fw : 0;
+    g = (g + 3) & ~3;
+    L.grp_words = g;
+    L.grp_off = o; o += g * (threads / G);
+    int envs_per_warp = 32 / G;
+    int obs_bytes = envs_per_warp * N * V2 + 32;   // +32: alignment slack (16 head + 16 tail)
+    int mask_bytes = envs_per_warp * N * 5 + 32;
+    int sw = ((obs_bytes + 15) / 16) * 4 + ((mask_bytes + 15) / 16) * 4;
+    L.stage_words = sw;
+    L.stage_off = o; o += sw * (threads / 32);
+    L.total_words = o;
+    (void)N;
+    return L;
+}
+
+// Copy `nbytes` staged bytes to global memory with 16-byte stores where possible.  The staged
+// bytes start at smem + (dst & 15) so that source and destination share their 16-byte phase.
+__device__ __forceinline__ void warp_copy_out(uint8_t *dst, const uint8_t *stage, int nbytes, int lane) {
+    uintptr_t d = (uintptr_t)dst;
+    int phase = (int)(d & 15);
+    const uint8_t *src = stage + phase;  // src[i] <-> dst[i]
+    int head = phase ? 16 - phase : 0;
+    if (head > nbytes) head = nbytes;
+    if (lane < head) dst[lane] = src[lane];
+    int body = (nbytes - head) & ~15;
+    const uint4 *s4 = reinterpret_cast<const uint4 *>(src + head);
+    uint4 *d4 = reinterpret_cast<uint4 *>(dst + head);
+    for (int i = lane; i < (body >> 4); i += 32) d4[i] = s4[i];
+    int tail = nbytes - head - body;
+    if (lane < tail) dst[head + body + lane] = src[head + body + lane];
+}
+
+// ------------------------------------------------------------------ the pair loop
+// Per lane (= agent i of one env) scan all agents a of the env from shared memory and build
+//   * the egocentric window (ENV:707-747) and the action mask (ENV:749-773),
+//   * (FULL) lock neighbours (ENV:389-398), intent blocking (ENV:609-623), co-location count
+//     (ENV:659-666) and the wait-for pointer.
+template <int G, int SR, bool FULL>
+struct PairOut {
+    typename WinBits<2 * SR + 1>::type occ, xgoal;
+    uint32_t nbmask;
+    int nbcount, red, colocated, wf_next;
+    bool intent_hit;
+};
+
+template <int G, int SR, bool FULL>
+__device__ __forceinline__ void pair_loop(const uint32_t *s_new, const uint32_t *s_snap,
+                                          const uint32_t *s_goal, const uint32_t *s_int,
+                                          const uint32_t *s_delta, int gl, uint32_t my_new_lin,
+                                          uint32_t my_new_packed, uint32_t my_intended, bool failed,
+                                          int nearby, PairOut<G, SR, FULL> &o) {
+    constexpr int V = 2 * SR + 1;
+    using WB = typename WinBits<V>::type;
+    o.occ = 0; o.xgoal = 0; o.nbmask = 0; o.nbcount = 0; o.red = 0; o.colocated = 0;
+    o.wf_next = -1; o.intent_hit = false;
+    const uint32_t origin = my_new_lin - (uint32_t)(SR * 1024 + SR);
+    const uint32_t nb_origin = my_new_lin - (uint32_t)(nearby * 1024 + nearby);
+    const uint32_t nb_side = 2u * (uint32_t)nearby;
+#pragma unroll
+    for (int a4 = 0; a4 < G; a4 += 4) {
+        const uint4 vn = *reinterpret_cast<const uint4 *>(s_new + a4);
+        const uint4 vs = *reinterpret_cast<const uint4 *>(s_snap + a4);
+        const uint4 vg = *reinterpret_cast<const uint4 *>(s_goal + a4);
+        uint4 vi = make_uint4(0, 0, 0, 0), vd = make_uint4(0, 0, 0, 0);
+        if (FULL) {
+            vi = *reinterpret_cast<const uint4 *>(s_int + a4);
+            vd = *reinterpret_cast<const uint4 *>(s_delta + a4);
+        }
+        const uint32_t an[4] = {vn.x, vn.y, vn.z, vn.w};
+        const uint32_t as[4] = {vs.x, vs.y, vs.z, vs.w};
+        const uint32_t ag[4] = {vg.x, vg.y, vg.z, vg.w};
+        const uint32_t ai[4] = {vi.x, vi.y, vi.z, vi.w};
+        const uint32_t ad[4] = {vd.x, vd.y, vd.z, vd.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int a = a4 + k;
+            const bool other = (a != gl);
+            // snapshot position of agent a as seen by me (F3): new if a <= me, else old/snap
+            const uint32_t ps = (a <= gl) ? an[k] : as[k];
+            uint32_t d = ps - origin;
+            uint32_t t1 = d & 1023u, t2 = d >> 10;
+            if (other && t1 < (uint32_t)V && t2 < (uint32_t)V) o.occ |= (WB)1 << (t2 * V + t1);
+            d = ag[k] - origin;
+            t1 = d & 1023u; t2 = d >> 10;
+            if (other && t1 < (uint32_t)V && t2 < (uint32_t)V) o.xgoal |= (WB)1 << (t2 * V + t1);
+            if (FULL) {
+                d = an[k] - nb_origin;
+                t1 = d & 1023u; t2 = d >> 10;
+                if (other && t1 <= nb_side && t2 <= nb_side) {
+                    int m = abs((int)t1 - nearby) + abs((int)t2 - nearby);
+                    if (m <= nearby) {
+                        if (m > 0) { o.nbmask |= 1u << a; o.nbcount++; o.red += (int)ad[k]; }
+                        else o.colocated++;
+                    }
+                }
+                if (other && ai[k] == my_new_lin) o.intent_hit = true;
+                if (other && failed && an[k] == my_intended) o.wf_next = a;
+            }
+        }
+    }
+    (void)my_new_packed;
+}
+
+// Window value bytes (ENV:730-745 priority) + action mask (ENV:761-771) into the staging area.
+template <int SR>
+__device__ __forceinline__ uint32_t emit_window(const uint32_t *rows, int wpr, int r, int c,
+                                                typename WinBits<2 * SR + 1>::type occ,
+                                                typename WinBits<2 * SR + 1>::type xgoal,
+                                                uint32_t goal_lin, uint32_t my_lin,
+                                                uint8_t *stage_obs /* may be null */) {
+    constexpr int V = 2 * SR + 1;
+    using WB = typename WinBits<V>::type;
+    WB obst = 0;
+    const int sb = c - SR + PAD, word = sb >> 5, sh = sb & 31;
+#pragma unroll
+    for (int wr = 0; wr < V; ++wr) {
+        const uint32_t *rw = rows + (r - SR + wr + PAD) * wpr + word;
+        uint32_t bits = __funnelshift_r(rw[0], rw[1], sh) & ((1u << V) - 1u);
+        obst |= (WB)bits << (wr * V);
+    }
+    WB own = 0;
+    {
+        uint32_t d = goal_lin - (my_lin - (uint32_t)(SR * 1024 + SR));
+        uint32_t t1 = d & 1023u, t2 = d >> 10;
+        if (t1 < (uint32_t)V && t2 < (uint32_t)V) own = (WB)1 << (t2 * V + t1);
+    }
+    const WB agent = occ & ~obst;
+    const WB blocked = obst | occ;
+    const WB g3 = own & ~blocked;
+    const WB g4 = xgoal & ~blocked & ~own;
+    if (stage_obs) {
+#pragma unroll
+        for (int k = 0; k < V * V; ++k) {
+            uint32_t v = (uint32_t)((obst >> k) & 1) + 2u * (uint32_t)((agent >> k) & 1) +
+                         3u * (uint32_t)((g3 >> k) & 1) + 4u * (uint32_t)((g4 >> k) & 1);
+            stage_obs[k] = (uint8_t)v;
+        }
+    }
+    constexpr int ctr = SR * V + SR;
+    uint32_t m = 1u;
+    m |= (uint32_t)(((~blocked) >> (ctr - V)) & 1) << 1;  // up
+    m |= (uint32_t)(((~blocked) >> (ctr + 1)) & 1) << 2;  // right
+    m |= (uint32_t)(((~blocked) >> (ctr + V)) & 1) << 3;  // down
+    m |= (uint32_t)(((~blocked) >> (ctr - 1)) & 1) << 4;  // left
+    return m;
+}
+
+// ENV:330-335
+__device__ __forceinline__ float2 goal_delta(uint32_t goal, uint32_t pos, int normalize, float den0,
+                                             float den1) {
+    float d0 = (float)(prow(goal) - prow(pos)), d1 = (float)(pcol(goal) - pcol(pos));
+    if (normalize) { d0 = __fdiv_rn(d0, den0); d1 = __fdiv_rn(d1, den1); }
+    return make_float2(d0, d1);
+}
+
+// Draw 2N distinct free cells (ENV:267-282) by symmetric rejection: every slot draws uniformly;
+// a slot that equals a lower-numbered slot redraws.  The rule is invariant under relabelling of
+// cells, hence the result is uniform over ordered tuples of distinct cells.
+// Slot order: starts 0..N-1, goals N..2N-1.  Returns packed start / goal for this lane.
+template <int G>
+__device__ __forceinline__ void draw_layout(const Philox &ph, uint32_t &rng_counter, int F,
+                                            const uint32_t *free_bm, int fw, int C, int N, int gl,
+                                            unsigned gbase, unsigned gmask, bool need,
+                                            uint32_t &start, uint32_t &goal) {
+    const unsigned full = 0xFFFFFFFFu;
+    int cs = -1, cg = -1;       // drawn cell ids
+    bool rs = need, rg = need;  // must (re)draw
+    uint32_t rounds = 0;        // rounds consumed by THIS env (group-uniform => shard invariant)
+    for (;;) {
+        const unsigned needmask = __ballot_sync(full, rs || rg);
+        if (!needmask) break;
+        const bool grp_need = (needmask & gmask) != 0;
+        if (rs || rg) {
+            uint4 x = ph(rng_counter + rounds, (uint32_t)gl, 0x52455345u /* "RESE" */, 0);
+            if (rs) cs = select_kth(free_bm, fw, (int)__umulhi(x.x, (uint32_t)F));
+            if (rg) cg = select_kth(free_bm, fw, (int)__umulhi(x.y, (uint32_t)F));
+        }
+        rs = false; rg = false;
+#pragma unroll
+        for (int a = 0; a < G; ++a) {
+            int os = __shfl_sync(full, cs, gbase + a);
+            int og = __shfl_sync(full, cg, gbase + a);
+            if (need && a < N) {
+                if (a < gl && os == cs) rs = true;   // lower start slot
+                if (os == cg) rg = true;             // every start slot is lower than a goal slot
+                if (a < gl && og == cg) rg = true;   // lower goal slot
+            }
+        }
+        if (grp_need) rounds++;
+    }
+    rng_counter += rounds;
+    if (need) {
+        start = pack_rc(cs / C, cs % C);
+        goal = pack_rc(cg / C, cg % C);
+    }
+}
+
+// ============================================================================ step kernel
+template <int G, int SR>
+__global__ void __launch_bounds__(256) mapf_step_kernel(const KParams p) {
+    constexpr int V = 2 * SR + 1, V2 = V * V;
+    using WB = typename WinBits<V>::type;
+    extern __shared__ __align__(16) uint32_t smem[];
+    const unsigned full = 0xFFFFFFFFu;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int gl = tid % G, grp = tid / G;
+    const int groups = blockDim.x / G;
+    const int env = blockIdx.x * groups + grp;
+    const unsigned gbase = (unsigned)(lane / G) * G;
+    const unsigned gmask = (G == 32) ? full : (((1u << G) - 1u) << gbase);
+    const int N = p.N;
+    const bool env_ok = env < p.B;
+    const bool act = env_ok && gl < N;
+
+    const SmemLayout L = make_layout(G, V2, N, p.wpr, p.R, p.fw, p.per_env_maps, blockDim.x);
+    uint32_t *gsm = smem + L.grp_off + grp * L.grp_words;
+    uint32_t *s_new = gsm + L.g_new, *s_snap = gsm + L.g_snap, *s_goal = gsm + L.g_goal;
+    uint32_t *s_int = gsm + L.g_int, *s_delta = gsm + L.g_delta, *s_scratch = gsm + L.g_scratch;
+    const uint32_t *rows, *freebm;
+    if (p.per_env_maps) {
+        uint32_t *mr = gsm + L.g_map, *fb = gsm + L.g_free;
+        if (env_ok) {
+            const uint32_t *src = p.map_rows + (size_t)env * p.map_words;
+            for (int i = gl; i < p.map_words; i += G) mr[i] = src[i];
+            const uint32_t *fsrc = p.free_bits + (size_t)env * p.fw;
+            for (int i = gl; i < p.fw; i += G) fb[i] = fsrc[i];
+        }
+        rows = mr; freebm = fb;
+        __syncwarp();
+    } else {
+        uint32_t *mr = smem + L.map_rows_off, *fb = smem + L.free_off;
+        for (int i = tid; i < p.map_words; i += blockDim.x) mr[i] = p.map_rows[i];
+        for (int i = tid; i < p.fw; i += blockDim.x) fb[i] = p.free_bits[i];
+        rows = mr; freebm = fb;
+        __syncthreads();
+    }
+    uint8_t *stage = reinterpret_cast<uint8_t *>(smem + L.stage_off + warp * L.stage_words);
+    const int envs_per_warp = 32 / G;
+    const int obs_stage_bytes = ((envs_per_warp * N * V2 + 32 + 15) / 16) * 16;
+    uint8_t *stage_obs = stage;
+    uint8_t *stage_mask = stage + obs_stage_bytes;
+
+    // ---------------------------------------------------------------- load
+    const size_t ai = (size_t)(env_ok ? env : 0) * N + (gl < N ? gl : 0);
+    uint32_t pos = act ? p.positions[ai] : NOCELL;
+    uint32_t goal = act ? p.goals[ai] : NOCELL - 1;
+    uint32_t aflags = act ? p.agent_flags[ai] : 0u;
+    int action = (act && p.actions) ? (int)p.actions[ai] : 0;
+    uint32_t errs = 0;
+    if (action < 0 || action > 4) { errs |= MAPF_DEV_ERR_INVALID_ACTION; action = 0; }
+    int4 w0 = make_int4(0, 0, 0, 0), w1 = w0, w2 = w0, w3 = w0;
+    if (env_ok) {
+        const int4 *ew = p.env_words + (size_t)env * 4;
+        w0 = ew[0]; w1 = ew[1]; w2 = ew[2]; w3 = ew[3];
+    }
+    int step_count = w0.x + 1;  // ENV:475
+    int lock_count = w0.y, lock_prev = w0.z, goals_total = w0.w;
+    int blocking_total = w1.x, dl_events = w1.y, ll_events = w1.z, dl_steps = w1.w;
+    int ll_steps = w2.x;
+    uint32_t rng_counter = (uint32_t)w2.y;
+    int ep_return_x2 = w2.z, wfg_steps = w2.w;
+    int episodes = w3.x;
+
+    // ---------------------------------------------------------------- move resolution, ENV:502-526
+    const int r0 = prow(pos), c0 = pcol(pos);
+    const int nr = r0 + (action == 3) - (action == 1);
+    const int nc = c0 + (action == 2) - (action == 4);
+    const uint32_t intended = pack_rc(nr, nc);  // ENV:514-515 (kept even when invalid)
+    bool wants = act && action != 0 && !map_blocked(rows, p.wpr, nr, nc);
+    const uint32_t target = wants ? intended : NOCELL;
+    uint32_t cur = pos;
+#pragma unroll
+    for (int i = 0; i < G; ++i) {
+        if (i >= N) break;
+        const uint32_t t = __shfl_sync(full, target, gbase + i);
+        const bool hit = (gl != i) && (cur == t);  // occupied by somebody else at agent i's turn
+        const unsigned blocked = __ballot_sync(full, hit) & gmask;
+        if (gl == i && t != NOCELL && !blocked) cur = t;
+    }
+    const uint32_t newpos = cur;
+    const bool moved = act && (newpos != pos);
+    const bool failed = act && action != 0 && !moved;  // ENV:583
+
+    // ---------------------------------------------------------------- goals, ENV:538-563
+    bool on_goal = act && newpos == goal;
+    int reward_x2 = 0;
+    bool gstep = false;
+    uint32_t goal_new = goal;
+    unsigned arrivals = 0;
+    if (!p.lifelong) {
+        if (on_goal && !(aflags & MAPF_AF_REACHED)) {
+            aflags |= MAPF_AF_REACHED | MAPF_AF_COMPLETED_ONCE;
+            reward_x2 += 1; gstep = true;
+        }
+    } else {
+        if (on_goal) {
+            reward_x2 += 1; gstep = true;
+            aflags |= MAPF_AF_COMPLETED_ONCE;
+            aflags &= ~MAPF_AF_REACHED;
+        }
+        arrivals = __ballot_sync(full, on_goal) & gmask;
+        unsigned pending = arrivals;
+        const Philox ph(p.seed, p.env_id_base + env);
+        while (__any_sync(full, pending != 0)) {  // ENV:284-304, in agent-index order
+            const int i = pending ? (__ffs(pending) - 1 - (int)gbase) : -1;
+            if (pending) for (int w = gl; w < p.fw; w += G) s_scratch[w] = freebm[w];
+            __syncwarp();
+            if (pending && act) {
+                const uint32_t oc = (gl <= i) ? newpos : pos;  // occupancy snapshot of agent i
+                int cell = prow(oc) * p.C + pcol(oc);
+                atomicAnd(&s_scratch[cell >> 5], ~(1u << (cell & 31)));
+                cell = prow(goal_new) * p.C + pcol(goal_new);
+                atomicAnd(&s_scratch[cell >> 5], ~(1u << (cell & 31)));
+            }
+            __syncwarp();
+            if (pending) {
+                uint32_t ng = NOCELL;
+                const size_t oi = (size_t)env * N + i;
+                if (p.goal_override) {
+                    uint32_t ov = p.goal_override[oi];
+                    if (prow(ov) >= 0) ng = ov;
+                }
+                if (ng == NOCELL) {
+                    int n = 0;
+                    for (int w = 0; w < p.fw; ++w) n += __popc(s_scratch[w]);
+                    int k = -1;
+                    if (p.goal_rank) k = p.goal_rank[oi];
+                    if (k < 0 && n > 0) {
+                        uint4 x = ph(rng_counter, (uint32_t)i, 0x474F414Cu /* "GOAL" */, 0);
+                        k = (int)__umulhi(x.x, (uint32_t)n);
+                        rng_counter++;
+                    }
+                    int cell = (n > 0 && k < n) ? select_kth(s_scratch, p.fw, k) : -1;
+                    if (cell >= 0) ng = pack_rc(cell / p.C, cell % p.C);
+                    else errs |= MAPF_DEV_ERR_NO_GOAL_CELL;
+                }
+                if (gl == i && ng != NOCELL) goal_new = ng;
+            }
+            pending &= pending - 1;
+            __syncwarp();
+        }
+        goals_total += __popc(arrivals);
+    }
+    if (!p.lifelong) goals_total += __popc(__ballot_sync(full, gstep) & gmask);
+    const bool reassigned = arrivals != 0;
+    // ENV:555: an arrived lifelong agent is no longer "on goal"; others keep their test
+    bool cur_on_goal = act && newpos == goal_new;
+    const bool reached_goal_scratch = p.lifelong ? false : cur_on_goal;
+
+    // ---------------------------------------------------------------- lock bookkeeping, ENV:581-594
+    uint32_t gpr = 0, mvr = 0, fmr = 0;
+    int dist_now = abs(prow(goal_new) - prow(newpos)) + abs(pcol(goal_new) - pcol(newpos));
+    int delta = 0;
+    const int count_after = lock_count + 1;
+    if (p.lock_enabled) {
+        if (act) { gpr = p.lock_gp[ai]; mvr = p.lock_mv[ai]; fmr = p.lock_fm[ai]; }
+        const bool prev_on_goal = p.lifelong ? false : (pos == goal_new);
+        const bool gp = p.lifelong ? gstep : (!prev_on_goal && cur_on_goal);
+        gpr = (gpr << 1) | (gp ? 1u : 0u);
+        mvr = (mvr << 1) | (moved ? 1u : 0u);
+        fmr = (fmr << 1) | (failed ? 1u : 0u);
+        const int LW = p.lw;
+        const int slot_new = lock_count % LW;
+        if (act) {
+            int16_t *ring = p.lock_dist + ((size_t)env * LW) * N + gl;
+            if (count_after >= LW && LW > 1) {
+                const int slot_old = (lock_count + 1) % LW;  // oldest row of the window, ENV:432
+                delta = (int)ring[(size_t)slot_old * N] - dist_now;
+            }
+            ring[(size_t)slot_new * N] = (int16_t)dist_now;
+        }
+    }
+
+    // ---------------------------------------------------------------- pair loop
+    const uint32_t my_lin = act ? lin(newpos) : LFAR;
+    s_new[gl] = my_lin;
+    s_snap[gl] = act ? lin(reassigned ? newpos : pos) : LFAR;
+    const uint32_t goal_for_obs = reassigned ? goal_new : goal;  // ENV:565-575 vs in-loop obs
+    s_goal[gl] = act ? lin(goal_for_obs) : LFAR;
+    // intent of agents that have not (sticky-)reached, ENV:619-621
+    s_int[gl] = (act && !(aflags & MAPF_AF_REACHED)) ? lin(intended) + 0u : LFAR + 1u;
+    s_delta[gl] = (uint32_t)delta;
+    __syncwarp();
+    PairOut<G, SR, true> po;
+    pair_loop<G, SR, true>(s_new, s_snap, s_goal, s_int, s_delta, gl, my_lin, newpos,
+                           failed ? lin(intended) : LFAR + 2u, failed, p.nearby, po);
+
+    // ---------------------------------------------------------------- observation channels
+    const int my_env_in_warp = lane / G;
+    uint8_t *my_stage_obs = nullptr;
+    const size_t warp_env0 = (size_t)blockIdx.x * groups + (size_t)(warp * envs_per_warp);
+    if (p.o_local_obs) {
+        uint8_t *dst0 = p.o_local_obs + warp_env0 * N * V2;
+        my_stage_obs = stage_obs + ((uintptr_t)dst0 & 15) + (size_t)(my_env_in_warp * N + gl) * V2;
+    }
+    uint32_t amask = 1u;
+    if (act)
+        amask = emit_window<SR>(rows, p.wpr, prow(newpos), pcol(newpos), po.occ, po.xgoal,
+                                lin(goal_for_obs), my_lin, my_stage_obs);
+    float2 gd = goal_delta(goal_for_obs, newpos, p.normalize, p.den0, p.den1);
+    const uint32_t bp_prev_out = (aflags >> 2) & 1u;  // value of the previous step, ENV:322 (F5)
+
+    // ---------------------------------------------------------------- lock detection, ENV:400-438,595-606
+    bool dl_step = false, ll_step = false, dl_event = false, ll_event = false;
+    if (p.lock_enabled) {
+        const uint32_t mdw = p.dw >= 32 ? full : ((1u << p.dw) - 1u);
+        const uint32_t mlw = p.lw >= 32 ? full : ((1u << p.lw) - 1u);
+        const unsigned Gd = (__ballot_sync(full, (gpr & mdw) != 0) & gmask) >> gbase;
+        const unsigned Md = (__ballot_sync(full, (mvr & mdw) != 0) & gmask) >> gbase;
+        const unsigned Fd = (__ballot_sync(full, (fmr & mdw) != 0) & gmask) >> gbase;
+        const unsigned Gl = (__ballot_sync(full, (gpr & mlw) != 0) & gmask) >> gbase;
+        const unsigned Ml = (__ballot_sync(full, (mvr & mlw) != 0) & gmask) >> gbase;
+        const bool focal = act && !cur_on_goal && po.nbcount >= p.min_nb;  // ENV:391-396
+        const unsigned P = po.nbmask | (1u << gl);
+        const bool dl_f = focal && !(P & Gd) && !(P & Md) && (P & Fd);
+        const bool ll_f = focal && !(P & Gl) && (P & Ml) && (po.red + delta <= p.eps_floor);
+        const bool dl_any = (__ballot_sync(full, dl_f) & gmask) != 0;
+        const bool ll_any = (__ballot_sync(full, ll_f) & gmask) != 0;
+        dl_step = count_after >= p.dw && dl_any;
+        ll_step = !dl_step && count_after >= p.lw && ll_any;
+        dl_event = dl_step && !(lock_prev & 1);
+        ll_event = ll_step && !(lock_prev & 2);
+        lock_prev = (dl_step ? 1 : 0) | (ll_step ? 2 : 0);
+        dl_steps += dl_step; ll_steps += ll_step; dl_events += dl_event; ll_events += ll_event;
+        lock_count = count_after;
+    }
+
+    // ---------------------------------------------------------------- blocking, ENV:608-625
+    const bool blocking = act && (aflags & MAPF_AF_REACHED) && !moved && po.intent_hit;
+    aflags = (aflags & ~MAPF_AF_BLOCKING_PREV) | (blocking ? MAPF_AF_BLOCKING_PREV : 0u);
+    blocking_total += __popc(__ballot_sync(full, blocking) & gmask);
+
+    // ---------------------------------------------------------------- wait-for graph (pointer jumping)
+    bool wf_cycle = false;
+    {
+        int ptr = po.wf_next;  // -1: no outgoing edge
+        unsigned reach = ptr >= 0 ? (1u << ptr) : 0u;
+#pragma unroll
+        for (int s = 1; s < G; s <<= 1) {
+            const int src = gbase + (ptr >= 0 ? ptr : gl);
+            const unsigned r2 = __shfl_sync(full, reach, src);
+            const int p2 = __shfl_sync(full, ptr, src);
+            if (ptr >= 0) { reach |= r2; ptr = p2; }
+        }
+        wf_cycle = act && ((reach >> gl) & 1u);
+    }
+    const bool wf_any = (__ballot_sync(full, wf_cycle) & gmask) != 0;
+    wfg_steps += wf_any;
+
+    // ---------------------------------------------------------------- rewards & termination, ENV:658-690
+    reward_x2 -= 2 * po.colocated;
+    const int n_on = __popc(__ballot_sync(full, act && reached_goal_scratch) & gmask);
+    bool terminated = false, truncated = false;
+    if (!p.lifelong && n_on == N) {
+        reward_x2 += 2; terminated = true;
+    } else if (step_count >= p.steps_per_episode) {
+        if (!p.lifelong && !reached_goal_scratch) reward_x2 -= 2;
+        terminated = true; truncated = true;  // F6
+    }
+    if (!act) reward_x2 = 0;
+    int rsum = reward_x2;
+#pragma unroll
+    for (int s = G / 2; s > 0; s >>= 1) rsum += __shfl_xor_sync(full, rsum, s);
+    ep_return_x2 += rsum;
+    const bool done = env_ok && (terminated || truncated);
+
+    // ---------------------------------------------------------------- per-step outputs
+    if (act) {
+        if (p.o_goal_delta) p.o_goal_delta[ai] = gd;
+        if (p.o_blocking_prev) p.o_blocking_prev[ai] = (uint8_t)bp_prev_out;
+        if (p.o_reward) p.o_reward[ai] = 0.5f * (float)reward_x2;
+        if (p.o_agent_step_flags)
+            p.o_agent_step_flags[ai] = (uint8_t)((moved ? MAPF_ASF_MOVED : 0) | (failed ? MAPF_ASF_FAILED_MOVE : 0) |
+                                                 (gstep ? MAPF_ASF_GOAL_REACHED : 0) | (blocking ? MAPF_ASF_BLOCKING : 0) |
+                                                 (wf_cycle ? MAPF_ASF_WFG_CYCLE : 0) | (cur_on_goal ? MAPF_ASF_ON_GOAL : 0));
+    }
+    const unsigned comp = __ballot_sync(full, act && (aflags & MAPF_AF_COMPLETED_ONCE)) & gmask;
+    const unsigned reach = __ballot_sync(full, act && (aflags & MAPF_AF_REACHED)) & gmask;
+    const int goals_step = __popc(__ballot_sync(full, gstep) & gmask);
+    const int blocking_step = __popc(__ballot_sync(full, blocking) & gmask);
+    if (env_ok && gl == 0) {
+        if (p.o_info) {  // integer sources of info["__all__"], ENV:639-656
+            int4 *io = p.o_info + (size_t)env * 4;
+            io[0] = make_int4(goals_step, p.lifelong ? goals_total : __popc(reach), blocking_step, blocking_total);
+            io[1] = make_int4(dl_step, ll_step, dl_event, ll_event);
+            io[2] = make_int4(dl_events, ll_events, dl_steps, ll_steps);
+            io[3] = make_int4(__popc(comp), step_count, __popc(reach), wfg_steps);
+        }
+        if (p.o_terminated) p.o_terminated[env] = terminated;
+        if (p.o_truncated) p.o_truncated[env] = truncated;
+        if (p.o_step_flags)
+            p.o_step_flags[env] = (uint8_t)((terminated ? MAPF_SF_TERMINATED : 0) | (truncated ? MAPF_SF_TRUNCATED : 0) |
+                                            (dl_step ? MAPF_SF_DEADLOCK_STEP : 0) | (ll_step ? MAPF_SF_LIVELOCK_STEP : 0) |
+                                            (dl_event ? MAPF_SF_DEADLOCK_EVENT : 0) | (ll_event ? MAPF_SF_LIVELOCK_EVENT : 0) |
+                                            (reassigned ? MAPF_SF_GOAL_REASSIGNED : 0) | (wf_any ? MAPF_SF_WFG_CYCLE : 0));
+    }
+
+    // ---------------------------------------------------------------- episode end: metrics, auto-reset
+    uint32_t out_pos = newpos, out_goal = goal_new, out_start = 0;
+    bool write_start = false;
+    // episode-end metric sums, src/trainers/callbacks.py:152,173,335-345
+    {
+        if (done && gl == 0) {
+            double *m = p.env_metrics + (size_t)env * MAPF_METRIC_COUNT;
+            const double gt = p.lifelong ? (double)goals_total : (double)__popc(reach);  // ENV:630-633
+            m[MAPF_M_EPISODES] += 1.0;
+            m[MAPF_M_RETURN_SUM] += 0.5 * (double)ep_return_x2;
+            m[MAPF_M_LENGTH_SUM] += (double)step_count;
+            m[MAPF_M_SUCCESS_SUM] += (terminated && !truncated) ? 1.0 : 0.0;
+            m[MAPF_M_GOALS_REACHED_SUM] += gt;
+            m[MAPF_M_BLOCKING_COUNT_SUM] += (double)blocking_total;
+            m[MAPF_M_DEADLOCK_COUNT_SUM] += (double)dl_events;
+            m[MAPF_M_LIVELOCK_COUNT_SUM] += (double)ll_events;
+            m[MAPF_M_DEADLOCK_STEPS_SUM] += (double)dl_steps;
+            m[MAPF_M_LIVELOCK_STEPS_SUM] += (double)ll_steps;
+            m[MAPF_M_THROUGHPUT_SUM] += gt / (double)(step_count > 1 ? step_count : 1);  // ENV:655
+            m[MAPF_M_COMPLETION_RATIO_SUM] += (double)__popc(comp) / (double)N;           // ENV:638
+            m[MAPF_M_WFG_CYCLE_STEPS_SUM] += (double)wfg_steps;
+        }
+    }
+    if (done) episodes += 1;
+
+    const bool do_reset = done && p.auto_reset;
+    __syncwarp();
+    if (__any_sync(full, do_reset)) {  // ENV:440-472 inside the launch (benchmark loop semantics)
+        uint32_t st = 0, gg = 0;
+        bool sample = do_reset && !p.deterministic;
+        const int F = p.num_free[p.per_env_maps ? (env_ok ? env : 0) : 0];
+        if (sample && F < 2 * N) { errs |= MAPF_DEV_ERR_TOO_FEW_CELLS; sample = false; }
+        const Philox ph(p.seed, p.env_id_base + env);
+        draw_layout<G>(ph, rng_counter, F, freebm, p.fw, p.C, N, gl, gbase, gmask, sample && act, st, gg);
+        if (do_reset) {
+            if (p.deterministic) { st = act ? p.starts[ai] : NOCELL; gg = goal_new; }  // F7
+            else if (sample) { write_start = true; out_start = st; }
+            else { st = newpos; gg = goal_new; }
+            out_pos = st; out_goal = gg;
+            aflags = 0; gpr = mvr = fmr = 0;
+            step_count = 0; lock_count = 0; lock_prev = 0; goals_total = 0; blocking_total = 0;
+            dl_events = ll_events = dl_steps = ll_steps = 0; ep_return_x2 = 0; wfg_steps = 0;
+            // first observation of the next episode (final-state, no staggering at reset)
+            const uint32_t l = act ? lin(st) : LFAR;
+            s_new[gl] = l; s_snap[gl] = l; s_goal[gl] = act ? lin(gg) : LFAR;
+        }
+        __syncwarp();
+        if (do_reset) {
+            PairOut<G, SR, false> pr;
+            pair_loop<G, SR, false>(s_new, s_snap, s_goal, s_int, s_delta, gl, act ? lin(st) : LFAR, st,
+                                    0u, false, p.nearby, pr);
+            if (act) {
+                amask = emit_window<SR>(rows, p.wpr, prow(st), pcol(st), pr.occ, pr.xgoal, lin(gg),
+                                        lin(st), my_stage_obs);
+                if (p.o_goal_delta) p.o_goal_delta[ai] = goal_delta(gg, st, p.normalize, p.den0, p.den1);
+                if (p.o_blocking_prev) p.o_blocking_prev[ai] = 0;
+            }
+        }
+    }
+
+    // ---------------------------------------------------------------- byte outputs through staging
+    if (p.o_action_mask) {
+        uint8_t *dst0 = reinterpret_cast<uint8_t *>(p.o_action_mask) + warp_env0 * N * 5;
+        uint8_t *ms = stage_mask + ((uintptr_t)dst0 & 15) + (size_t)(my_env_in_warp * N + gl) * 5;
+        if (act) {
+#pragma unroll
+            for (int k = 0; k < 5; ++k) ms[k] = (uint8_t)((amask >> k) & 1u);
+        }
+    }
+    __syncwarp();
+    {
+        long long envs_left = (long long)p.B - (long long)warp_env0;
+        int nenv = envs_left < 0 ? 0 : (envs_left < envs_per_warp ? (int)envs_left : envs_per_warp);
+        if (nenv > 0) {
+            if (p.o_local_obs)
+                warp_copy_out(p.o_local_obs + warp_env0 * N * V2, stage_obs, nenv * N * V2, lane);
+            if (p.o_action_mask)
+                warp_copy_out(reinterpret_cast<uint8_t *>(p.o_action_mask) + warp_env0 * N * 5,
+                              stage_mask, nenv * N * 5, lane);
+        }
+    }
+
+    // ---------------------------------------------------------------- state write-back
+    if (act) {
+        p.positions[ai] = out_pos;
+        if (out_goal != goal) p.goals[ai] = out_goal;
+        if (write_start) p.starts[ai] = out_start;
+        p.agent_flags[ai] = (uint8_t)aflags;
+        if (p.lock_enabled) { p.lock_gp[ai] = gpr; p.lock_mv[ai] = mvr; p.lock_fm[ai] = fmr; }
+    }
+    if (env_ok && gl == 0) {
+        int4 *ew = p.env_words + (size_t)env * 4;
+        ew[0] = make_int4(step_count, lock_count, lock_prev, goals_total);
+        ew[1] = make_int4(blocking_total, dl_events, ll_events, dl_steps);
+        ew[2] = make_int4(ll_steps, (int)rng_counter, ep_return_x2, wfg_steps);
+        ew[3] = make_int4(episodes, w3.y, w3.z, w3.w);
+    }
+    errs = __reduce_or_sync(full, errs);
+    if (errs && lane == 0) atomicOr(p.err_bits, errs);
+}
+
+// ============================================================================ reset kernel
+template <int G, int SR>
+__global__ void __launch_bounds__(256) mapf_reset_kernel(const KParams p) {
+    constexpr int V = 2 * SR + 1, V2 = V * V;
+    extern __shared__ __align__(16) uint32_t smem[];
+    const unsigned full = 0xFFFFFFFFu;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int gl = tid % G, grp = tid / G;
+    const int groups = blockDim.x / G;
+    const int env = blockIdx.x * groups + grp;
+    const unsigned gbase = (unsigned)(lane / G) * G;
+    const unsigned gmask = (G == 32) ? full : (((1u << G) - 1u) << gbase);
+    const int N = p.N;
+    const bool env_ok = env < p.B;
+    const bool sel = env_ok && (!p.reset_mask || p.reset_mask[env] != 0);
+    const bool act = sel && gl < N;
+
+    const SmemLayout L = make_layout(G, V2, N, p.wpr, p.R, p.fw, p.per_env_maps, blockDim.x);
+    uint32_t *gsm = smem + L.grp_off + grp * L.grp_words;
+    uint32_t *s_new = gsm + L.g_new, *s_snap = gsm + L.g_snap, *s_goal = gsm + L.g_goal;
+    uint32_t *s_int = gsm + L.g_int, *s_delta = gsm + L.g_delta;
+    const uint32_t *rows, *freebm;
+    if (p.per_env_maps) {
+        uint32_t *mr = gsm + L.g_map, *fb = gsm + L.g_free;
+        if (env_ok) {
+            const uint32_t *src = p.map_rows + (size_t)env * p.map_words;
+            for (int i = gl; i < p.map_words; i += G) mr[i] = src[i];
+            const uint32_t *fsrc = p.free_bits + (size_t)env * p.fw;
+            for (int i = gl; i < p.fw; i += G) fb[i] = fsrc[i];
+        }
+        rows = mr; freebm = fb;
+        __syncwarp();
+    } else {
+        uint32_t *mr = smem + L.map_rows_off, *fb = smem + L.free_off;
+        for (int i = tid; i < p.map_words; i += blockDim.x) mr[i] = p.map_rows[i];
+        for (int i = tid; i < p.fw; i += blockDim.x) fb[i] = p.free_bits[i];
+        rows = mr; freebm = fb;
+        __syncthreads();
+    }
+    uint8_t *stage = reinterpret_cast<uint8_t *>(smem + L.stage_off + warp * L.stage_words);
+    const int envs_per_warp = 32 / G;
+    const int obs_stage_bytes = ((envs_per_warp * N * V2 + 32 + 15) / 16) * 16;
+    uint8_t *stage_obs = stage, *stage_mask = stage + obs_stage_bytes;
+
+    const size_t ai = (size_t)(env_ok ? env : 0) * N + (gl < N ? gl : 0);
+    int4 w2 = make_int4(0, 0, 0, 0), w3 = w2;
+    if (env_ok) { w2 = p.env_words[(size_t)env * 4 + 2]; w3 = p.env_words[(size_t)env * 4 + 3]; }
+    uint32_t rng_counter = (uint32_t)w2.y;
+    uint32_t errs = 0;
+
+    // layout: overrides > deterministic table (ENV:452-455) > Philox draw (ENV:267-282)
+    uint32_t st = NOCELL, gg = NOCELL - 1;
+    const bool have_override = p.starts_override && p.goals_override;
+    bool sample = sel && !have_override && !p.deterministic && !p.observe_only;
+    const int F = p.num_free[p.per_env_maps ? (env_ok ? env : 0) : 0];
+    if (sample && F < 2 * N) { errs |= MAPF_DEV_ERR_TOO_FEW_CELLS; sample = false; }
+    const Philox ph(p.seed, p.env_id_base + env);
+    draw_layout<G>(ph, rng_counter, F, freebm, p.fw, p.C, N, gl, gbase, gmask, sample && act, st, gg);
+    bool write_layout = false;
+    if (act) {
+        if (p.observe_only) { st = p.positions[ai]; gg = p.goals[ai]; }
+        else if (have_override) { st = p.starts_override[ai]; gg = p.goals_override[ai]; write_layout = true; }
+        else if (p.deterministic) { st = p.starts[ai]; gg = p.goals[ai]; }
+        else if (sample) write_layout = true;
+        else { st = p.positions[ai]; gg = p.goals[ai]; }
+    }
+
+    const uint32_t l = act ? lin(st) : LFAR;
+    s_new[gl] = l; s_snap[gl] = l; s_goal[gl] = act ? lin(gg) : LFAR;
+    __syncwarp();
+    PairOut<G, SR, false> pr;
+    pair_loop<G, SR, false>(s_new, s_snap, s_goal, s_int, s_delta, gl, l, st, 0u, false, p.nearby, pr);
+
+    const int my_env_in_warp = lane / G;
+    const size_t warp_env0 = (size_t)blockIdx.x * groups + (size_t)(warp * envs_per_warp);
+    // outputs of unselected envs must stay untouched: selected groups write their channels directly
+    if (act) {
+        uint8_t tmp[V2];
+        uint32_t amask = emit_window<SR>(rows, p.wpr, prow(st), pcol(st), pr.occ, pr.xgoal, lin(gg), l, tmp);
+        if (p.o_local_obs) {
+            uint8_t *dst = p.o_local_obs + ai * V2;
+#pragma unroll
+            for (int k = 0; k < V2; ++k) dst[k] = tmp[k];
+        }
+        if (p.o_action_mask) {
+            int8_t *dst = p.o_action_mask + ai * 5;
+#pragma unroll
+            for (int k = 0; k < 5; ++k) dst[k] = (int8_t)((amask >> k) & 1u);
+        }
+        if (p.o_goal_delta) p.o_goal_delta[ai] = goal_delta(gg, st, p.normalize, p.den0, p.den1);
+        if (p.observe_only) {
+            if (p.o_blocking_prev) p.o_blocking_prev[ai] = (p.agent_flags[ai] >> 2) & 1u;
+        } else {
+        if (p.o_blocking_prev) p.o_blocking_prev[ai] = 0;
+        if (p.o_reward) p.o_reward[ai] = 0.f;
+        if (p.o_agent_step_flags) p.o_agent_step_flags[ai] = (st == gg) ? MAPF_ASF_ON_GOAL : 0;
+        // state, ENV:441-450
+        p.positions[ai] = st;
+        if (write_layout) { p.starts[ai] = st; p.goals[ai] = gg; }
+        p.agent_flags[ai] = 0;
+        if (p.lock_gp) { p.lock_gp[ai] = 0; p.lock_mv[ai] = 0; p.lock_fm[ai] = 0; }
+        if (p.lock_dist)
+            for (int s = 0; s < p.lw; ++s) p.lock_dist[((size_t)env * p.lw + s) * N + gl] = 0;
+        }
+    }
+    if (sel && gl == 0 && !p.observe_only) {
+        if (p.o_terminated) p.o_terminated[env] = 0;
+        if (p.o_truncated) p.o_truncated[env] = 0;
+        if (p.o_step_flags) p.o_step_flags[env] = 0;
+        if (p.o_info) {
+            int4 *io = p.o_info + (size_t)env * 4;
+            io[0] = io[1] = io[2] = io[3] = make_int4(0, 0, 0, 0);
+        }
+        int4 *ew = p.env_words + (size_t)env * 4;
+        ew[0] = make_int4(0, 0, 0, 0);
+        ew[1] = make_int4(0, 0, 0, 0);
+        ew[2] = make_int4(0, (int)rng_counter, 0, 0);
+        ew[3] = w3;
+    }
+    (void)stage_obs; (void)stage_mask; (void)my_env_in_warp; (void)warp_env0;
+    errs = __reduce_or_sync(full, errs);
+    if (errs && lane == 0) atomicOr(p.err_bits, errs);
+}
+
+// ============================================================================ small kernels
+// ENV:306-328 flat float32 observation, one thread per output element.
+__global__ void mapf_pack_flat_kernel(const uint8_t *local_obs, const float2 *goal_delta,
+                                      const uint8_t *bp, const int8_t *mask, float *flat, long long BN,
+                                      int V2, int gdist, int use_bp, int use_mask, int D) {
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= BN * D) return;
+    long long a = idx / D;
+    int k = (int)(idx - a * D);
+    float v;
+    if (k < V2) v = (float)local_obs[a * V2 + k];
+    else {
+        k -= V2;
+        float2 g = goal_delta[a];
+        if (k == 0) v = g.x;
+        else if (k == 1) v = g.y;
+        else {
+            k -= 2;
+            if (gdist && k == 0) v = __fadd_rn(fabsf(g.x), fabsf(g.y));  // ENV:320
+            else {
+                k -= gdist;
+                if (use_bp && k == 0) v = (float)bp[a];
+                else { k -= use_bp; v = (float)mask[a * 5 + k]; }
+            }
+        }
+    }
+    flat[idx] = v;
+    (void)use_mask;
+}
+
+__global__ void mapf_sample_actions_kernel(const int8_t *mask, int8_t *actions, long long BN, int N,
+                                           unsigned long long seed, long long env_id_base,
+                                           unsigned long long counter) {
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= BN) return;
+    long long env = idx / N;
+    int a = (int)(idx - env * N);
+    Philox ph(seed ^ 0xA511E9B3ull, env_id_base + env);
+    uint4 x = ph((uint32_t)counter, (uint32_t)(counter >> 32), (uint32_t)a, 0x41435421u);
+    int act;
+    if (mask) {  // scripts/benchmark_multi_agent_env.py:42-57
+        const int8_t *m = mask + idx * 5;
+        int bits = 0;
+        for (int k = 0; k < 5; ++k) bits |= (m[k] != 0) << k;
+        int n = __popc(bits);
+        act = n ? (int)__fns((unsigned)bits, 0, (int)__umulhi(x.x, (uint32_t)n) + 1) : 0;
+    } else {
+        act = (int)__umulhi(x.x, 5u);  // scripts/benchmark_multi_agent_env.py:38-39
+    }
+    actions[idx] = (int8_t)act;
+}
+
+// Deterministic reduction of env_metrics[B,K]: CTA k reduces metric k in a fixed order
+// (strided partial sums, then a shared-memory tree), so the result does not depend on timing.
+__global__ void mapf_metrics_reduce_kernel(const double *env_metrics, int B, double *out) {
+    __shared__ double sm[256];
+    const int k = blockIdx.x;
+    double s = 0.0;
+    for (int e = threadIdx.x; e < B; e += blockDim.x) s += env_metrics[(size_t)e * MAPF_METRIC_COUNT + k];
+    sm[threadIdx.x] = s;
+    __syncthreads();
+    for (int st = blockDim.x / 2; st > 0; st >>= 1) {
+        if ((int)threadIdx.x < st) sm[threadIdx.x] += sm[threadIdx.x + st];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[k] = sm[0];
+}
+
+}  // namespace mapf

@@ -1,0 +1,280 @@
+/*
+ * mapf_b200.h -- C ABI of libmapf_b200.so: the batched, B200-native (sm_100a) implementation
+ * of the MAPF environment transition of Nerozud/dl_reference_models.
+ *
+ * Reference interface replaced (ENV = src/environments/reference_model_multi_agent.py):
+ *   ReferenceModel.__init__(env_config)   ENV:34-193   -> mapf_create + mapf_set_map + mapf_bind_state
+ *   ReferenceModel.reset()                ENV:440-472  -> mapf_reset / mapf_reset_host
+ *   ReferenceModel.step(action_dict)      ENV:474-695  -> mapf_step  / mapf_step_host
+ *   get_obs / get_action_mask             ENV:707-773  -> the local_obs / action_mask outputs
+ *   _flatten_observation                  ENV:306-328  -> mapf_pack_flat_obs
+ *   private state arrays (ENV:82-120), written by the reference's tests -> mapf_state tensors
+ *   info["__all__"] + RLlib callback metric set (src/trainers/callbacks.py:152,173,335-345)
+ *                                                       -> env_words / mapf_metrics_reduce
+ *
+ * Conventions
+ *   - plain C: opaque handle, plain pointers and sizes, every call returns 0 or a negative
+ *     MAPF_ERR_* code; mapf_last_error() gives the message (thread-local).  No exceptions.
+ *   - one handle <-> one CUDA device; a handle is not thread-safe.
+ *   - B = num_envs on this device, N = num_agents (<= 32), V = 2*sensor_range+1 (sr <= 3),
+ *     coordinates are (row, col) int16 pairs like the reference's int16 [N,2] arrays.
+ *   - `stream` arguments are cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - "device pointer" buffers are caller-owned (e.g. torch tensors); *_host entry points take
+ *     host pointers and do the H2D / D2H copies themselves on the handle's own stream (pass
+ *     page-locked buffers for full PCIe/NVLink-C2C bandwidth; pageable memory works too).
+ *   - there is NO CPU fallback: every entry point that computes launches sm_100a kernels.
+ */
+#ifndef MAPF_B200_H
+#define MAPF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MAPF_MAX_AGENTS 32
+#define MAPF_MAX_SENSOR_RANGE 3
+#define MAPF_MAX_LOCK_WINDOW 32
+#define MAPF_MAX_DIM 255
+
+#define MAPF_OK 0
+#define MAPF_ERR_INVALID_ARG (-1)
+#define MAPF_ERR_CUDA (-2)
+#define MAPF_ERR_UNSUPPORTED (-3)
+#define MAPF_ERR_STATE (-4)
+
+/* device-side error bits, see mapf_poll_errors() */
+#define MAPF_DEV_ERR_INVALID_ACTION 1u /* ENV:504-506 (ValueError in the reference) */
+#define MAPF_DEV_ERR_NO_GOAL_CELL 2u   /* ENV:296-298 (RuntimeError in the reference) */
+#define MAPF_DEV_ERR_TOO_FEW_CELLS 4u  /* ENV:270-275 (ValueError in the reference) */
+
+/* env_config keys that affect the transition (ENV:38-61), plus batching/sharding keys. */
+typedef struct mapf_config {
+    int32_t num_envs;    /* B: envs owned by this handle (this GPU's shard) */
+    int32_t num_agents;  /* N, 1..32 */
+    int32_t rows, cols;  /* map shape, 1..255 */
+    int32_t sensor_range;      /* 1..3 */
+    int32_t steps_per_episode; /* ENV:38 */
+    int32_t lifelong_mapf;     /* ENV:51 */
+    int32_t enable_lock_metrics;   /* ENV:61 */
+    int32_t deadlock_window_steps; /* ENV:56, 1..32 */
+    int32_t livelock_window_steps; /* ENV:57, 1..32 */
+    int32_t lock_nearby_manhattan; /* ENV:58 */
+    int32_t lock_min_neighbors;    /* ENV:60 */
+    int32_t lock_progress_epsilon_floor; /* floor(ENV:59): distances are integers */
+    int32_t normalize_goal_delta;  /* ENV:42 */
+    int32_t deterministic;   /* ENV:41: reset restores `starts`, keeps goals (ENV:452-455) */
+    int32_t per_env_maps;    /* 0: one map shared by all envs; 1: one map per env */
+    int64_t env_id_base;     /* global id of env 0 (Philox key => results independent of sharding) */
+    uint64_t seed;           /* ENV:74 */
+    int32_t device;          /* CUDA device ordinal */
+    int32_t reserved;
+} mapf_config;
+
+/* Words of the per-env int32 state block env_words[B, MAPF_ENV_WORDS]. */
+enum {
+    MAPF_W_STEP_COUNT = 0,      /* ENV:37 */
+    MAPF_W_LOCK_COUNT,          /* ENV:119 _lock_hist_count, not saturated: history rows appended since reset */
+    MAPF_W_LOCK_PREV,           /* bit0 _deadlock_state_prev, bit1 _livelock_state_prev (ENV:68-69) */
+    MAPF_W_GOALS_TOTAL,         /* ENV:88  _episode_goals_reached_total */
+    MAPF_W_BLOCKING_TOTAL,      /* ENV:63  _episode_blocking_count */
+    MAPF_W_DEADLOCK_EVENTS,     /* ENV:64 */
+    MAPF_W_LIVELOCK_EVENTS,     /* ENV:65 */
+    MAPF_W_DEADLOCK_STEPS,      /* ENV:66 */
+    MAPF_W_LIVELOCK_STEPS,      /* ENV:67 */
+    MAPF_W_RNG_COUNTER,         /* Philox draws consumed by this env */
+    MAPF_W_EPISODE_RETURN_X2,   /* 2 * sum of rewards of all agents this episode (exact integer) */
+    MAPF_W_WFG_CYCLE_STEPS,     /* steps of this episode with a wait-for-graph cycle */
+    MAPF_W_EPISODES,            /* finished episodes of this env */
+    MAPF_W_RESERVED0,
+    MAPF_W_RESERVED1,
+    MAPF_W_RESERVED2,
+    MAPF_ENV_WORDS
+};
+
+/* agent_flags bits (state tensor agent_flags[B,N], uint8) */
+#define MAPF_AF_REACHED 1u        /* ENV:86 _reached_arr (sticky) */
+#define MAPF_AF_COMPLETED_ONCE 2u /* ENV:87 _completed_once_arr */
+#define MAPF_AF_BLOCKING_PREV 4u  /* ENV:89 _blocking_pressure_prev_arr (as 0/1) */
+
+/* Device-resident state, caller-owned (torch tensors).  Layout mirrors ENV:82-120. */
+typedef struct mapf_state {
+    int16_t *positions;    /* [B,N,2] ENV:84 */
+    int16_t *goals;        /* [B,N,2] ENV:85 */
+    int16_t *starts;       /* [B,N,2] ENV:83 */
+    uint8_t *agent_flags;  /* [B,N]   MAPF_AF_* */
+    uint32_t *lock_goal_progress; /* [B,N] bit t = flag t steps ago (ENV:115) */
+    uint32_t *lock_moved;         /* [B,N] (ENV:116) */
+    uint32_t *lock_failed_move;   /* [B,N] (ENV:117) */
+    int16_t *lock_distance;       /* [B,LW,N] ring over the livelock window (ENV:118) */
+    int32_t *env_words;    /* [B,MAPF_ENV_WORDS] */
+    double *env_metrics;   /* [B,MAPF_METRIC_COUNT] per-env episode-end sums (see below) */
+} mapf_state;
+
+/* Episode-end metric sums (the set the reference's RLlib callbacks log,
+ * src/trainers/callbacks.py:152,173,335-345).  Per env in env_metrics, reduced by
+ * mapf_metrics_reduce(); ranks all-reduce(sum) the reduced vector. */
+enum {
+    MAPF_M_EPISODES = 0,
+    MAPF_M_RETURN_SUM,
+    MAPF_M_LENGTH_SUM,
+    MAPF_M_SUCCESS_SUM,      /* terminated && !truncated, callbacks.py:172 */
+    MAPF_M_GOALS_REACHED_SUM,
+    MAPF_M_BLOCKING_COUNT_SUM,
+    MAPF_M_DEADLOCK_COUNT_SUM,
+    MAPF_M_LIVELOCK_COUNT_SUM,
+    MAPF_M_DEADLOCK_STEPS_SUM,
+    MAPF_M_LIVELOCK_STEPS_SUM,
+    MAPF_M_THROUGHPUT_SUM,
+    MAPF_M_COMPLETION_RATIO_SUM,
+    MAPF_M_WFG_CYCLE_STEPS_SUM,
+    MAPF_M_RESERVED0,
+    MAPF_M_RESERVED1,
+    MAPF_M_RESERVED2,
+    MAPF_METRIC_COUNT
+};
+
+/* step_flags bits (output step_flags[B], uint8) */
+#define MAPF_SF_TERMINATED 1u      /* ENV:675,686 */
+#define MAPF_SF_TRUNCATED 2u       /* ENV:687 */
+#define MAPF_SF_DEADLOCK_STEP 4u   /* ENV:644 */
+#define MAPF_SF_LIVELOCK_STEP 8u   /* ENV:645 */
+#define MAPF_SF_DEADLOCK_EVENT 16u /* ENV:646 */
+#define MAPF_SF_LIVELOCK_EVENT 32u /* ENV:647 */
+#define MAPF_SF_GOAL_REASSIGNED 64u /* ENV:556 */
+#define MAPF_SF_WFG_CYCLE 128u     /* wait-for-graph cycle present (no reference counterpart) */
+
+/* agent_step_flags bits (output agent_step_flags[B,N], uint8) */
+#define MAPF_ASF_MOVED 1u          /* ENV:582 */
+#define MAPF_ASF_FAILED_MOVE 2u    /* ENV:583 */
+#define MAPF_ASF_GOAL_REACHED 4u   /* info[aid]["goal_reached_step"], ENV:629 */
+#define MAPF_ASF_BLOCKING 8u       /* info[aid]["blocking"], ENV:628 */
+#define MAPF_ASF_WFG_CYCLE 16u     /* agent is on a wait-for-graph cycle */
+#define MAPF_ASF_ON_GOAL 32u       /* ENV:588 current_on_goal */
+
+/* Outputs of reset/step.  Caller-owned; any pointer may be NULL (that channel is skipped). */
+typedef struct mapf_outputs {
+    uint8_t *local_obs;     /* [B,N,V,V] ENV:707-747 (staggered snapshot, F3) */
+    int8_t *action_mask;    /* [B,N,5]   ENV:749-773 */
+    float *goal_delta;      /* [B,N,2]   ENV:330-335 */
+    uint8_t *blocking_prev; /* [B,N]     ENV:322 (0/1) */
+    float *reward;          /* [B,N] */
+    uint8_t *terminated;    /* [B] */
+    uint8_t *truncated;     /* [B] */
+    uint8_t *step_flags;        /* [B]   MAPF_SF_* */
+    uint8_t *agent_step_flags;  /* [B,N] MAPF_ASF_* */
+    int32_t *info;              /* [B,MAPF_INFO_WORDS] integer sources of info["__all__"], ENV:639-656 */
+} mapf_outputs;
+
+/* Words of the per-step info block (all exact integers; the two ratios of ENV:638,655 are
+ * completed_count / N and goals_reached_total / max(step_count, 1), formed by the caller in
+ * float64 like the reference does). */
+enum {
+    MAPF_I_GOALS_REACHED_STEP = 0,
+    MAPF_I_GOALS_REACHED_TOTAL,   /* lifelong: cumulative arrivals, else sum(_reached_arr), ENV:630-633 */
+    MAPF_I_BLOCKING_COUNT_STEP,
+    MAPF_I_BLOCKING_COUNT_TOTAL,
+    MAPF_I_DEADLOCK_STEP,
+    MAPF_I_LIVELOCK_STEP,
+    MAPF_I_DEADLOCK_EVENT_STEP,
+    MAPF_I_LIVELOCK_EVENT_STEP,
+    MAPF_I_DEADLOCK_EVENTS_TOTAL,
+    MAPF_I_LIVELOCK_EVENTS_TOTAL,
+    MAPF_I_DEADLOCK_STEPS_TOTAL,
+    MAPF_I_LIVELOCK_STEPS_TOTAL,
+    MAPF_I_COMPLETED_COUNT,       /* sum(_completed_once_arr), ENV:638 */
+    MAPF_I_STEP_COUNT,            /* ENV:655 */
+    MAPF_I_REACHED_COUNT,         /* sum(_reached_arr) */
+    MAPF_I_WFG_CYCLE_STEPS,
+    MAPF_INFO_WORDS
+};
+
+typedef struct mapf_handle mapf_handle;
+
+const char *mapf_version(void);
+const char *mapf_last_error(void);
+
+/* ENV:34-193.  Validates cfg (limits above), allocates the handle's small device tables. */
+int mapf_create(const mapf_config *cfg, mapf_handle **out);
+int mapf_destroy(mapf_handle *h);
+
+/* grid: HOST uint8 [R,C] (shared) or [B,R,C] (per_env_maps), 0 free / 1 obstacle (ENV:80-82).
+ * Returns MAPF_ERR_INVALID_ARG if a map has fewer than 2N free cells and cfg is not
+ * deterministic (ENV:270-275). */
+int mapf_set_map(mapf_handle *h, const uint8_t *grid);
+
+/* Bytes the caller must allocate for each mapf_state member (same order as the struct). */
+int mapf_state_nbytes(const mapf_handle *h, int64_t out_nbytes[10]);
+/* Install the device pointers of the state tensors (kept by reference, not copied). */
+int mapf_bind_state(mapf_handle *h, const mapf_state *state);
+/* Alternative for callers without their own device allocator (plain C / cgo / ctypes users):
+ * the handle allocates, zeroes, binds and later frees the state block itself. */
+int mapf_alloc_state(mapf_handle *h);
+/* Copy the bound state device -> host / host -> device.  `host` holds HOST pointers with the
+ * mapf_state layout; NULL members are skipped.  This is the injection path the reference's
+ * tests use by writing the private numpy arrays (tests/test_reference_model_lifelong.py:29-39). */
+int mapf_get_state_host(mapf_handle *h, const mapf_state *host);
+int mapf_set_state_host(mapf_handle *h, const mapf_state *host);
+
+/* ENV:440-472.  reset_mask: device uint8 [B] (NULL = every env).
+ * starts_override / goals_override: device int16 [B,N,2] or NULL.  With overrides the layout is
+ * taken from them (what rng.choice produced, ENV:277-280); otherwise deterministic cfg restores
+ * `starts`, and non-deterministic cfg draws 2N distinct free cells with Philox4x32-10
+ * keyed by (seed, env_id_base + env). */
+int mapf_reset(mapf_handle *h, const uint8_t *reset_mask, const int16_t *starts_override,
+               const int16_t *goals_override, const mapf_outputs *out, void *stream);
+
+/* ENV:707-773 on the CURRENT state (the public get_obs()/get_action_mask() of the reference):
+ * fills local_obs / action_mask / goal_delta / blocking_prev of `out`, mutates nothing. */
+int mapf_observe(mapf_handle *h, const mapf_outputs *out, void *stream);
+int mapf_observe_host(mapf_handle *h, const mapf_outputs *out_host);
+
+/* ENV:474-695.  actions: device int8 [B,N] in 0..4 (NULL = all NO_OP, ENV:498-500).
+ * goal_override: device int16 [B,N,2]; a row >= 0 replaces the lifelong goal draw of that agent
+ *   (replay hook for bit-exact parity; NULL = none).
+ * goal_rank: device int32 [B,N]; a value >= 0 replaces rng.integers(n) at ENV:300 (NULL = none).
+ * auto_reset != 0: an env whose episode ended is reset in the same launch (its obs outputs are
+ *   the first observation of the next episode; reward/terminated/truncated are the final step's),
+ *   like run_benchmark's `if done: reset()` (scripts/benchmark_multi_agent_env.py:89-95). */
+int mapf_step(mapf_handle *h, const int8_t *actions, const int16_t *goal_override,
+              const int32_t *goal_rank, const mapf_outputs *out, int32_t auto_reset, void *stream);
+
+/* Host-buffer variants: same semantics, every pointer is HOST memory (NULL = skip).
+ * H2D of inputs, the kernel, and D2H of the requested outputs all happen inside the call,
+ * which returns after the results are in the host buffers. */
+int mapf_reset_host(mapf_handle *h, const uint8_t *reset_mask, const int16_t *starts_override,
+                    const int16_t *goals_override, const mapf_outputs *out_host);
+int mapf_step_host(mapf_handle *h, const int8_t *actions, const int16_t *goal_override,
+                   const int32_t *goal_rank, const mapf_outputs *out_host, int32_t auto_reset);
+
+/* ENV:306-328: pack channels into float32 flat[B,N,D] (device pointers),
+ * D = V*V + 2 + gdist + bp + 5*mask, component order of ENV:214-236. */
+int mapf_flat_obs_dim(const mapf_handle *h, int32_t include_goal_distance,
+                      int32_t include_blocking_pressure, int32_t include_action_mask);
+int mapf_pack_flat_obs(mapf_handle *h, const mapf_outputs *channels, int32_t include_goal_distance,
+                       int32_t include_blocking_pressure, int32_t include_action_mask,
+                       float *flat, void *stream);
+
+/* Uniform choice among the valid actions of each agent (device int8 masks [B,N,5] ->
+ * device int8 actions [B,N]); the action sampler of the reference's "masked" benchmark mode
+ * (scripts/benchmark_multi_agent_env.py:42-57), Philox keyed by (seed, env id, counter). */
+int mapf_sample_masked_actions(mapf_handle *h, const int8_t *action_mask, int8_t *actions,
+                               uint64_t counter, void *stream);
+/* Uniform actions in 0..4 (scripts/benchmark_multi_agent_env.py:38-39). */
+int mapf_sample_random_actions(mapf_handle *h, int8_t *actions, uint64_t counter, void *stream);
+
+/* Deterministic tree reduction of env_metrics[B,K] over the B envs into
+ * device double out[MAPF_METRIC_COUNT] (off the step path; ranks then all-reduce it). */
+int mapf_metrics_reduce(mapf_handle *h, double *out_device, void *stream);
+
+/* OR of MAPF_DEV_ERR_* bits raised by kernels since the last poll (synchronises `stream`). */
+int mapf_poll_errors(mapf_handle *h, uint32_t *bits, void *stream);
+
+/* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
+int64_t mapf_launch_count(const mapf_handle *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAPF_B200_H */

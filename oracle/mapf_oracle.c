@@ -37,6 +37,7 @@ struct oracle_env {
     float *goal_step_flags, *blocking_flags;
     int8_t *actions_taken;
     int32_t *last_cand;
+    int32_t *last_rank; /* rank drawn by the last reassignment of each agent (debug / replay) */
     int32_t *perm; /* [F] scratch for sampling without replacement */
     uint8_t *tmp_obs; /* [V*V] */
 };
@@ -109,6 +110,7 @@ oracle_env *oracle_create(const oracle_config *cfg, const uint8_t *grid, uint64_
     e->blocking_flags = (float *)zalloc(sizeof(float) * N);
     e->actions_taken = (int8_t *)zalloc(N);
     e->last_cand = (int32_t *)zalloc(sizeof(int32_t) * N);
+    e->last_rank = (int32_t *)zalloc(sizeof(int32_t) * N);
     e->perm = (int32_t *)zalloc(sizeof(int32_t) * RC);
     e->tmp_obs = (uint8_t *)zalloc((size_t)e->V * e->V);
     e->rng = seed * 0x9E3779B97F4A7C15ull + 0x1234567ull;
@@ -123,7 +125,7 @@ void oracle_destroy(oracle_env *e) {
     free(e->goal_owner); free(e->h_gp); free(e->h_mv); free(e->h_fm); free(e->h_dist);
     free(e->prev_pos); free(e->intended); free(e->reached_goal); free(e->moved); free(e->failed);
     free(e->gprog); free(e->prev_on_goal); free(e->cur_on_goal); free(e->dist);
-    free(e->goal_step_flags); free(e->blocking_flags); free(e->actions_taken); free(e->last_cand);
+    free(e->goal_step_flags); free(e->blocking_flags); free(e->actions_taken); free(e->last_cand); free(e->last_rank);
     free(e->perm); free(e->tmp_obs);
     free(e);
 }
@@ -331,6 +333,7 @@ static int assign_new_goal(oracle_env *e, int idx, int rank, const int16_t *over
         if (n == 0) return ORACLE_ERR_NO_GOAL_CELL; /* ENV:296-298 */
         int k = rank >= 0 ? rank : (int)rng_below(&e->rng, (uint32_t)n); /* ENV:300 */
         if (k >= n) return ORACLE_ERR_BAD_ARG;
+        e->last_rank[idx] = k;
         r = e->free_pos[2 * e->perm[k]];
         c = e->free_pos[2 * e->perm[k] + 1];
     }
@@ -415,6 +418,7 @@ int oracle_step(oracle_env *e, const int8_t *actions, const int32_t *goal_rank,
     int goal_reassigned = 0;
     for (int a = 0; a < N; ++a) {
         reward[a] = 0.0f;
+        e->last_rank[a] = -1;
         e->reached_goal[a] = 0;
         e->goal_step_flags[a] = 0.0f;
         e->blocking_flags[a] = 0.0f;
@@ -603,6 +607,76 @@ void oracle_get_owner_grids(const oracle_env *e, int16_t *occ, int16_t *goal) {
 
 void oracle_get_last_candidate_counts(const oracle_env *e, int32_t *out) {
     memcpy(out, e->last_cand, sizeof(int32_t) * e->N);
+}
+
+void oracle_get_last_ranks(const oracle_env *e, int32_t *out) {
+    memcpy(out, e->last_rank, sizeof(int32_t) * e->N);
+}
+
+/* ---------------------------------------------------------------- batched stepping (tests) */
+static void offset_outputs(const oracle_outputs *o, int b, int N, int V2, oracle_outputs *r) {
+    memset(r, 0, sizeof(*r));
+    if (!o) return;
+    if (o->local_obs) r->local_obs = o->local_obs + (size_t)b * N * V2;
+    if (o->action_mask) r->action_mask = o->action_mask + (size_t)b * N * 5;
+    if (o->goal_delta) r->goal_delta = o->goal_delta + (size_t)b * N * 2;
+    if (o->goal_distance) r->goal_distance = o->goal_distance + (size_t)b * N;
+    if (o->blocking_prev) r->blocking_prev = o->blocking_prev + (size_t)b * N;
+    if (o->reward) r->reward = o->reward + (size_t)b * N;
+    if (o->terminated) r->terminated = o->terminated + b;
+    if (o->truncated) r->truncated = o->truncated + b;
+    if (o->blocking) r->blocking = o->blocking + (size_t)b * N;
+    if (o->goal_reached_step) r->goal_reached_step = o->goal_reached_step + (size_t)b * N;
+    if (o->info_all) r->info_all = o->info_all + (size_t)b * ORACLE_INFO_COUNT;
+    if (o->moved) r->moved = o->moved + (size_t)b * N;
+    if (o->failed_move) r->failed_move = o->failed_move + (size_t)b * N;
+    if (o->intended_next) r->intended_next = o->intended_next + (size_t)b * N * 2;
+    if (o->goal_reassigned) r->goal_reassigned = o->goal_reassigned + b;
+}
+
+int oracle_reset_many(oracle_env **envs, int num_envs, int mode, const int16_t *starts,
+                      const int16_t *goals, const uint8_t *mask, oracle_outputs *out) {
+    for (int b = 0; b < num_envs; ++b) {
+        if (mask && !mask[b]) continue;
+        oracle_env *e = envs[b];
+        oracle_outputs o;
+        offset_outputs(out, b, e->N, e->V * e->V, &o);
+        int rc = oracle_reset(e, mode, starts ? starts + (size_t)b * e->N * 2 : NULL,
+                              goals ? goals + (size_t)b * e->N * 2 : NULL, out ? &o : NULL);
+        if (rc) return rc;
+    }
+    return ORACLE_OK;
+}
+
+int oracle_step_many(oracle_env **envs, int num_envs, const int8_t *actions, const int32_t *goal_rank,
+                     const int16_t *goal_override, oracle_outputs *out, int32_t *ranks_out) {
+    for (int b = 0; b < num_envs; ++b) {
+        oracle_env *e = envs[b];
+        int N = e->N;
+        oracle_outputs o;
+        offset_outputs(out, b, N, e->V * e->V, &o);
+        int rc = oracle_step(e, actions ? actions + (size_t)b * N : NULL,
+                             goal_rank ? goal_rank + (size_t)b * N : NULL,
+                             goal_override ? goal_override + (size_t)b * N * 2 : NULL, out ? &o : NULL);
+        if (rc) return rc;
+        if (ranks_out) memcpy(ranks_out + (size_t)b * N, e->last_rank, sizeof(int32_t) * N);
+    }
+    return ORACLE_OK;
+}
+
+void oracle_get_state_many(oracle_env **envs, int num_envs, int16_t *positions, int16_t *starts,
+                           int16_t *goals, uint8_t *reached, uint8_t *completed_once,
+                           float *blocking_prev, int32_t *step_count, double *episode_counters) {
+    for (int b = 0; b < num_envs; ++b) {
+        int N = envs[b]->N;
+        oracle_get_state(envs[b], positions ? positions + (size_t)b * N * 2 : NULL,
+                         starts ? starts + (size_t)b * N * 2 : NULL,
+                         goals ? goals + (size_t)b * N * 2 : NULL, reached ? reached + (size_t)b * N : NULL,
+                         completed_once ? completed_once + (size_t)b * N : NULL,
+                         blocking_prev ? blocking_prev + (size_t)b * N : NULL,
+                         step_count ? step_count + b : NULL,
+                         episode_counters ? episode_counters + (size_t)b * 6 : NULL);
+    }
 }
 
 /* ---------------------------------------------------------------- flat obs, ENV:214-265,306-328 */

@@ -125,6 +125,19 @@ void oracle_get_owner_grids(const oracle_env *env, int16_t *occupancy_owner, int
 /* number of candidate cells the last reassignment of each agent saw (debug), [N] */
 void oracle_get_last_candidate_counts(const oracle_env *env, int32_t *out);
 
+/* rank (index into the candidate list, ENV:300) used by the last step's reassignment of each
+ * agent, -1 where none happened; lets a recorded oracle run be replayed through goal_rank. [N] */
+void oracle_get_last_ranks(const oracle_env *env, int32_t *out);
+
+/* Batched variants for parity tests at B > 1: env b uses slice b of every [B, ...] array. */
+int oracle_reset_many(oracle_env **envs, int num_envs, int mode, const int16_t *starts,
+                      const int16_t *goals, const uint8_t *mask, oracle_outputs *out);
+int oracle_step_many(oracle_env **envs, int num_envs, const int8_t *actions, const int32_t *goal_rank,
+                     const int16_t *goal_override, oracle_outputs *out, int32_t *ranks_out);
+void oracle_get_state_many(oracle_env **envs, int num_envs, int16_t *positions, int16_t *starts,
+                           int16_t *goals, uint8_t *reached, uint8_t *completed_once,
+                           float *blocking_prev, int32_t *step_count, double *episode_counters);
+
 /* ENV:306-328: pack channels into the flat float32 vector.  Returns D. */
 int oracle_flat_obs_dim(const oracle_config *cfg, int include_goal_distance,
                         int include_blocking_pressure, int include_action_mask);

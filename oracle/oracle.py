@@ -109,6 +109,12 @@ def lib():
         L.oracle_get_state.argtypes = [C.c_void_p] + [C.c_void_p] * 8
         L.oracle_get_owner_grids.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.oracle_get_last_candidate_counts.argtypes = [C.c_void_p, C.c_void_p]
+        L.oracle_get_last_ranks.argtypes = [C.c_void_p, C.c_void_p]
+        L.oracle_reset_many.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.POINTER(_Outputs)]
+        L.oracle_step_many.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.POINTER(_Outputs), C.c_void_p]
+        L.oracle_get_state_many.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 8
         L.oracle_bench_run.restype = C.c_int64
         L.oracle_bench_run.argtypes = [
             C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int,
@@ -275,6 +281,76 @@ class OracleEnv:
         out = np.zeros(self.N, np.int32)
         lib().oracle_get_last_candidate_counts(self._h, _ptr(out))
         return out
+
+
+class OracleBatch:
+    """B independent oracle envs stepped by one C call; outputs are [B, ...] numpy arrays that are
+    overwritten by the next call (same channel names as :class:`StepResult`, plus ``ranks``)."""
+
+    def __init__(self, env_config: dict, grid: np.ndarray, num_envs: int, seed: int = 0):
+        grid = np.ascontiguousarray(grid, np.uint8)
+        per_env = grid.ndim == 3
+        self.envs = [OracleEnv(env_config, grid[b] if per_env else grid, seed=seed + b)
+                     for b in range(num_envs)]
+        self.B, self.N, self.V = num_envs, self.envs[0].N, self.envs[0].V
+        self.lifelong = self.envs[0].lifelong
+        self._arr = (C.c_void_p * num_envs)(*[e.handle for e in self.envs])
+        B, N, V = self.B, self.N, self.V
+        self.buf = {
+            "local_obs": np.zeros((B, N, V, V), np.uint8), "action_mask": np.zeros((B, N, 5), np.int8),
+            "goal_delta": np.zeros((B, N, 2), np.float32), "goal_distance": np.zeros((B, N), np.float32),
+            "blocking_prev": np.zeros((B, N), np.float32), "reward": np.zeros((B, N), np.float32),
+            "terminated": np.zeros(B, np.uint8), "truncated": np.zeros(B, np.uint8),
+            "blocking": np.zeros((B, N), np.float32), "goal_reached_step": np.zeros((B, N), np.float32),
+            "info_all": np.zeros((B, len(INFO_KEYS)), np.float64), "moved": np.zeros((B, N), np.uint8),
+            "failed_move": np.zeros((B, N), np.uint8), "intended_next": np.zeros((B, N, 2), np.int16),
+            "goal_reassigned": np.zeros(B, np.uint8),
+        }
+        self.ranks = np.full((B, N), -1, np.int32)
+        self._out = _Outputs(**{k: _ptr(v) for k, v in self.buf.items()})
+
+    def reset(self, mode: int = 2, starts=None, goals=None, mask=None) -> dict:
+        s = None if starts is None else np.ascontiguousarray(starts, np.int16)
+        g = None if goals is None else np.ascontiguousarray(goals, np.int16)
+        m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+        OracleEnv._check(lib().oracle_reset_many(self._arr, self.B, mode, _ptr(s), _ptr(g), _ptr(m),
+                                                 C.byref(self._out)))
+        return self.buf
+
+    def step(self, actions, goal_rank=None, goal_override=None) -> dict:
+        a = np.ascontiguousarray(actions, np.int8)
+        gr = None if goal_rank is None else np.ascontiguousarray(goal_rank, np.int32)
+        go = None if goal_override is None else np.ascontiguousarray(goal_override, np.int16)
+        OracleEnv._check(lib().oracle_step_many(self._arr, self.B, _ptr(a), _ptr(gr), _ptr(go),
+                                                C.byref(self._out), _ptr(self.ranks)))
+        return self.buf
+
+    def state(self) -> dict:
+        B, N = self.B, self.N
+        st = {
+            "positions": np.zeros((B, N, 2), np.int16), "starts": np.zeros((B, N, 2), np.int16),
+            "goals": np.zeros((B, N, 2), np.int16), "reached": np.zeros((B, N), np.uint8),
+            "completed_once": np.zeros((B, N), np.uint8), "blocking_prev": np.zeros((B, N), np.float32),
+            "step_count": np.zeros(B, np.int32), "episode_counters": np.zeros((B, 6), np.float64),
+        }
+        lib().oracle_get_state_many(self._arr, self.B, *[_ptr(st[k]) for k in (
+            "positions", "starts", "goals", "reached", "completed_once", "blocking_prev",
+            "step_count", "episode_counters")])
+        return st
+
+
+def flat_obs_batch(buf: dict, include_goal_distance=False, include_blocking_pressure=True,
+                   include_action_mask=False) -> np.ndarray:
+    """ENV:306-328 for [B, N, ...] channel arrays -> [B, N, D] float32."""
+    B, N = buf["local_obs"].shape[:2]
+    parts = [buf["local_obs"].reshape(B, N, -1).astype(np.float32), buf["goal_delta"].astype(np.float32)]
+    if include_goal_distance:
+        parts.append(buf["goal_distance"].reshape(B, N, 1))
+    if include_blocking_pressure:
+        parts.append(buf["blocking_prev"].reshape(B, N, 1))
+    if include_action_mask:
+        parts.append(buf["action_mask"].astype(np.float32))
+    return np.concatenate(parts, axis=2).astype(np.float32)
 
 
 def flat_obs(res: StepResult, include_goal_distance=False, include_blocking_pressure=True,
