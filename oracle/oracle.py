@@ -367,21 +367,27 @@ def flat_obs(res: StepResult, include_goal_distance=False, include_blocking_pres
     return np.concatenate(parts, axis=1).astype(np.float32)
 
 
+def bench_envs(env_config: dict, grid: np.ndarray, num_envs: int, deterministic_layout=None) -> list:
+    envs = [OracleEnv(env_config, grid, seed=int(env_config.get("seed") or 0) + i) for i in range(num_envs)]
+    if deterministic_layout is not None:
+        for e in envs:
+            e.set_layout(*deterministic_layout)
+    return envs
+
+
 def bench_run(env_config: dict, grid: np.ndarray, num_envs: int, steps: int, mode: str = "random",
-              deterministic_layout=None, action_seed: int = 999, threads: int | None = None):
+              deterministic_layout=None, action_seed: int = 999, threads: int | None = None, envs: list | None = None):
     """Time the oracle's benchmark loop (mirrors scripts/benchmark_multi_agent_env.py:59-107).
 
-    Returns (env_steps, episodes, elapsed_s, threads)."""
+    Returns (env_steps, episodes, elapsed_s, threads).  ``envs`` (from :func:`bench_envs`) lets
+    repeated samples reuse the same env objects."""
     import time
 
     threads = threads or len(os.sched_getaffinity(0))
-    envs = [OracleEnv(env_config, grid, seed=int(env_config.get("seed") or 0) + i)
-            for i in range(num_envs)]
-    det = 0
-    if deterministic_layout is not None:
-        det = 1
-        for e in envs:
-            e.set_layout(*deterministic_layout)
+    if envs is None:
+        envs = bench_envs(env_config, grid, num_envs, deterministic_layout)
+    num_envs = len(envs)
+    det = 1 if deterministic_layout is not None else 0
     arr = (C.c_void_p * num_envs)(*[e.handle for e in envs])
     eps = C.c_int64(0)
     cs = C.c_uint64(0)

@@ -60,7 +60,7 @@ def _run_parity(cfg, grid, B, steps, seed, policy="random", per_env_grid=False, 
         out = env.step(torch.from_numpy(acts), goal_rank=torch.from_numpy(ranks) if lifelong else None)
         got = gpu_channels(env, out)
         ref = dict(ob.buf)
-        ref.update(ob.state())
+        ref.update({k: v for k, v in ob.state().items() if k != "blocking_prev"})
         ref["flat_obs"] = flat_obs_batch(ob.buf, True, True, True)
         assert_batch_equal(got, ref, ORACLE_STEP_KEYS + STATE_KEYS + ("flat_obs",), f"step {s}", lifelong, lock)
         done = (ob.buf["terminated"] | ob.buf["truncated"]).astype(np.uint8)
