@@ -297,9 +297,12 @@ def run_b200(args, rank: int, local_rank: int, world: int):
 
     # ---- reduce over ranks (max time), metric all-reduce off the step path
     t = torch.tensor([ms_total, kernel_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    nl = torch.tensor([float(launches)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(nl, op=dist.ReduceOp.SUM)
     ms_total, kernel_ms, e2e_ms = (float(x) for x in t.tolist())
+    launches = int(nl.item())
     mvec = envs[0].metrics_vector().clone()
     for e in envs[1:]:
         mvec += e.metrics_vector()

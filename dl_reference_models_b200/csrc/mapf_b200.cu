@@ -83,6 +83,7 @@ struct mapf_handle {
     int wpr, map_words, fw;
     int threads;
     size_t smem_bytes;
+    mapf::SmemLayout layout;
     KernelFn step_fn, reset_fn;
     uint32_t *d_map_rows, *d_free_bits;
     int32_t *d_num_free;
@@ -210,6 +211,7 @@ void fill_params(const mapf_handle *h, mapf::KParams &p) {
     p.env_words = reinterpret_cast<int4 *>(h->st.env_words);
     p.env_metrics = h->st.env_metrics;
     p.err_bits = h->d_err;
+    p.L = h->layout;
 }
 
 void fill_outputs(mapf::KParams &p, const mapf_outputs *o) {
@@ -321,11 +323,12 @@ int mapf_create(const mapf_config *cfg, mapf_handle **out) {
     h->reset_fn = pick_reset(h->G, h->SR);
     h->threads = 0;
     for (int t = 256; t >= 32; t >>= 1) {
-        mapf::SmemLayout L = mapf::make_layout(h->G, h->V2, c.num_agents, h->wpr, c.rows, h->fw,
+        mapf::SmemLayout L = mapf::make_layout(h->G, h->V2, c.num_agents, h->wpr, c.rows, c.cols, h->SR, h->fw,
                                                c.per_env_maps != 0, t);
         if ((size_t)L.total_words * 4 <= kMaxSmem) {
             h->threads = t;
             h->smem_bytes = (size_t)L.total_words * 4;
+            h->layout = L;
             break;
         }
     }

@@ -26,43 +26,6 @@ constexpr int PAD = MAPF_MAX_SENSOR_RANGE;  // obstacle padding around the map i
 constexpr uint32_t NOCELL = 0x7FFF7FFFu;    // packed (row, col) that never matches a real cell
 constexpr uint32_t LFAR = 0x40000000u;      // linear code of an absent agent (far from any window)
 
-struct KParams {
-    int B, N, R, C;
-    int steps_per_episode, lifelong, lock_enabled, dw, lw, nearby, min_nb, eps_floor;
-    int normalize, deterministic, per_env_maps, auto_reset;
-    int observe_only;  // reset kernel: rebuild the observation channels from the current state, write nothing else
-    long long env_id_base;
-    unsigned long long seed;
-    float den0, den1;  // ENV:152-155
-    // map tables (device).  Shared map: one copy; per-env maps: B copies, strides below.
-    const uint32_t *map_rows;   // [(R+2*PAD) * wpr] bit (c+PAD) of padded row (r+PAD) = obstacle/OOB
-    const uint32_t *free_bits;  // [fw] bit (r*C+c) = free cell
-    const int32_t *num_free;    // [1] or [B]
-    int wpr, map_words, fw;
-    // state
-    uint32_t *positions, *goals, *starts;  // int16 pairs viewed as u32: row | col << 16
-    uint8_t *agent_flags;
-    uint32_t *lock_gp, *lock_mv, *lock_fm;
-    int16_t *lock_dist;
-    int4 *env_words;  // [B, 4] int4 = 16 words
-    double *env_metrics;
-    // step / reset inputs
-    const int8_t *actions;
-    const uint32_t *goal_override;  // int16 pairs
-    const int32_t *goal_rank;
-    const uint8_t *reset_mask;
-    const uint32_t *starts_override, *goals_override;
-    // outputs
-    uint8_t *o_local_obs;
-    int8_t *o_action_mask;
-    float2 *o_goal_delta;
-    uint8_t *o_blocking_prev;
-    float *o_reward;
-    uint8_t *o_terminated, *o_truncated, *o_step_flags, *o_agent_step_flags;
-    int4 *o_info;  // [B, 4] int4 = MAPF_INFO_WORDS int32
-    uint32_t *err_bits;
-};
-
 // ------------------------------------------------------------------ Philox4x32-10
 struct Philox {
     uint32_t k0, k1;
@@ -119,19 +82,63 @@ __device__ __forceinline__ int select_kth(const uint32_t *bm, int words, int k) 
 // the staging buffers for the byte outputs.
 struct SmemLayout {
     int map_rows_off, free_off;    // CTA-wide (shared map)
+    int gdt_off, gdt_words;        // CTA-wide goal-delta table: (2R-1) row quotients, then (2C-1) col quotients
     int grp_off, grp_words;        // per group block
     int g_new, g_snap, g_goal, g_int, g_delta, g_scratch, g_map, g_free;  // offsets inside a group block
+    int g_rowm, g_colm, g_growm, g_gcolm, g_mask_words;  // agent / goal bucket masks (padded by KB on both sides)
     int stage_off, stage_words;    // per warp staging (obs + mask), 16-byte aligned
     int total_words;
 };
 
-__host__ __device__ inline SmemLayout make_layout(int G, int V2, int N, int wpr, int R, int fw,
+struct KParams {
+    int B, N, R, C;
+    int steps_per_episode, lifelong, lock_enabled, dw, lw, nearby, min_nb, eps_floor;
+    int normalize, deterministic, per_env_maps, auto_reset;
+    int observe_only;  // reset kernel: rebuild the observation channels from the current state, write nothing else
+    long long env_id_base;
+    unsigned long long seed;
+    float den0, den1;  // ENV:152-155
+    // map tables (device).  Shared map: one copy; per-env maps: B copies, strides below.
+    const uint32_t *map_rows;   // [(R+2*PAD) * wpr] bit (c+PAD) of padded row (r+PAD) = obstacle/OOB
+    const uint32_t *free_bits;  // [fw] bit (r*C+c) = free cell
+    const int32_t *num_free;    // [1] or [B]
+    int wpr, map_words, fw;
+    // state
+    uint32_t *positions, *goals, *starts;  // int16 pairs viewed as u32: row | col << 16
+    uint8_t *agent_flags;
+    uint32_t *lock_gp, *lock_mv, *lock_fm;
+    int16_t *lock_dist;
+    int4 *env_words;  // [B, 4] int4 = 16 words
+    double *env_metrics;
+    // step / reset inputs
+    const int8_t *actions;
+    const uint32_t *goal_override;  // int16 pairs
+    const int32_t *goal_rank;
+    const uint8_t *reset_mask;
+    const uint32_t *starts_override, *goals_override;
+    // outputs
+    uint8_t *o_local_obs;
+    int8_t *o_action_mask;
+    float2 *o_goal_delta;
+    uint8_t *o_blocking_prev;
+    float *o_reward;
+    uint8_t *o_terminated, *o_truncated, *o_step_flags, *o_agent_step_flags;
+    int4 *o_info;  // [B, 4] int4 = MAPF_INFO_WORDS int32
+    uint32_t *err_bits;
+    SmemLayout L;  // computed once on the host (mapf_create)
+};
+
+// bucket-mask padding: interactions reach SR + 1 cells (snapshot positions differ from final ones by <= 1)
+__host__ __device__ constexpr int bucket_pad(int sr) { return sr + 1; }
+
+__host__ __device__ inline SmemLayout make_layout(int G, int V2, int N, int wpr, int R, int C, int SR, int fw,
                                                   int per_env_maps, int threads) {
     SmemLayout L;
     int map_words = (R + 2 * PAD) * wpr;
     int o = 0;
     L.map_rows_off = o; o += per_env_maps ? 0 : map_words;
     L.free_off = o; o += per_env_maps ? 0 : fw;
+    L.gdt_off = o; L.gdt_words = (2 * R - 1) + (2 * C - 1); o += L.gdt_words;
     o = (o + 3) & ~3;
     int g = 0;
     int GA = G;  // arrays padded to G entries (G is a multiple of 4)
@@ -140,6 +147,13 @@ __host__ __device__ inline SmemLayout make_layout(int G, int V2, int N, int wpr,
     L.g_goal = g; g += GA;
     L.g_int = g; g += GA;
     L.g_delta = g; g += GA;
+    const int KB = bucket_pad(SR);
+    L.g_rowm = g; g += R + 2 * KB;
+    L.g_colm = g; g += C + 2 * KB;
+    L.g_growm = g; g += R + 2 * KB;
+    L.g_gcolm = g; g += C + 2 * KB;
+    g = (g + 3) & ~3;
+    L.g_mask_words = g - L.g_rowm;
     L.g_scratch = g; g += fw;
     L.g_map = g; g += per_env_maps ? map_words : 0;
     L.g_free = g; g += per_env_maps ? fw : 0;
@@ -153,7 +167,6 @@ __host__ __device__ inline SmemLayout make_layout(int G, int V2, int N, int wpr,
     L.stage_words = sw;
     L.stage_off = o; o += sw * (threads / 32);
     L.total_words = o;
-    (void)N;
     return L;
 }
 
@@ -162,6 +175,12 @@ __host__ __device__ inline SmemLayout make_layout(int G, int V2, int N, int wpr,
 __device__ __forceinline__ void warp_copy_out(uint8_t *dst, const uint8_t *stage, int nbytes, int lane) {
     uintptr_t d = (uintptr_t)dst;
     int phase = (int)(d & 15);
+    if (phase == 0 && (nbytes & 15) == 0) {  // the common case: whole 16-byte chunks, aligned
+        const uint4 *s4 = reinterpret_cast<const uint4 *>(stage);
+        uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+        for (int i = lane; i < (nbytes >> 4); i += 32) d4[i] = s4[i];
+        return;
+    }
     const uint8_t *src = stage + phase;  // src[i] <-> dst[i]
     int head = phase ? 16 - phase : 0;
     if (head > nbytes) head = nbytes;
@@ -245,6 +264,63 @@ __device__ __forceinline__ void pair_loop(const uint32_t *s_new, const uint32_t 
     (void)my_new_packed;
 }
 
+// Bucket masks: rowm[r + KB] / colm[c + KB] hold one bit per agent whose (final) row / column is r / c.
+// OR-ing 2K+1 consecutive entries of each and AND-ing the two gives every agent inside the
+// (2K+1)^2 box around a cell -- the only agents a lane can interact with -- in O(K) instead of O(N).
+template <int K, int KB>
+__device__ __forceinline__ uint32_t gather_box(const uint32_t *rowm, const uint32_t *colm, int r, int c) {
+    uint32_t mr = 0, mc = 0;
+#pragma unroll
+    for (int d = 0; d <= 2 * K; ++d) {
+        mr |= rowm[r + (KB - K) + d];
+        mc |= colm[c + (KB - K) + d];
+    }
+    return mr & mc;
+}
+
+// Same outputs as pair_loop<G, SR, true>, visiting only the candidate agents.
+template <int G, int SR>
+__device__ __forceinline__ void scan_candidates(const uint32_t *s_new, const uint32_t *s_snap,
+                                                const uint32_t *s_goal, const uint32_t *s_int,
+                                                const uint32_t *s_delta, int gl, uint32_t cand, uint32_t gcand,
+                                                uint32_t my_new_lin, uint32_t my_intended, bool failed,
+                                                int nearby, PairOut<G, SR, true> &o) {
+    constexpr int V = 2 * SR + 1;
+    using WB = typename WinBits<V>::type;
+    o.occ = 0; o.xgoal = 0; o.nbmask = 0; o.nbcount = 0; o.red = 0; o.colocated = 0;
+    o.wf_next = -1; o.intent_hit = false;
+    const uint32_t origin = my_new_lin - (uint32_t)(SR * 1024 + SR);
+    const uint32_t nb_origin = my_new_lin - (uint32_t)(nearby * 1024 + nearby);
+    const uint32_t nb_side = 2u * (uint32_t)nearby;
+    while (cand) {
+        const int a = __ffs(cand) - 1;
+        cand &= cand - 1;
+        const uint32_t an = s_new[a];
+        const uint32_t ps = (a <= gl) ? an : s_snap[a];  // snapshot position of agent a as seen by me (F3)
+        uint32_t d = ps - origin;
+        uint32_t t1 = d & 1023u, t2 = d >> 10;
+        if (t1 < (uint32_t)V && t2 < (uint32_t)V) o.occ |= (WB)1 << (t2 * V + t1);
+        d = an - nb_origin;
+        t1 = d & 1023u; t2 = d >> 10;
+        if (t1 <= nb_side && t2 <= nb_side) {
+            const int m = abs((int)t1 - nearby) + abs((int)t2 - nearby);
+            if (m <= nearby) {
+                if (m > 0) { o.nbmask |= 1u << a; o.nbcount++; o.red += (int)s_delta[a]; }
+                else o.colocated++;
+            }
+        }
+        if (s_int[a] == my_new_lin) o.intent_hit = true;
+        if (failed && an == my_intended) o.wf_next = a;
+    }
+    while (gcand) {
+        const int a = __ffs(gcand) - 1;
+        gcand &= gcand - 1;
+        const uint32_t d = s_goal[a] - origin;
+        const uint32_t t1 = d & 1023u, t2 = d >> 10;
+        if (t1 < (uint32_t)V && t2 < (uint32_t)V) o.xgoal |= (WB)1 << (t2 * V + t1);
+    }
+}
+
 // Window value bytes (ENV:730-745 priority) + action mask (ENV:761-771) into the staging area.
 template <int SR>
 __device__ __forceinline__ uint32_t emit_window(const uint32_t *rows, int wpr, int r, int c,
@@ -273,11 +349,20 @@ __device__ __forceinline__ uint32_t emit_window(const uint32_t *rows, int wpr, i
     const WB g3 = own & ~blocked;
     const WB g4 = xgoal & ~blocked & ~own;
     if (stage_obs) {
+        // cell code = b0 + 2*b1 + 4*b2 with b0 = obstacle|own goal, b1 = agent|own goal, b2 = other goal
+        // (1 = 001, 2 = 010, 3 = 011, 4 = 100).  Four cells at a time: a nibble times 0x00204081 puts
+        // bit j of the nibble at bit 8*j, so three multiplies build four output bytes.
+        const WB b0 = obst | g3, b1 = agent | g3, b2 = g4;
 #pragma unroll
-        for (int k = 0; k < V * V; ++k) {
-            uint32_t v = (uint32_t)((obst >> k) & 1) + 2u * (uint32_t)((agent >> k) & 1) +
-                         3u * (uint32_t)((g3 >> k) & 1) + 4u * (uint32_t)((g4 >> k) & 1);
-            stage_obs[k] = (uint8_t)v;
+        for (int k = 0; k < V * V; k += 4) {
+            const uint32_t n0 = (uint32_t)(b0 >> k) & 15u, n1 = (uint32_t)(b1 >> k) & 15u,
+                           n2 = (uint32_t)(b2 >> k) & 15u;
+            const uint32_t w = ((n0 * 0x00204081u) & 0x01010101u) | (((n1 * 0x00204081u) & 0x01010101u) << 1) |
+                               (((n2 * 0x00204081u) & 0x01010101u) << 2);
+            stage_obs[k] = (uint8_t)w;
+            if (k + 1 < V * V) stage_obs[k + 1] = (uint8_t)(w >> 8);
+            if (k + 2 < V * V) stage_obs[k + 2] = (uint8_t)(w >> 16);
+            if (k + 3 < V * V) stage_obs[k + 3] = (uint8_t)(w >> 24);
         }
     }
     constexpr int ctr = SR * V + SR;
@@ -289,12 +374,20 @@ __device__ __forceinline__ uint32_t emit_window(const uint32_t *rows, int wpr, i
     return m;
 }
 
-// ENV:330-335
-__device__ __forceinline__ float2 goal_delta(uint32_t goal, uint32_t pos, int normalize, float den0,
-                                             float den1) {
-    float d0 = (float)(prow(goal) - prow(pos)), d1 = (float)(pcol(goal) - pcol(pos));
-    if (normalize) { d0 = __fdiv_rn(d0, den0); d1 = __fdiv_rn(d1, den1); }
-    return make_float2(d0, d1);
+// ENV:330-335.  The quotients (goal - pos) / denominator take only 2R-1 / 2C-1 distinct values; the
+// CTA tabulates them once with IEEE division (__fdiv_rn), lanes look them up.
+__device__ __forceinline__ void fill_goal_delta_table(float *gdt, int R, int C, int normalize, float den0,
+                                                      float den1, int tid, int nthreads) {
+    const int nr = 2 * R - 1, n = nr + 2 * C - 1;
+    for (int i = tid; i < n; i += nthreads) {
+        const bool row = i < nr;
+        const float d = (float)(row ? i - (R - 1) : i - nr - (C - 1));
+        gdt[i] = normalize ? __fdiv_rn(d, row ? den0 : den1) : d;
+    }
+}
+__device__ __forceinline__ float2 goal_delta(const float *gdt, int R, int C, uint32_t goal, uint32_t pos) {
+    const int i0 = prow(goal) - prow(pos) + (R - 1), i1 = pcol(goal) - pcol(pos) + (C - 1) + 2 * R - 1;
+    return make_float2(gdt[i0], gdt[i1]);
 }
 
 // Draw 2N distinct free cells (ENV:267-282) by symmetric rejection: every slot draws uniformly;
@@ -356,10 +449,20 @@ __global__ void __launch_bounds__(256) mapf_step_kernel(const KParams p) {
     const bool env_ok = env < p.B;
     const bool act = env_ok && gl < N;
 
-    const SmemLayout L = make_layout(G, V2, N, p.wpr, p.R, p.fw, p.per_env_maps, blockDim.x);
+    constexpr int KB = bucket_pad(SR);
+    const SmemLayout &L = p.L;
     uint32_t *gsm = smem + L.grp_off + grp * L.grp_words;
     uint32_t *s_new = gsm + L.g_new, *s_snap = gsm + L.g_snap, *s_goal = gsm + L.g_goal;
     uint32_t *s_int = gsm + L.g_int, *s_delta = gsm + L.g_delta, *s_scratch = gsm + L.g_scratch;
+    uint32_t *s_rowm = gsm + L.g_rowm, *s_colm = gsm + L.g_colm;
+    uint32_t *s_growm = gsm + L.g_growm, *s_gcolm = gsm + L.g_gcolm;
+    const float *gdt = reinterpret_cast<const float *>(smem + L.gdt_off);
+    fill_goal_delta_table(reinterpret_cast<float *>(smem + L.gdt_off), p.R, p.C, p.normalize, p.den0, p.den1,
+                          tid, blockDim.x);
+    {   // clear the group's bucket masks (contiguous, 16-byte aligned, multiple of 4 words)
+        uint4 *mz = reinterpret_cast<uint4 *>(s_rowm);
+        for (int i = gl; i < (L.g_mask_words >> 2); i += G) mz[i] = make_uint4(0, 0, 0, 0);
+    }
     const uint32_t *rows, *freebm;
     if (p.per_env_maps) {
         uint32_t *mr = gsm + L.g_map, *fb = gsm + L.g_free;
@@ -370,14 +473,13 @@ __global__ void __launch_bounds__(256) mapf_step_kernel(const KParams p) {
             for (int i = gl; i < p.fw; i += G) fb[i] = fsrc[i];
         }
         rows = mr; freebm = fb;
-        __syncwarp();
     } else {
         uint32_t *mr = smem + L.map_rows_off, *fb = smem + L.free_off;
         for (int i = tid; i < p.map_words; i += blockDim.x) mr[i] = p.map_rows[i];
         for (int i = tid; i < p.fw; i += blockDim.x) fb[i] = p.free_bits[i];
         rows = mr; freebm = fb;
-        __syncthreads();
     }
+    __syncthreads();
     uint8_t *stage = reinterpret_cast<uint8_t *>(smem + L.stage_off + warp * L.stage_words);
     const int envs_per_warp = 32 / G;
     const int obs_stage_bytes = ((envs_per_warp * N * V2 + 32 + 15) / 16) * 16;
@@ -515,7 +617,7 @@ __global__ void __launch_bounds__(256) mapf_step_kernel(const KParams p) {
         }
     }
 
-    // ---------------------------------------------------------------- pair loop
+    // ---------------------------------------------------------------- interaction scan
     const uint32_t my_lin = act ? lin(newpos) : LFAR;
     s_new[gl] = my_lin;
     s_snap[gl] = act ? lin(reassigned ? newpos : pos) : LFAR;
@@ -524,10 +626,26 @@ __global__ void __launch_bounds__(256) mapf_step_kernel(const KParams p) {
     // intent of agents that have not (sticky-)reached, ENV:619-621
     s_int[gl] = (act && !(aflags & MAPF_AF_REACHED)) ? lin(intended) + 0u : LFAR + 1u;
     s_delta[gl] = (uint32_t)delta;
+    if (act) {
+        atomicOr(&s_rowm[prow(newpos) + KB], 1u << gl);
+        atomicOr(&s_colm[pcol(newpos) + KB], 1u << gl);
+        atomicOr(&s_growm[prow(goal_for_obs) + KB], 1u << gl);
+        atomicOr(&s_gcolm[pcol(goal_for_obs) + KB], 1u << gl);
+    }
     __syncwarp();
     PairOut<G, SR, true> po;
-    pair_loop<G, SR, true>(s_new, s_snap, s_goal, s_int, s_delta, gl, my_lin, newpos,
-                           failed ? lin(intended) : LFAR + 2u, failed, p.nearby, po);
+    {
+        uint32_t cand = 0, gcand = 0;
+        if (act) {
+            const uint32_t others = ((N >= 32) ? 0xFFFFFFFFu : ((1u << N) - 1u)) & ~(1u << gl);
+            // every interaction lies within SR+1 cells of my final position unless the lock
+            // neighbourhood is wider than that: then fall back to scanning all agents
+            cand = (p.nearby <= KB) ? (gather_box<KB, KB>(s_rowm, s_colm, prow(newpos), pcol(newpos)) & others) : others;
+            gcand = gather_box<SR, KB>(s_growm, s_gcolm, prow(newpos), pcol(newpos)) & others;
+        }
+        scan_candidates<G, SR>(s_new, s_snap, s_goal, s_int, s_delta, gl, cand, gcand, my_lin,
+                               failed ? lin(intended) : LFAR + 2u, failed, p.nearby, po);
+    }
 
     // ---------------------------------------------------------------- observation channels
     const int my_env_in_warp = lane / G;
@@ -541,7 +659,7 @@ __global__ void __launch_bounds__(256) mapf_step_kernel(const KParams p) {
     if (act)
         amask = emit_window<SR>(rows, p.wpr, prow(newpos), pcol(newpos), po.occ, po.xgoal,
                                 lin(goal_for_obs), my_lin, my_stage_obs);
-    float2 gd = goal_delta(goal_for_obs, newpos, p.normalize, p.den0, p.den1);
+    float2 gd = act ? goal_delta(gdt, p.R, p.C, goal_for_obs, newpos) : make_float2(0.f, 0.f);
     const uint32_t bp_prev_out = (aflags >> 2) & 1u;  // value of the previous step, ENV:322 (F5)
 
     // ---------------------------------------------------------------- lock detection, ENV:400-438,595-606
@@ -693,7 +811,7 @@ __global__ void __launch_bounds__(256) mapf_step_kernel(const KParams p) {
             if (act) {
                 amask = emit_window<SR>(rows, p.wpr, prow(st), pcol(st), pr.occ, pr.xgoal, lin(gg),
                                         lin(st), my_stage_obs);
-                if (p.o_goal_delta) p.o_goal_delta[ai] = goal_delta(gg, st, p.normalize, p.den0, p.den1);
+                if (p.o_goal_delta) p.o_goal_delta[ai] = goal_delta(gdt, p.R, p.C, gg, st);
                 if (p.o_blocking_prev) p.o_blocking_prev[ai] = 0;
             }
         }
@@ -757,10 +875,13 @@ __global__ void __launch_bounds__(256) mapf_reset_kernel(const KParams p) {
     const bool sel = env_ok && (!p.reset_mask || p.reset_mask[env] != 0);
     const bool act = sel && gl < N;
 
-    const SmemLayout L = make_layout(G, V2, N, p.wpr, p.R, p.fw, p.per_env_maps, blockDim.x);
+    const SmemLayout &L = p.L;
     uint32_t *gsm = smem + L.grp_off + grp * L.grp_words;
     uint32_t *s_new = gsm + L.g_new, *s_snap = gsm + L.g_snap, *s_goal = gsm + L.g_goal;
     uint32_t *s_int = gsm + L.g_int, *s_delta = gsm + L.g_delta;
+    const float *gdt = reinterpret_cast<const float *>(smem + L.gdt_off);
+    fill_goal_delta_table(reinterpret_cast<float *>(smem + L.gdt_off), p.R, p.C, p.normalize, p.den0, p.den1,
+                          tid, blockDim.x);
     const uint32_t *rows, *freebm;
     if (p.per_env_maps) {
         uint32_t *mr = gsm + L.g_map, *fb = gsm + L.g_free;
@@ -771,14 +892,13 @@ __global__ void __launch_bounds__(256) mapf_reset_kernel(const KParams p) {
             for (int i = gl; i < p.fw; i += G) fb[i] = fsrc[i];
         }
         rows = mr; freebm = fb;
-        __syncwarp();
     } else {
         uint32_t *mr = smem + L.map_rows_off, *fb = smem + L.free_off;
         for (int i = tid; i < p.map_words; i += blockDim.x) mr[i] = p.map_rows[i];
         for (int i = tid; i < p.fw; i += blockDim.x) fb[i] = p.free_bits[i];
         rows = mr; freebm = fb;
-        __syncthreads();
     }
+    __syncthreads();
     uint8_t *stage = reinterpret_cast<uint8_t *>(smem + L.stage_off + warp * L.stage_words);
     const int envs_per_warp = 32 / G;
     const int obs_stage_bytes = ((envs_per_warp * N * V2 + 32 + 15) / 16) * 16;
@@ -829,7 +949,7 @@ __global__ void __launch_bounds__(256) mapf_reset_kernel(const KParams p) {
 #pragma unroll
             for (int k = 0; k < 5; ++k) dst[k] = (int8_t)((amask >> k) & 1u);
         }
-        if (p.o_goal_delta) p.o_goal_delta[ai] = goal_delta(gg, st, p.normalize, p.den0, p.den1);
+        if (p.o_goal_delta) p.o_goal_delta[ai] = goal_delta(gdt, p.R, p.C, gg, st);
         if (p.observe_only) {
             if (p.o_blocking_prev) p.o_blocking_prev[ai] = (p.agent_flags[ai] >> 2) & 1u;
         } else {
