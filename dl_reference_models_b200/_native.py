@@ -15,7 +15,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 REPO = PKG.parent
 CSRC = PKG / "csrc"
-LIB_PATH = PKG / "libmapf_b200.so"
+LIB_PATH = Path(os.environ.get("MAPF_B200_LIB", PKG / "libmapf_b200.so"))
 SOURCES = (CSRC / "mapf_b200.cu", CSRC / "mapf_kernels.cuh", REPO / "include" / "mapf_b200.h")
 
 MAX_AGENTS = 32
@@ -32,7 +32,7 @@ DEV_ERR_INVALID_ACTION, DEV_ERR_NO_GOAL_CELL, DEV_ERR_TOO_FEW_CELLS = 1, 2, 4
 # env_words indices
 (W_STEP_COUNT, W_LOCK_COUNT, W_LOCK_PREV, W_GOALS_TOTAL, W_BLOCKING_TOTAL, W_DEADLOCK_EVENTS,
  W_LIVELOCK_EVENTS, W_DEADLOCK_STEPS, W_LIVELOCK_STEPS, W_RNG_COUNTER, W_EPISODE_RETURN_X2,
- W_WFG_CYCLE_STEPS, W_EPISODES) = range(13)
+ W_WFG_CYCLE_STEPS, W_EPISODES, W_LOCK_HEAD) = range(14)
 
 AF_REACHED, AF_COMPLETED_ONCE, AF_BLOCKING_PREV = 1, 2, 4
 
@@ -96,6 +96,8 @@ def nvcc_command(out: Path = LIB_PATH) -> list[str]:
 
 
 def needs_build() -> bool:
+    if "MAPF_B200_LIB" in os.environ:  # explicit library (kernel A/B experiments): never rebuild over it
+        return False
     if not LIB_PATH.exists():
         return True
     if not all(s.exists() for s in SOURCES):

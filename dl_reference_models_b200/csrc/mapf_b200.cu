@@ -84,6 +84,7 @@ struct mapf_handle {
     int threads;
     size_t smem_bytes;
     mapf::SmemLayout layout;
+    int step_grid_cap;
     KernelFn step_fn, reset_fn;
     uint32_t *d_map_rows, *d_free_bits;
     int32_t *d_num_free;
@@ -226,7 +227,9 @@ void fill_outputs(mapf::KParams &p, const mapf_outputs *o) {
 
 int launch(mapf_handle *h, KernelFn fn, const mapf::KParams &p, cudaStream_t s) {
     const int groups = h->threads / h->G;
-    const unsigned grid = (unsigned)((h->cfg.num_envs + groups - 1) / groups);
+    unsigned grid = (unsigned)((h->cfg.num_envs + groups - 1) / groups);
+    // the step kernel is persistent: one wave of resident CTAs walks over the env tiles
+    if (fn == h->step_fn && h->step_grid_cap > 0 && grid > (unsigned)h->step_grid_cap) grid = (unsigned)h->step_grid_cap;
     fn<<<grid, h->threads, h->smem_bytes, s>>>(p);
     CUDA_TRY(cudaGetLastError());
     h->launches++;
@@ -340,6 +343,16 @@ int mapf_create(const mapf_config *cfg, mapf_handle **out) {
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
     cudaError_t e2 = cudaFuncSetAttribute(reinterpret_cast<const void *>(h->reset_fn),
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
+    int nsm = 0, per_sm = 0;
+    if (e1 == cudaSuccess) e1 = cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c.device);
+    if (e1 == cudaSuccess)
+        e1 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reinterpret_cast<const void *>(h->step_fn),
+                                                           h->threads, h->smem_bytes);
+    h->step_grid_cap = nsm * (per_sm > 0 ? per_sm : 1);
+    if (const char *ov = getenv("MAPF_STEP_CTAS_PER_SM")) {  // tuning knob: 0 = one CTA per tile (not persistent)
+        const int v = atoi(ov);
+        h->step_grid_cap = v > 0 ? nsm * v : 0;
+    }
     cudaError_t e3 = cudaMalloc(&h->d_err, 4);
     if (e3 == cudaSuccess) e3 = cudaMemset(h->d_err, 0, 4);
     if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {

@@ -85,7 +85,9 @@ struct SmemLayout {
     int gdt_off, gdt_words;        // CTA-wide goal-delta table: (2R-1) row quotients, then (2C-1) col quotients
     int grp_off, grp_words;        // per group block
     int g_new, g_snap, g_goal, g_int, g_delta, g_scratch, g_map, g_free;  // offsets inside a group block
-    int g_rowm, g_colm, g_growm, g_gcolm, g_mask_words;  // agent / goal bucket masks (padded by KB on both sides)
+    int g_rowm, g_colm, g_growm, g_gcolm;   // final-position / goal bucket masks (padded by KB on both sides)
+    int g_orow, g_ocol, g_trow, g_tcol;     // old-position / move-target bucket masks (move resolution)
+    int g_mask_words;
     int stage_off, stage_words;    // per warp staging (obs + mask), 16-byte aligned
     int total_words;
 };
@@ -152,6 +154,10 @@ __host__ __device__ inline SmemLayout make_layout(int G, int V2, int N, int wpr,
     L.g_colm = g; g += C + 2 * KB;
     L.g_growm = g; g += R + 2 * KB;
     L.g_gcolm = g; g += C + 2 * KB;
+    L.g_orow = g; g += R + 2 * KB;
+    L.g_ocol = g; g += C + 2 * KB;
+    L.g_trow = g; g += R + 2 * KB;
+    L.g_tcol = g; g += C + 2 * KB;
     g = (g + 3) & ~3;
     L.g_mask_words = g - L.g_rowm;
     L.g_scratch = g; g += fw;
@@ -433,8 +439,14 @@ __device__ __forceinline__ void draw_layout(const Philox &ph, uint32_t &rng_coun
 }
 
 // ============================================================================ step kernel
+#ifndef MAPF_MOVE_CHAIN
+#define MAPF_MOVE_CHAIN 0
+#endif
+#ifndef MAPF_STEP_MIN_CTAS
+#define MAPF_STEP_MIN_CTAS 4
+#endif
 template <int G, int SR>
-__global__ void __launch_bounds__(256) mapf_step_kernel(const KParams p) {
+__global__ void __launch_bounds__(256, MAPF_STEP_MIN_CTAS) mapf_step_kernel(const KParams p) {
     constexpr int V = 2 * SR + 1, V2 = V * V;
     using WB = typename WinBits<V>::type;
     extern __shared__ __align__(16) uint32_t smem[];
@@ -442,12 +454,10 @@ __global__ void __launch_bounds__(256) mapf_step_kernel(const KParams p) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int gl = tid % G, grp = tid / G;
     const int groups = blockDim.x / G;
-    const int env = blockIdx.x * groups + grp;
     const unsigned gbase = (unsigned)(lane / G) * G;
     const unsigned gmask = (G == 32) ? full : (((1u << G) - 1u) << gbase);
     const int N = p.N;
-    const bool env_ok = env < p.B;
-    const bool act = env_ok && gl < N;
+    const uint32_t mybit = 1u << gl, lower = mybit - 1u;
 
     constexpr int KB = bucket_pad(SR);
     const SmemLayout &L = p.L;
@@ -456,24 +466,14 @@ __global__ void __launch_bounds__(256) mapf_step_kernel(const KParams p) {
     uint32_t *s_int = gsm + L.g_int, *s_delta = gsm + L.g_delta, *s_scratch = gsm + L.g_scratch;
     uint32_t *s_rowm = gsm + L.g_rowm, *s_colm = gsm + L.g_colm;
     uint32_t *s_growm = gsm + L.g_growm, *s_gcolm = gsm + L.g_gcolm;
+    uint32_t *s_orow = gsm + L.g_orow, *s_ocol = gsm + L.g_ocol;
+    uint32_t *s_trow = gsm + L.g_trow, *s_tcol = gsm + L.g_tcol;
     const float *gdt = reinterpret_cast<const float *>(smem + L.gdt_off);
+    // CTA-wide tables, loaded once; the CTA then walks over tiles of `groups` envs (persistent grid)
     fill_goal_delta_table(reinterpret_cast<float *>(smem + L.gdt_off), p.R, p.C, p.normalize, p.den0, p.den1,
                           tid, blockDim.x);
-    {   // clear the group's bucket masks (contiguous, 16-byte aligned, multiple of 4 words)
-        uint4 *mz = reinterpret_cast<uint4 *>(s_rowm);
-        for (int i = gl; i < (L.g_mask_words >> 2); i += G) mz[i] = make_uint4(0, 0, 0, 0);
-    }
-    const uint32_t *rows, *freebm;
-    if (p.per_env_maps) {
-        uint32_t *mr = gsm + L.g_map, *fb = gsm + L.g_free;
-        if (env_ok) {
-            const uint32_t *src = p.map_rows + (size_t)env * p.map_words;
-            for (int i = gl; i < p.map_words; i += G) mr[i] = src[i];
-            const uint32_t *fsrc = p.free_bits + (size_t)env * p.fw;
-            for (int i = gl; i < p.fw; i += G) fb[i] = fsrc[i];
-        }
-        rows = mr; freebm = fb;
-    } else {
+    const uint32_t *rows = gsm + L.g_map, *freebm = gsm + L.g_free;
+    if (!p.per_env_maps) {
         uint32_t *mr = smem + L.map_rows_off, *fb = smem + L.free_off;
         for (int i = tid; i < p.map_words; i += blockDim.x) mr[i] = p.map_rows[i];
         for (int i = tid; i < p.fw; i += blockDim.x) fb[i] = p.free_bits[i];
@@ -485,6 +485,25 @@ __global__ void __launch_bounds__(256) mapf_step_kernel(const KParams p) {
     const int obs_stage_bytes = ((envs_per_warp * N * V2 + 32 + 15) / 16) * 16;
     uint8_t *stage_obs = stage;
     uint8_t *stage_mask = stage + obs_stage_bytes;
+    uint32_t errs = 0;
+    const int ntiles = (p.B + groups - 1) / groups;
+
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int env = tile * groups + grp;
+    const bool env_ok = env < p.B;
+    const bool act = env_ok && gl < N;
+    {   // clear the group's bucket masks (contiguous, 16-byte aligned, multiple of 4 words)
+        uint4 *mz = reinterpret_cast<uint4 *>(s_rowm);
+        for (int i = gl; i < (L.g_mask_words >> 2); i += G) mz[i] = make_uint4(0, 0, 0, 0);
+    }
+    if (p.per_env_maps && env_ok) {
+        uint32_t *mr = gsm + L.g_map, *fb = gsm + L.g_free;
+        const uint32_t *src = p.map_rows + (size_t)env * p.map_words;
+        for (int i = gl; i < p.map_words; i += G) mr[i] = src[i];
+        const uint32_t *fsrc = p.free_bits + (size_t)env * p.fw;
+        for (int i = gl; i < p.fw; i += G) fb[i] = fsrc[i];
+    }
+    __syncwarp();
 
     // ---------------------------------------------------------------- load
     const size_t ai = (size_t)(env_ok ? env : 0) * N + (gl < N ? gl : 0);
@@ -492,7 +511,6 @@ __global__ void __launch_bounds__(256) mapf_step_kernel(const KParams p) {
     uint32_t goal = act ? p.goals[ai] : NOCELL - 1;
     uint32_t aflags = act ? p.agent_flags[ai] : 0u;
     int action = (act && p.actions) ? (int)p.actions[ai] : 0;
-    uint32_t errs = 0;
     if (action < 0 || action > 4) { errs |= MAPF_DEV_ERR_INVALID_ACTION; action = 0; }
     int4 w0 = make_int4(0, 0, 0, 0), w1 = w0, w2 = w0, w3 = w0;
     if (env_ok) {
@@ -506,6 +524,20 @@ __global__ void __launch_bounds__(256) mapf_step_kernel(const KParams p) {
     uint32_t rng_counter = (uint32_t)w2.y;
     int ep_return_x2 = w2.z, wfg_steps = w2.w;
     int episodes = w3.x;
+    int lock_head = w3.y;  // ring slot the next distance goes to (MAPF_W_LOCK_HEAD)
+    // Lock history is fetched here, ahead of the warp barriers of the move resolution, so that its
+    // DRAM latency overlaps with them (the compiler cannot hoist loads across __syncwarp).
+    uint32_t gpr = 0, mvr = 0, fmr = 0;
+    int ring_old = 0;
+    const int count_after = lock_count + 1;
+    if (lock_head < 0 || lock_head >= p.lw) lock_head = 0;
+    const int slot_new = lock_head;
+    const int slot_next = (lock_head + 1 == p.lw) ? 0 : lock_head + 1;
+    if (p.lock_enabled && act) {
+        gpr = p.lock_gp[ai]; mvr = p.lock_mv[ai]; fmr = p.lock_fm[ai];
+        if (count_after >= p.lw && p.lw > 1)  // slot_next still holds the oldest row of the window, ENV:432
+            ring_old = (int)p.lock_dist[((size_t)env * p.lw + slot_next) * N + gl];
+    }
 
     // ---------------------------------------------------------------- move resolution, ENV:502-526
     const int r0 = prow(pos), c0 = pcol(pos);
@@ -513,6 +545,9 @@ __global__ void __launch_bounds__(256) mapf_step_kernel(const KParams p) {
     const int nc = c0 + (action == 2) - (action == 4);
     const uint32_t intended = pack_rc(nr, nc);  // ENV:514-515 (kept even when invalid)
     bool wants = act && action != 0 && !map_blocked(rows, p.wpr, nr, nc);
+#if MAPF_MOVE_CHAIN
+    // The reference's sequential agent loop as an N-step shuffle/ballot chain: at agent i's turn its
+    // target is held iff some other lane's *current* cell equals it.
     const uint32_t target = wants ? intended : NOCELL;
     uint32_t cur = pos;
 #pragma unroll
@@ -524,6 +559,44 @@ __global__ void __launch_bounds__(256) mapf_step_kernel(const KParams p) {
         if (gl == i && t != NOCELL && !blocked) cur = t;
     }
     const uint32_t newpos = cur;
+#else
+    // Sequential semantics without the N-step chain: agent i is blocked iff its target cell is held
+    // at its turn, i.e. by a higher-index agent that has not moved yet, by a lower-index agent that
+    // stayed, or by a lower-index agent that moved in first (same target).  Occupants and co-claimants
+    // of a cell come from row/column bucket masks (their AND is the exact cell); dependencies point to
+    // lower indices only, so the fix-point below settles in (longest follow-chain) rounds.
+    if (act) {
+        atomicOr(&s_orow[r0 + KB], mybit);
+        atomicOr(&s_ocol[c0 + KB], mybit);
+    }
+    if (wants) {
+        atomicOr(&s_trow[nr + KB], mybit);
+        atomicOr(&s_tcol[nc + KB], mybit);
+    }
+    __syncwarp();
+    uint32_t occ_lo = 0, dup_lo = 0;
+    bool blocked_hi = false;
+    if (wants) {
+        const uint32_t occm = s_orow[nr + KB] & s_ocol[nc + KB] & ~mybit;
+        blocked_hi = (occm & ~lower) != 0;
+        occ_lo = occm & lower;
+        dup_lo = s_trow[nr + KB] & s_tcol[nc + KB] & lower;
+    }
+    const uint32_t deps = occ_lo | dup_lo;
+    bool known = !wants || blocked_hi || deps == 0;
+    bool moves = wants && !blocked_hi && deps == 0;
+    for (;;) {
+        const unsigned kb = __ballot_sync(full, known);
+        if (kb == full) break;
+        const unsigned Kn = (kb & gmask) >> gbase;
+        const unsigned Mv = (__ballot_sync(full, moves) & gmask) >> gbase;
+        if (!known) {
+            const bool blk = ((occ_lo & Kn & ~Mv) | (dup_lo & Mv)) != 0;  // a settled dependency already blocks
+            if (blk || (deps & ~Kn) == 0) { known = true; moves = !blk; }
+        }
+    }
+    const uint32_t newpos = moves ? intended : pos;
+#endif
     const bool moved = act && (newpos != pos);
     const bool failed = act && action != 0 && !moved;  // ENV:583
 
@@ -594,27 +667,19 @@ __global__ void __launch_bounds__(256) mapf_step_kernel(const KParams p) {
     const bool reached_goal_scratch = p.lifelong ? false : cur_on_goal;
 
     // ---------------------------------------------------------------- lock bookkeeping, ENV:581-594
-    uint32_t gpr = 0, mvr = 0, fmr = 0;
     int dist_now = abs(prow(goal_new) - prow(newpos)) + abs(pcol(goal_new) - pcol(newpos));
     int delta = 0;
-    const int count_after = lock_count + 1;
     if (p.lock_enabled) {
-        if (act) { gpr = p.lock_gp[ai]; mvr = p.lock_mv[ai]; fmr = p.lock_fm[ai]; }
         const bool prev_on_goal = p.lifelong ? false : (pos == goal_new);
         const bool gp = p.lifelong ? gstep : (!prev_on_goal && cur_on_goal);
         gpr = (gpr << 1) | (gp ? 1u : 0u);
         mvr = (mvr << 1) | (moved ? 1u : 0u);
         fmr = (fmr << 1) | (failed ? 1u : 0u);
-        const int LW = p.lw;
-        const int slot_new = lock_count % LW;
         if (act) {
-            int16_t *ring = p.lock_dist + ((size_t)env * LW) * N + gl;
-            if (count_after >= LW && LW > 1) {
-                const int slot_old = (lock_count + 1) % LW;  // oldest row of the window, ENV:432
-                delta = (int)ring[(size_t)slot_old * N] - dist_now;
-            }
-            ring[(size_t)slot_new * N] = (int16_t)dist_now;
+            if (count_after >= p.lw && p.lw > 1) delta = ring_old - dist_now;
+            p.lock_dist[((size_t)env * p.lw + slot_new) * N + gl] = (int16_t)dist_now;
         }
+        lock_head = slot_next;
     }
 
     // ---------------------------------------------------------------- interaction scan
@@ -650,7 +715,7 @@ __global__ void __launch_bounds__(256) mapf_step_kernel(const KParams p) {
     // ---------------------------------------------------------------- observation channels
     const int my_env_in_warp = lane / G;
     uint8_t *my_stage_obs = nullptr;
-    const size_t warp_env0 = (size_t)blockIdx.x * groups + (size_t)(warp * envs_per_warp);
+    const size_t warp_env0 = (size_t)tile * groups + (size_t)(warp * envs_per_warp);
     if (p.o_local_obs) {
         uint8_t *dst0 = p.o_local_obs + warp_env0 * N * V2;
         my_stage_obs = stage_obs + ((uintptr_t)dst0 & 15) + (size_t)(my_env_in_warp * N + gl) * V2;
@@ -797,7 +862,7 @@ __global__ void __launch_bounds__(256) mapf_step_kernel(const KParams p) {
             else { st = newpos; gg = goal_new; }
             out_pos = st; out_goal = gg;
             aflags = 0; gpr = mvr = fmr = 0;
-            step_count = 0; lock_count = 0; lock_prev = 0; goals_total = 0; blocking_total = 0;
+            step_count = 0; lock_count = 0; lock_head = 0; lock_prev = 0; goals_total = 0; blocking_total = 0;
             dl_events = ll_events = dl_steps = ll_steps = 0; ep_return_x2 = 0; wfg_steps = 0;
             // first observation of the next episode (final-state, no staggering at reset)
             const uint32_t l = act ? lin(st) : LFAR;
@@ -852,8 +917,10 @@ __global__ void __launch_bounds__(256) mapf_step_kernel(const KParams p) {
         ew[0] = make_int4(step_count, lock_count, lock_prev, goals_total);
         ew[1] = make_int4(blocking_total, dl_events, ll_events, dl_steps);
         ew[2] = make_int4(ll_steps, (int)rng_counter, ep_return_x2, wfg_steps);
-        ew[3] = make_int4(episodes, w3.y, w3.z, w3.w);
+        ew[3] = make_int4(episodes, lock_head, w3.z, w3.w);
     }
+    __syncwarp();
+    }  // tile loop
     errs = __reduce_or_sync(full, errs);
     if (errs && lane == 0) atomicOr(p.err_bits, errs);
 }
@@ -977,7 +1044,7 @@ __global__ void __launch_bounds__(256) mapf_reset_kernel(const KParams p) {
         ew[0] = make_int4(0, 0, 0, 0);
         ew[1] = make_int4(0, 0, 0, 0);
         ew[2] = make_int4(0, (int)rng_counter, 0, 0);
-        ew[3] = w3;
+        ew[3] = make_int4(w3.x, 0, w3.z, w3.w);
     }
     (void)stage_obs; (void)stage_mask; (void)my_env_in_warp; (void)warp_env0;
     errs = __reduce_or_sync(full, errs);

@@ -320,6 +320,7 @@ class ReferenceModel(MultiAgentEnv):
         self._episode_deadlock_steps = self._episode_livelock_steps = 0.0
         self._deadlock_state_prev = self._livelock_state_prev = False
         self._hs["env_words"][0, nat.W_LOCK_COUNT] = 0
+        self._hs["env_words"][0, nat.W_LOCK_HEAD] = 0
         self._lock_hist_count = 0
         self._upload(self._MIRRORED + ("lock_goal_progress", "lock_moved", "lock_failed_move", "lock_distance"))
 

@@ -87,7 +87,7 @@ enum {
     MAPF_W_EPISODE_RETURN_X2,   /* 2 * sum of rewards of all agents this episode (exact integer) */
     MAPF_W_WFG_CYCLE_STEPS,     /* steps of this episode with a wait-for-graph cycle */
     MAPF_W_EPISODES,            /* finished episodes of this env */
-    MAPF_W_RESERVED0,
+    MAPF_W_LOCK_HEAD,           /* ENV:120 _lock_hist_head of the distance ring (slot of the next row) */
     MAPF_W_RESERVED1,
     MAPF_W_RESERVED2,
     MAPF_ENV_WORDS
