@@ -9,8 +9,8 @@ Workload (BASELINE config 3, SURVEY 8d "C3"): 65 536 envs x 16 agents PER GPU on
 30 % i.i.d. obstacles (map seed 2026), sensor_range 2, lifelong goal resampling, lock metrics on,
 256 steps per episode with the reset inside the step launch (like run_benchmark's `if done:
 reset()`, scripts/benchmark_multi_agent_env.py:89-95), actions uniform over the valid mask.
-A "step" is one pass of the hot path over the whole batch: the action-sampler kernel plus the
-step kernel.  Envs shard independently across GPUs (weak scaling, no data-path collective); the one
+A "step" is one pass of the hot path over the whole batch: ONE launch of the step kernel, which
+also draws the next step's masked-uniform actions (the benchmark sampler fused in).  Envs shard independently across GPUs (weak scaling, no data-path collective); the one
 NCCL all-reduce (episode/lock metric sums) runs once after the timed region.
 
 Prints ONE JSON line (rank 0).  `value` = agent-steps/s with inputs resident in HBM; `e2e` = the
@@ -229,13 +229,14 @@ def run_b200(args, rank: int, local_rank: int, world: int):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def one_step(i):
-        e = envs[i % len(envs)]
-        a = e.sample_actions(masked=True)
-        e.step(a, auto_reset=True)
+    # the benchmark's masked action sampler is fused into the step launch: one kernel per env step
+    for e in envs:
+        e._next = e.sample_actions(masked=True)
+        e.fuse_sampler("masked")
 
     for i in range(W):
-        one_step(i)
+        e = envs[i % len(envs)]
+        e.step(e._next, auto_reset=True)
     ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -249,9 +250,8 @@ def run_b200(args, rank: int, local_rank: int, world: int):
     t_begin.record()
     for i in range(K):
         e = envs[(W + i) % len(envs)]
-        a = e.sample_actions(masked=True)
         ev0[i].record()
-        e.step(a, auto_reset=True)
+        e.step(e._next, auto_reset=True)
         ev1[i].record()
     t_end.record()
     barrier()
@@ -266,6 +266,7 @@ def run_b200(args, rank: int, local_rank: int, world: int):
     # ---- e2e: the C ABI's host-buffer entry point, pinned host memory, copies inside the timed region
     import ctypes as C
     e2e_env = envs[0]
+    e2e_env.fuse_sampler(None)
     host_out = {
         "local_obs": torch.empty((B, N, V, V), dtype=torch.uint8).pin_memory(),
         "action_mask": torch.empty((B, N, 5), dtype=torch.int8).pin_memory(),

@@ -153,6 +153,7 @@ def lib():
     L.mapf_sample_masked_actions.argtypes = [vp, vp, vp, u64, vp]
     L.mapf_sample_random_actions.argtypes = [vp, vp, u64, vp]
     L.mapf_metrics_reduce.argtypes = [vp, vp, vp]
+    L.mapf_set_fused_sampler.argtypes = [vp, vp, i32, u64]
     L.mapf_poll_errors.argtypes = [vp, C.POINTER(C.c_uint32), vp]
     L.mapf_launch_count.argtypes = [vp]
     L.mapf_launch_count.restype = i64
@@ -169,7 +170,7 @@ EXPORTS = (
     "mapf_set_state_host", "mapf_reset", "mapf_step", "mapf_reset_host", "mapf_step_host",
     "mapf_observe", "mapf_observe_host",
     "mapf_flat_obs_dim", "mapf_pack_flat_obs", "mapf_sample_masked_actions",
-    "mapf_sample_random_actions", "mapf_metrics_reduce", "mapf_poll_errors", "mapf_launch_count",
+    "mapf_sample_random_actions", "mapf_set_fused_sampler", "mapf_metrics_reduce", "mapf_poll_errors", "mapf_launch_count",
 )
 
 

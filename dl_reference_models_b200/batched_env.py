@@ -184,8 +184,12 @@ class BatchedMapfEnv:
         a = self._dev_tensor(actions, torch.int8, (B, N))
         go = self._dev_tensor(goal_override, torch.int16, (B, N, 2))
         gr = self._dev_tensor(goal_rank, torch.int32, (B, N))
+        # with the fused sampler the kernel may read this step's actions from the very buffer it refills
+        # for the next step: every lane reads its own element before it writes it, so in-place is safe
         nat.check(self._lib.mapf_step(self._h, self._ptr(a), self._ptr(go), self._ptr(gr),
                                       C.byref(self._cout), int(bool(auto_reset)), self._stream()))
+        if getattr(self, "_fused", 0):
+            self._sample_counter += 1
         return self._output()
 
     def sample_actions(self, masked: bool = True) -> torch.Tensor:
@@ -199,6 +203,17 @@ class BatchedMapfEnv:
         else:
             nat.check(self._lib.mapf_sample_random_actions(
                 self._h, self._ptr(self._actions), C.c_uint64(self._sample_counter), self._stream()))
+        return self._actions
+
+    def fuse_sampler(self, mode: str | None = "masked") -> torch.Tensor:
+        """Fold the benchmark's action sampler into the step launch: from now on every ``step``
+        also writes the actions for the next step (uniform over the new mask, or over 0..4) into the
+        returned int8 [B,N] tensor -- one launch per env step instead of two.  ``mode=None`` turns it
+        off.  Draws are identical to :meth:`sample_actions` with the same call counter."""
+        code = {None: 0, "masked": 1, "random": 2}[mode]
+        nat.check(self._lib.mapf_set_fused_sampler(self._h, self._ptr(self._actions) if code else None, code,
+                                                   C.c_uint64(self._sample_counter + 1)))
+        self._fused = code
         return self._actions
 
     # ------------------------------------------------------------------ observations

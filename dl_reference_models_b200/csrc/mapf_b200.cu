@@ -85,6 +85,9 @@ struct mapf_handle {
     size_t smem_bytes;
     mapf::SmemLayout layout;
     int step_grid_cap;
+    int8_t *fused_actions;
+    int fused_mode;
+    uint64_t fused_counter;
     KernelFn step_fn, reset_fn;
     uint32_t *d_map_rows, *d_free_bits;
     int32_t *d_num_free;
@@ -554,6 +557,11 @@ int mapf_step(mapf_handle *h, const int8_t *actions, const int16_t *goal_overrid
     p.goal_override = reinterpret_cast<const uint32_t *>(goal_override);
     p.goal_rank = goal_rank;
     p.auto_reset = auto_reset != 0;
+    if (h->fused_mode && h->fused_actions) {
+        p.o_next_actions = h->fused_actions;
+        p.sample_mode = h->fused_mode;
+        p.sample_counter = h->fused_counter++;
+    }
     return launch(h, h->step_fn, p, static_cast<cudaStream_t>(stream));
 }
 
@@ -658,6 +666,16 @@ int mapf_sample_masked_actions(mapf_handle *h, const int8_t *action_mask, int8_t
 
 int mapf_sample_random_actions(mapf_handle *h, int8_t *actions, uint64_t counter, void *stream) {
     return sample_actions(h, nullptr, actions, counter, stream);
+}
+
+int mapf_set_fused_sampler(mapf_handle *h, int8_t *next_actions, int32_t mode, uint64_t first_counter) {
+    if (!h) return fail(MAPF_ERR_INVALID_ARG, "null handle");
+    if (mode < 0 || mode > 2) return fail(MAPF_ERR_INVALID_ARG, "sampler mode %d outside 0..2", mode);
+    if (mode != 0 && !next_actions) return fail(MAPF_ERR_INVALID_ARG, "null next_actions");
+    h->fused_actions = next_actions;
+    h->fused_mode = mode;
+    h->fused_counter = first_counter;
+    return MAPF_OK;
 }
 
 int mapf_metrics_reduce(mapf_handle *h, double *out_device, void *stream) {

@@ -48,6 +48,16 @@ struct Philox {
     }
 };
 
+// One action draw: Philox keyed by (seed, global env id), counter = (call counter, agent).
+__device__ __forceinline__ int sample_action(unsigned long long seed, long long env_global, int agent,
+                                             unsigned long long counter, int mask_bits /* <0: unmasked */) {
+    Philox ph(seed ^ 0xA511E9B3ull, env_global);
+    uint4 x = ph((uint32_t)counter, (uint32_t)(counter >> 32), (uint32_t)agent, 0x41435421u);
+    if (mask_bits < 0) return (int)__umulhi(x.x, 5u);  // scripts/benchmark_multi_agent_env.py:38-39
+    const int n = __popc(mask_bits);                   // scripts/benchmark_multi_agent_env.py:42-57
+    return n ? (int)__fns((unsigned)mask_bits, 0, (int)__umulhi(x.x, (uint32_t)n) + 1) : 0;
+}
+
 // ------------------------------------------------------------------ small helpers
 __device__ __forceinline__ int prow(uint32_t p) { return (int)(short)(p & 0xFFFFu); }
 __device__ __forceinline__ int pcol(uint32_t p) { return (int)(short)(p >> 16); }
@@ -126,6 +136,9 @@ struct KParams {
     float *o_reward;
     uint8_t *o_terminated, *o_truncated, *o_step_flags, *o_agent_step_flags;
     int4 *o_info;  // [B, 4] int4 = MAPF_INFO_WORDS int32
+    int8_t *o_next_actions;  // fused benchmark sampler (scripts/benchmark_multi_agent_env.py:38-57)
+    int sample_mode;         // 0 off, 1 uniform over the new action mask, 2 uniform over 0..4
+    unsigned long long sample_counter;
     uint32_t *err_bits;
     SmemLayout L;  // computed once on the host (mapf_create)
 };
@@ -882,6 +895,11 @@ __global__ void __launch_bounds__(256, MAPF_STEP_MIN_CTAS) mapf_step_kernel(cons
         }
     }
 
+    // ---------------------------------------------------------------- fused action sampler for the next step
+    if (p.sample_mode && act)
+        p.o_next_actions[ai] = (int8_t)sample_action(p.seed, p.env_id_base + env, gl, p.sample_counter,
+                                                     p.sample_mode == 1 ? (int)amask : -1);
+
     // ---------------------------------------------------------------- byte outputs through staging
     if (p.o_action_mask) {
         uint8_t *dst0 = reinterpret_cast<uint8_t *>(p.o_action_mask) + warp_env0 * N * 5;
@@ -1088,19 +1106,13 @@ __global__ void mapf_sample_actions_kernel(const int8_t *mask, int8_t *actions, 
     if (idx >= BN) return;
     long long env = idx / N;
     int a = (int)(idx - env * N);
-    Philox ph(seed ^ 0xA511E9B3ull, env_id_base + env);
-    uint4 x = ph((uint32_t)counter, (uint32_t)(counter >> 32), (uint32_t)a, 0x41435421u);
-    int act;
-    if (mask) {  // scripts/benchmark_multi_agent_env.py:42-57
+    int bits = -1;
+    if (mask) {
         const int8_t *m = mask + idx * 5;
-        int bits = 0;
+        bits = 0;
         for (int k = 0; k < 5; ++k) bits |= (m[k] != 0) << k;
-        int n = __popc(bits);
-        act = n ? (int)__fns((unsigned)bits, 0, (int)__umulhi(x.x, (uint32_t)n) + 1) : 0;
-    } else {
-        act = (int)__umulhi(x.x, 5u);  // scripts/benchmark_multi_agent_env.py:38-39
     }
-    actions[idx] = (int8_t)act;
+    actions[idx] = (int8_t)sample_action(seed, env_id_base + env, a, counter, bits);
 }
 
 // Deterministic reduction of env_metrics[B,K]: CTA k reduces metric k in a fixed order

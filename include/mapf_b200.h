@@ -264,6 +264,13 @@ int mapf_sample_masked_actions(mapf_handle *h, const int8_t *action_mask, int8_t
 /* Uniform actions in 0..4 (scripts/benchmark_multi_agent_env.py:38-39). */
 int mapf_sample_random_actions(mapf_handle *h, int8_t *actions, uint64_t counter, void *stream);
 
+/* Fuse the sampler into the step launch: after this call every mapf_step also writes the actions
+ * for the NEXT step to next_actions (device int8 [B,N]): mode 1 = uniform over the new action
+ * mask, mode 2 = uniform over 0..4, mode 0 / NULL = off.  The draw for call number c is identical
+ * to mapf_sample_*_actions(..., counter = c) on the same masks; `first_counter` is the counter
+ * of the next step call and increments by one per call. */
+int mapf_set_fused_sampler(mapf_handle *h, int8_t *next_actions, int32_t mode, uint64_t first_counter);
+
 /* Deterministic tree reduction of env_metrics[B,K] over the B envs into
  * device double out[MAPF_METRIC_COUNT] (off the step path; ranks then all-reduce it). */
 int mapf_metrics_reduce(mapf_handle *h, double *out_device, void *stream);
