@@ -1,0 +1,187 @@
+"""On-device rollout loop around the batched env (BASELINE config 5).
+
+The caller side of the hot path, restated without RLlib so that observations never leave HBM:
+
+* :class:`ActionMaskPolicy` -- the reference's action-mask MLP (``models/action_mask_model.py:8-67``:
+  shared ``Linear-ReLU`` trunk over the flat features, a logits head, a value head, and
+  ``logits + clamp(log(mask + 1e-6), min=FLOAT_MIN)`` masking, ``:51-64``) as a plain ``nn.Module``
+  that takes the feature block and the int8 mask as separate tensors (the batched env already
+  emits them separately);
+* :func:`collect` -- T steps of ``policy -> sample -> BatchedMapfEnv.step(auto_reset=True)``;
+* :func:`gae` and :func:`ppo_update` -- the PPO arithmetic with the reference's hyper-parameters
+  (``src/agents/ppo.py:104-117``: gamma 0.99, lambda 0.95, clip 0.05, lr 1e-3, entropy 1e-3,
+  vf coeff 0.5, minibatch 1024, 12 epochs) so the loop is a complete, runnable learner.
+
+This module is plain PyTorch by design (the policy is the user's model, not part of the env hot
+path); the env transition inside the loop is the CUDA kernel.
+"""
+from __future__ import annotations
+
+import time
+from dataclasses import dataclass
+
+import torch
+from torch import nn
+
+FLOAT_MIN = -3.4e38  # ray.rllib.utils.torch_utils.FLOAT_MIN
+
+
+class ActionMaskPolicy(nn.Module):
+    def __init__(self, feature_dim: int, num_actions: int = 5, hiddens=(64, 64), no_masking: bool = False):
+        super().__init__()
+        layers, last = [], int(feature_dim)
+        for h in hiddens:
+            layers += [nn.Linear(last, int(h)), nn.ReLU()]
+            last = int(h)
+        self.trunk = nn.Sequential(*layers) if layers else nn.Identity()
+        self.logits = nn.Linear(last, num_actions)
+        self.value = nn.Linear(last, 1)
+        self.no_masking = no_masking
+
+    def forward(self, features: torch.Tensor, action_mask: torch.Tensor):
+        """features [..., F] float, action_mask [..., A] (0/1 of any dtype) -> (masked logits, value)."""
+        z = self.trunk(features.float())
+        logits = self.logits(z)
+        value = self.value(z).squeeze(-1)
+        if self.no_masking:
+            return logits, value
+        inf_mask = torch.clamp(torch.log(action_mask.to(logits.dtype) + 1e-6), min=FLOAT_MIN)
+        return logits + inf_mask, value
+
+
+@dataclass
+class Batch:
+    features: torch.Tensor   # [T,B,N,F]
+    masks: torch.Tensor      # [T,B,N,5] int8
+    actions: torch.Tensor    # [T,B,N] int64
+    logp: torch.Tensor       # [T,B,N]
+    values: torch.Tensor     # [T,B,N]
+    rewards: torch.Tensor    # [T,B,N]
+    dones: torch.Tensor      # [T,B] bool (episode ended at this step; the env auto-reset)
+    last_value: torch.Tensor  # [B,N] bootstrap value of the observation after the last step
+
+
+def sample_categorical(logits: torch.Tensor):
+    """Gumbel-max draw from softmax(logits) and its log-probability (no multinomial kernel)."""
+    logp_all = torch.log_softmax(logits, dim=-1)
+    u = torch.rand_like(logits).clamp_(1e-20, 1.0)
+    a = torch.argmax(logp_all - torch.log(-torch.log(u)), dim=-1)
+    return a, torch.gather(logp_all, -1, a.unsqueeze(-1)).squeeze(-1)
+
+
+@torch.no_grad()
+def collect(env, policy: ActionMaskPolicy, steps: int, out=None) -> Batch:
+    """Roll the policy for ``steps`` env steps entirely on the env's device."""
+    B, N = env.B, env.N
+    dev = env.device
+    F = env.flat_obs_dim(include_action_mask=False)
+    T = int(steps)
+    feats = torch.empty((T, B, N, F), device=dev)
+    masks = torch.empty((T, B, N, 5), dtype=torch.int8, device=dev)
+    actions = torch.empty((T, B, N), dtype=torch.int64, device=dev)
+    logp = torch.empty((T, B, N), device=dev)
+    values = torch.empty((T, B, N), device=dev)
+    rewards = torch.empty((T, B, N), device=dev)
+    dones = torch.empty((T, B), dtype=torch.bool, device=dev)
+    if out is None:
+        out = env._output()
+    for t in range(T):
+        env.flat_obs(include_action_mask=False, out=feats[t])
+        masks[t].copy_(out.action_mask)
+        lg, v = policy(feats[t], masks[t])
+        a, lp = sample_categorical(lg)
+        actions[t], logp[t], values[t] = a, lp, v
+        out = env.step(a.to(torch.int8), auto_reset=True)
+        rewards[t].copy_(out.reward)
+        dones[t] = (out.terminated | out.truncated).bool()
+    last_feats = env.flat_obs(include_action_mask=False)
+    _, last_value = policy(last_feats, out.action_mask)
+    return Batch(feats, masks, actions, logp, values, rewards, dones, last_value)
+
+
+@torch.no_grad()
+def gae(rewards, values, dones, last_value, gamma: float = 0.99, lam: float = 0.95):
+    """Generalised advantage estimation over [T,B,N]; ``dones`` [T,B] cuts the bootstrap."""
+    T = rewards.shape[0]
+    adv = torch.zeros_like(rewards)
+    running = torch.zeros_like(last_value)
+    next_value = last_value
+    for t in range(T - 1, -1, -1):
+        nd = (~dones[t]).to(rewards.dtype).unsqueeze(-1)
+        delta = rewards[t] + gamma * next_value * nd - values[t]
+        running = delta + gamma * lam * nd * running
+        adv[t] = running
+        next_value = values[t]
+    return adv, adv + values
+
+
+def ppo_update(policy, optimizer, batch: Batch, *, clip: float = 0.05, vf_coeff: float = 0.5,
+               entropy_coeff: float = 0.001, epochs: int = 12, minibatch: int = 1024, gamma: float = 0.99,
+               lam: float = 0.95, max_minibatches: int | None = None) -> dict:
+    adv, ret = gae(batch.rewards, batch.values, batch.dones, batch.last_value, gamma, lam)
+    F = batch.features.shape[-1]
+    feats = batch.features.reshape(-1, F)
+    masks = batch.masks.reshape(-1, batch.masks.shape[-1])
+    acts, old_logp = batch.actions.reshape(-1), batch.logp.reshape(-1)
+    adv, ret = adv.reshape(-1), ret.reshape(-1)
+    adv = (adv - adv.mean()) / (adv.std() + 1e-8)
+    n = feats.shape[0]
+    stats, done_mb = {}, 0
+    for _ in range(epochs):
+        perm = torch.randperm(n, device=feats.device)
+        for i in range(0, n, minibatch):
+            idx = perm[i:i + minibatch]
+            lg, v = policy(feats[idx], masks[idx])
+            dist = torch.distributions.Categorical(logits=lg)
+            lp = dist.log_prob(acts[idx])
+            ratio = torch.exp(lp - old_logp[idx])
+            surr = torch.min(ratio * adv[idx], torch.clamp(ratio, 1 - clip, 1 + clip) * adv[idx])
+            vf = (v - ret[idx]).pow(2).mean()
+            ent = dist.entropy().mean()
+            loss = -surr.mean() + vf_coeff * vf - entropy_coeff * ent
+            optimizer.zero_grad(set_to_none=True)
+            loss.backward()
+            optimizer.step()
+            stats = {"loss": float(loss), "vf_loss": float(vf), "entropy": float(ent),
+                     "policy_loss": float(-surr.mean())}
+            done_mb += 1
+            if max_minibatches is not None and done_mb >= max_minibatches:
+                return stats
+    return stats
+
+
+def benchmark(num_envs: int = 65536, steps: int = 64, device: str = "cuda:0") -> dict:
+    """BASELINE config 5: env-only vs policy+env loop throughput (agent-steps/s) on one GPU."""
+    from . import maps
+    from .batched_env import BatchedMapfEnv
+
+    cfg = {"num_agents": 16, "sensor_range": 2, "steps_per_episode": 256, "lifelong_mapf": True, "seed": 999,
+           "grid": maps.random_obstacle_grid(32, 32, 0.30, 2026, min_free=32)}
+    env = BatchedMapfEnv(cfg, num_envs, device)
+    env.reset()
+    policy = ActionMaskPolicy(env.flat_obs_dim(include_action_mask=False)).to(env.device)
+    collect(env, policy, 4)  # warm-up
+    torch.cuda.synchronize(env.device)
+    t0 = time.perf_counter()
+    collect(env, policy, steps)
+    torch.cuda.synchronize(env.device)
+    loop_s = time.perf_counter() - t0
+    a = env.sample_actions(masked=True)
+    env.fuse_sampler("masked")
+    for _ in range(4):
+        env.step(a, auto_reset=True)
+    torch.cuda.synchronize(env.device)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        env.step(a, auto_reset=True)
+    torch.cuda.synchronize(env.device)
+    env_s = time.perf_counter() - t0
+    n = num_envs * env.N * steps
+    return {"envs": num_envs, "agents": env.N, "steps": steps, "env_only_agent_steps_per_s": n / env_s,
+            "policy_loop_agent_steps_per_s": n / loop_s}
+
+
+if __name__ == "__main__":
+    import json
+
+    print(json.dumps(benchmark()))
