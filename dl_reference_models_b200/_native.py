@@ -16,7 +16,8 @@ PKG = Path(__file__).resolve().parent
 REPO = PKG.parent
 CSRC = PKG / "csrc"
 LIB_PATH = Path(os.environ.get("MAPF_B200_LIB", PKG / "libmapf_b200.so"))
-SOURCES = (CSRC / "mapf_b200.cu", CSRC / "mapf_kernels.cuh", REPO / "include" / "mapf_b200.h")
+SOURCES = (CSRC / "mapf_b200.cu", CSRC / "mapf_kernels.cuh", CSRC / "mapf_env_kernel.cuh",
+           REPO / "include" / "mapf_b200.h")
 
 MAX_AGENTS = 32
 MAX_SENSOR_RANGE = 3
@@ -61,7 +62,7 @@ class MapfConfig(C.Structure):
         ("livelock_window_steps", C.c_int32), ("lock_nearby_manhattan", C.c_int32),
         ("lock_min_neighbors", C.c_int32), ("lock_progress_epsilon_floor", C.c_int32),
         ("normalize_goal_delta", C.c_int32), ("deterministic", C.c_int32), ("per_env_maps", C.c_int32),
-        ("env_id_base", C.c_int64), ("seed", C.c_uint64), ("device", C.c_int32), ("reserved", C.c_int32),
+        ("env_id_base", C.c_int64), ("seed", C.c_uint64), ("device", C.c_int32), ("step_kernel", C.c_int32),
     ]
 
 
@@ -157,6 +158,7 @@ def lib():
     L.mapf_poll_errors.argtypes = [vp, C.POINTER(C.c_uint32), vp]
     L.mapf_launch_count.argtypes = [vp]
     L.mapf_launch_count.restype = i64
+    L.mapf_step_kernel_kind.argtypes = [vp]
     for name in EXPORTS:
         if name not in ("mapf_version", "mapf_last_error", "mapf_launch_count"):
             getattr(L, name).restype = C.c_int
@@ -171,6 +173,7 @@ EXPORTS = (
     "mapf_observe", "mapf_observe_host",
     "mapf_flat_obs_dim", "mapf_pack_flat_obs", "mapf_sample_masked_actions",
     "mapf_sample_random_actions", "mapf_set_fused_sampler", "mapf_metrics_reduce", "mapf_poll_errors", "mapf_launch_count",
+    "mapf_step_kernel_kind",
 )
 
 
@@ -206,5 +209,5 @@ def make_config(env_config: dict, rows: int, cols: int, num_envs: int, device: i
         env_id_base=int(env_id_base),
         seed=(int(seed) if seed is not None else int.from_bytes(os.urandom(8), "little")) & (2 ** 64 - 1),
         device=int(device),
-        reserved=0,
+        step_kernel={'auto': 0, 'lane': 1, 'env': 2}[str(g('step_kernel', 'auto'))],
     )

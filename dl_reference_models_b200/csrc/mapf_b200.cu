@@ -2,7 +2,7 @@
 // of mapf_kernels.cuh.  Host side only: argument validation, map bit-packing, launch geometry,
 // state/IO buffer management.  There is no CPU implementation of the transition in here: every
 // entry point that computes launches a kernel, and fails with MAPF_ERR_CUDA if it cannot.
-#include "mapf_kernels.cuh"
+#include "mapf_env_kernel.cuh"
 
 #include <cstdarg>
 #include <cstdio>
@@ -74,6 +74,18 @@ KernelFn pick_reset(int G, int sr) {
 }
 
 constexpr size_t kMaxSmem = 200 * 1024;
+constexpr size_t kMaxSmemEnv = 227 * 1024;  // opt-in limit of one sm_100 CTA
+
+using EnvKernelFn = void (*)(const mapf::KParams, const mapf::EnvLayout);
+template <bool VEC>
+EnvKernelFn env_step_for_sr(int sr) {
+    switch (sr) {
+        case 1: return mapf::mapf_step_env_kernel<1, VEC>;
+        case 2: return mapf::mapf_step_env_kernel<2, VEC>;
+        case 3: return mapf::mapf_step_env_kernel<3, VEC>;
+    }
+    return nullptr;
+}
 
 }  // namespace
 
@@ -89,6 +101,11 @@ struct mapf_handle {
     int fused_mode;
     uint64_t fused_counter;
     KernelFn step_fn, reset_fn;
+    // env-per-thread step kernel (maps up to 32 columns wide, shared map); 0 threads = not available
+    EnvKernelFn env_fn;
+    mapf::EnvLayout env_layout;
+    int env_threads, env_grid;
+    bool use_env_kernel;
     uint32_t *d_map_rows, *d_free_bits;
     int32_t *d_num_free;
     bool map_set;
@@ -228,7 +245,15 @@ void fill_outputs(mapf::KParams &p, const mapf_outputs *o) {
     p.o_info = reinterpret_cast<int4 *>(o->info);
 }
 
+int launch_env_step(mapf_handle *h, const mapf::KParams &p, cudaStream_t s) {
+    h->env_fn<<<h->env_grid, h->env_threads, h->env_layout.total_bytes, s>>>(p, h->env_layout);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    return MAPF_OK;
+}
+
 int launch(mapf_handle *h, KernelFn fn, const mapf::KParams &p, cudaStream_t s) {
+    if (fn == h->step_fn && h->use_env_kernel) return launch_env_step(h, p, s);
     const int groups = h->threads / h->G;
     unsigned grid = (unsigned)((h->cfg.num_envs + groups - 1) / groups);
     // the step kernel is persistent: one wave of resident CTAs walks over the env tiles
@@ -303,6 +328,7 @@ int mapf_create(const mapf_config *cfg, mapf_handle **out) {
     if (c.lock_nearby_manhattan < 1 || c.lock_nearby_manhattan > 255 || c.lock_min_neighbors < 1)
         return fail(MAPF_ERR_INVALID_ARG, "lock_nearby_manhattan / lock_min_neighbors must be >= 1");
     if (c.steps_per_episode < 1) return fail(MAPF_ERR_INVALID_ARG, "steps_per_episode must be >= 1");
+    if (c.step_kernel < 0 || c.step_kernel > 2) return fail(MAPF_ERR_INVALID_ARG, "step_kernel must be 0 (auto), 1 (lane) or 2 (env)");
 
     int ndev = 0;
     cudaError_t ce = cudaGetDeviceCount(&ndev);
@@ -355,6 +381,46 @@ int mapf_create(const mapf_config *cfg, mapf_handle **out) {
     if (const char *ov = getenv("MAPF_STEP_CTAS_PER_SM")) {  // tuning knob: 0 = one CTA per tile (not persistent)
         const int v = atoi(ov);
         h->step_grid_cap = v > 0 ? nsm * v : 0;
+    }
+    // Step-kernel choice (cfg.step_kernel: 0 auto, 1 lane-per-agent, 2 env-per-thread; the environment
+    // variable MAPF_STEP_KERNEL=lane|env overrides "auto").  Both are sm_100a kernels with identical results.
+    h->env_threads = 0;
+    h->use_env_kernel = false;
+    if (e1 == cudaSuccess && c.cols <= 32 && c.rows <= 64 && !c.per_env_maps) {
+        const int ntiles = (c.num_envs + 31) / 32;
+        int want = (ntiles + (nsm > 0 ? nsm : 1) - 1) / (nsm > 0 ? nsm : 1);  // warps per CTA for one resident wave
+        if (want > 16) want = 16;
+        if (want < 1) want = 1;
+        for (int w = want; w >= 1; --w) {
+            mapf::EnvLayout E = mapf::make_env_layout(c.num_agents, c.rows, c.cols, h->SR, h->fw, w);
+            if ((size_t)E.total_bytes <= kMaxSmemEnv) {
+                h->env_threads = 32 * w;
+                h->env_layout = E;
+                break;
+            }
+        }
+        if (h->env_threads) {
+            h->env_fn = (c.num_agents % 4 == 0) ? env_step_for_sr<true>(h->SR) : env_step_for_sr<false>(h->SR);
+            e1 = cudaFuncSetAttribute(reinterpret_cast<const void *>(h->env_fn),
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmemEnv);
+            const int w = h->env_threads / 32;
+            int grid = (ntiles + w - 1) / w;
+            if (nsm > 0 && grid > nsm) grid = nsm;  // persistent: every warp walks over env tiles
+            h->env_grid = grid;
+        }
+    }
+    {
+        int want_kernel = c.step_kernel;
+        if (want_kernel == 0) {
+            if (const char *ov = getenv("MAPF_STEP_KERNEL")) want_kernel = (ov[0] == 'l') ? 1 : (ov[0] == 'e') ? 2 : 0;
+        }
+        if (want_kernel == 2 && !h->env_threads) {
+            delete h;
+            return fail(MAPF_ERR_UNSUPPORTED,
+                        "env-per-thread step kernel needs cols <= 32, rows <= 64 and a shared map (got %dx%d, per_env_maps=%d)",
+                        c.rows, c.cols, c.per_env_maps);
+        }
+        h->use_env_kernel = h->env_threads && want_kernel != 1;
     }
     cudaError_t e3 = cudaMalloc(&h->d_err, 4);
     if (e3 == cudaSuccess) e3 = cudaMemset(h->d_err, 0, 4);
@@ -704,5 +770,7 @@ int mapf_poll_errors(mapf_handle *h, uint32_t *bits, void *stream) {
 }
 
 int64_t mapf_launch_count(const mapf_handle *h) { return h ? h->launches : 0; }
+
+int mapf_step_kernel_kind(const mapf_handle *h) { return h ? (h->use_env_kernel ? 2 : 1) : 0; }
 
 }  // extern "C"

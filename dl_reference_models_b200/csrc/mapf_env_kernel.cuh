@@ -1,0 +1,882 @@
+// mapf_env_kernel.cuh -- env-per-thread step kernel (sm_100a) of the batched MAPF transition.
+//
+// Reference semantics: src/environments/reference_model_multi_agent.py ("ENV:line").
+//
+// Why a second mapping.  The lane-per-agent kernel (mapf_kernels.cuh) spends ~1 900 warp
+// instructions per 32 agent-steps: every lane re-executes the env-level coordination (ballots,
+// candidate loops that run to the longest lane, predicated single-lane blocks) and ncu shows it
+// bound by instruction issue, not by HBM.  Here ONE THREAD owns ONE ENV and walks its agents in
+// index order exactly like the reference's python loop (ENV:502-563), so the sequential
+// semantics need no cross-lane protocol at all and nothing is computed redundantly:
+//   * the occupancy and goal owner grids (ENV:102-103) are two bitboards (one 32-bit word per map
+//     row, map width <= 32) in shared memory, laid out [row][lane] so a warp's accesses never
+//     conflict; a move is "test one bit, clear one bit, set one bit";
+//   * staggered observations (ENV:528-536) fall out of a second, DESCENDING walk that
+//     un-does agent i's move after emitting its window: the board then is snapshot i-1;
+//   * a window row is 3 table lookups: the row bits of obstacle / agent / goal planes index a
+//     2^V-entry nibble-spread table, and PRMT turns 4 nibbles into 4 output bytes;
+//   * lock neighbourhoods, intent blocking, co-location and the wait-for graph use per-row /
+//     per-column agent masks (their AND is the owner set of a cell) built in the board memory
+//     once the boards are dead; wait-for cycles are found by stripping leaves off the functional
+//     graph with agent bitmasks;
+//   * state is read and written with 128-bit accesses (4 agents per access); the byte channels
+//     (local_obs, action_mask) go through a per-warp staging tile and leave coalesced.
+// No tensor cores: there is no dense contraction on this path.
+#pragma once
+
+#include "mapf_kernels.cuh"
+
+namespace mapf {
+
+// Shared-memory carve-up of the env-per-thread kernel (byte offsets, computed on the host).
+struct EnvLayout {
+    int lut_off;       // obstacle window of every cell: u32[R*32] (V <= 5) or u64[R*32] (V = 7)
+    int freerow_off;   // u32[R]: bit c = cell (r, c) is free
+    int freebits_off;  // u32[fw]: cell-linear free bitmap (reset draws, ENV:267-282)
+    int gdt_off;       // float[(2R-1)+(2C-1)] goal-delta quotients (ENV:330-335)
+    int t1_off;        // u32[1 << V]: bit j -> nibble j
+    int kth_off;       // u8[32*8]: position of the (k+1)-th set bit of a 5-bit mask
+    int warp_off, warp_bytes;                 // per-warp block
+    int board_off, scratch_off, stage_off;    // inside a warp block
+    int board_rows;    // max(R, C)
+    int nq;            // ceil(N / 4)
+    int stage_stride;  // words per lane (odd => conflict-free)
+    int total_bytes;
+};
+
+__host__ __device__ inline EnvLayout make_env_layout(int N, int R, int C, int SR, int fw, int warps) {
+    const int V = 2 * SR + 1, V2 = V * V;
+    EnvLayout E;
+    int o = 0;
+    E.lut_off = o; o += R * 32 * (V > 5 ? 8 : 4);
+    E.freerow_off = o; o += R * 4;
+    E.freebits_off = o; o += fw * 4;
+    E.gdt_off = o; o += ((2 * R - 1) + (2 * C - 1)) * 4;
+    E.t1_off = o; o += (1 << V) * 4;
+    E.kth_off = o; o += 32 * 8;
+    o = (o + 15) & ~15;
+    E.board_rows = R > C ? R : C;
+    if (N > E.board_rows) E.board_rows = N;  // reset draws park 2N cell ids in the dead boards
+    E.nq = (N + 3) / 4;
+    int w = 0;
+    E.board_off = w; w += E.board_rows * 32 * 8;
+    E.scratch_off = w; w += E.nq * 32 * 20;  // per quad and lane: 4 x u16 cell, 4 x i16 delta, 4 x u8 action
+    int sw = (4 * V2 + 20 + 3) / 4;
+    if (!(sw & 1)) sw += 1;
+    E.stage_stride = sw;
+    E.stage_off = w; w += 32 * sw * 4;
+    w = (w + 15) & ~15;
+    E.warp_bytes = w;
+    E.warp_off = o; o += w * warps;
+    E.total_bytes = o;
+    return E;
+}
+
+// quad (4 consecutive agents of one env) loads / stores; VEC = N % 4 == 0 => one 128-bit access
+template <bool VEC>
+__device__ __forceinline__ uint4 ldq32(const uint32_t *a, size_t i, int i0, int N, bool ok, uint32_t d) {
+    uint4 v = make_uint4(d, d, d, d);
+    if (VEC) { if (ok) v = *reinterpret_cast<const uint4 *>(a + i); }
+    else if (ok) {
+        if (i0 + 0 < N) v.x = a[i + 0];
+        if (i0 + 1 < N) v.y = a[i + 1];
+        if (i0 + 2 < N) v.z = a[i + 2];
+        if (i0 + 3 < N) v.w = a[i + 3];
+    }
+    return v;
+}
+template <bool VEC>
+__device__ __forceinline__ void stq32(uint32_t *a, size_t i, int i0, int N, bool ok, uint4 v) {
+    if (!ok) return;
+    if (VEC) *reinterpret_cast<uint4 *>(a + i) = v;
+    else {
+        if (i0 + 0 < N) a[i + 0] = v.x;
+        if (i0 + 1 < N) a[i + 1] = v.y;
+        if (i0 + 2 < N) a[i + 2] = v.z;
+        if (i0 + 3 < N) a[i + 3] = v.w;
+    }
+}
+template <bool VEC>
+__device__ __forceinline__ uint32_t ldq8(const uint8_t *a, size_t i, int i0, int N, bool ok) {
+    uint32_t v = 0;
+    if (VEC) { if (ok) v = *reinterpret_cast<const uint32_t *>(a + i); }
+    else if (ok) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) if (i0 + k < N) v |= (uint32_t)a[i + k] << (8 * k);
+    }
+    return v;
+}
+template <bool VEC>
+__device__ __forceinline__ void stq8(uint8_t *a, size_t i, int i0, int N, bool ok, uint32_t v) {
+    if (!ok) return;
+    if (VEC) *reinterpret_cast<uint32_t *>(a + i) = v;
+    else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) if (i0 + k < N) a[i + k] = (uint8_t)(v >> (8 * k));
+    }
+}
+template <bool VEC>
+__device__ __forceinline__ uint2 ldq16(const int16_t *a, size_t i, int i0, int N, bool ok) {
+    uint2 v = make_uint2(0, 0);
+    if (VEC) { if (ok) v = *reinterpret_cast<const uint2 *>(a + i); }
+    else if (ok) {
+        if (i0 + 0 < N) v.x |= (uint32_t)(uint16_t)a[i + 0];
+        if (i0 + 1 < N) v.x |= (uint32_t)(uint16_t)a[i + 1] << 16;
+        if (i0 + 2 < N) v.y |= (uint32_t)(uint16_t)a[i + 2];
+        if (i0 + 3 < N) v.y |= (uint32_t)(uint16_t)a[i + 3] << 16;
+    }
+    return v;
+}
+template <bool VEC>
+__device__ __forceinline__ void stq16(int16_t *a, size_t i, int i0, int N, bool ok, uint2 v) {
+    if (!ok) return;
+    if (VEC) *reinterpret_cast<uint2 *>(a + i) = v;
+    else {
+        if (i0 + 0 < N) a[i + 0] = (int16_t)(v.x & 0xFFFFu);
+        if (i0 + 1 < N) a[i + 1] = (int16_t)(v.x >> 16);
+        if (i0 + 2 < N) a[i + 2] = (int16_t)(v.y & 0xFFFFu);
+        if (i0 + 3 < N) a[i + 3] = (int16_t)(v.y >> 16);
+    }
+}
+
+__device__ __forceinline__ uint32_t qget(const uint4 &v, int k) { return k == 0 ? v.x : k == 1 ? v.y : k == 2 ? v.z : v.w; }
+__device__ __forceinline__ void qset(uint4 &v, int k, uint32_t x) { if (k == 0) v.x = x; else if (k == 1) v.y = x; else if (k == 2) v.z = x; else v.w = x; }
+// u16 lane k of a 4 x u16 pack
+__device__ __forceinline__ uint32_t hget(const uint2 &v, int k) { const uint32_t w = (k < 2) ? v.x : v.y; return (k & 1) ? (w >> 16) : (w & 0xFFFFu); }
+__device__ __forceinline__ void hset(uint2 &v, int k, uint32_t x) {
+    uint32_t &w = (k < 2) ? v.x : v.y;
+    w = (k & 1) ? ((w & 0x0000FFFFu) | (x << 16)) : ((w & 0xFFFF0000u) | (x & 0xFFFFu));
+}
+// cell code = row * 32 + col (map width <= 32); the state tensors hold int16 (row, col) pairs
+__device__ __forceinline__ uint32_t code_of(uint32_t packed) { return ((packed & 0xFFFFu) << 5) | (packed >> 16); }
+__device__ __forceinline__ uint32_t packed_of(uint32_t code) { return (code >> 5) | ((code & 31u) << 16); }
+
+// One Philox call serves the 4 agents of a quad (scripts/benchmark_multi_agent_env.py:38-57).
+__device__ __forceinline__ uint4 sample_quad(unsigned long long seed, long long env_global, int quad,
+                                             unsigned long long counter) {
+    Philox ph(seed ^ 0xA511E9B3ull, env_global);
+    return ph((uint32_t)counter, (uint32_t)(counter >> 32), (uint32_t)quad, 0x41435421u);
+}
+
+template <int SR, bool VEC>
+__global__ void __launch_bounds__(512, 1) mapf_step_env_kernel(const KParams p, const EnvLayout E) {
+    constexpr int V = 2 * SR + 1, V2 = V * V;
+    constexpr uint32_t VM = (1u << V) - 1u;
+    constexpr int OBS_W = V2;                 // obs words per quad and env (4 * V2 bytes)
+    using WB = typename WinBits<V>::type;
+    extern __shared__ __align__(16) unsigned char esm[];
+    const unsigned full = 0xFFFFFFFFu;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, warps = blockDim.x >> 5;
+    const int N = p.N, R = p.R, C = p.C, NQ = E.nq;
+
+    // ------------------------------------------------------------------ CTA-wide tables
+    WB *lut = reinterpret_cast<WB *>(esm + E.lut_off);
+    uint32_t *freerow = reinterpret_cast<uint32_t *>(esm + E.freerow_off);
+    uint32_t *freebits = reinterpret_cast<uint32_t *>(esm + E.freebits_off);
+    float *gdt = reinterpret_cast<float *>(esm + E.gdt_off);
+    uint32_t *t1 = reinterpret_cast<uint32_t *>(esm + E.t1_off);
+    uint8_t *kth = esm + E.kth_off;
+    for (int cell = tid; cell < R * 32; cell += blockDim.x) {
+        const int r = cell >> 5, c = cell & 31;
+        WB w = 0;
+        if (c < C) {
+            const int sb = c - SR + PAD, word = sb >> 5, sh = sb & 31;
+#pragma unroll
+            for (int wr = 0; wr < V; ++wr) {
+                const uint32_t *rw = p.map_rows + (r - SR + wr + PAD) * p.wpr + word;
+                w |= (WB)(__funnelshift_r(rw[0], rw[1], sh) & VM) << (wr * V);
+            }
+        }
+        lut[cell] = w;
+    }
+    for (int r = tid; r < R; r += blockDim.x) {
+        const uint32_t *rw = p.map_rows + (r + PAD) * p.wpr;
+        const uint32_t bits = __funnelshift_r(rw[0], rw[1], PAD);  // bit c = obstacle at column c (c < 32)
+        freerow[r] = ~bits & (C >= 32 ? 0xFFFFFFFFu : ((1u << C) - 1u));
+    }
+    for (int i = tid; i < p.fw; i += blockDim.x) freebits[i] = p.free_bits[i];
+    fill_goal_delta_table(gdt, R, C, p.normalize, p.den0, p.den1, tid, blockDim.x);
+    for (int x = tid; x < (1 << V); x += blockDim.x) {
+        uint32_t s = 0;
+#pragma unroll
+        for (int j = 0; j < V; ++j) s |= ((x >> j) & 1u) << (4 * j);
+        t1[x] = s;
+    }
+    for (int x = tid; x < 256; x += blockDim.x) {
+        const int m = x >> 3, k = x & 7;
+        kth[x] = (uint8_t)((k < __popc(m)) ? __fns((unsigned)m, 0, k + 1) : 0);
+    }
+    __syncthreads();
+
+    unsigned char *wsm = esm + E.warp_off + warp * E.warp_bytes;
+    uint2 *board = reinterpret_cast<uint2 *>(wsm + E.board_off) + lane;       // row r at board[r * 32]: .x occupancy, .y goals
+    uint2 *scr_pos = reinterpret_cast<uint2 *>(wsm + E.scratch_off) + lane;   // quad q at [q * 32]: 4 x u16 cell codes
+    uint2 *scr_delta = scr_pos + NQ * 32;                                     // 4 x i16 distance deltas
+    uint32_t *scr_act = reinterpret_cast<uint32_t *>(scr_delta + NQ * 32 - lane) + lane;  // 4 x u8 action / wait-for pointer
+    uint32_t *stage_w = reinterpret_cast<uint32_t *>(wsm + E.stage_off);      // [lane][stage_stride] words
+    uint32_t *my_stage = stage_w + lane * E.stage_stride;
+    const int ntiles = (p.B + 31) >> 5;
+    uint32_t errs = 0;
+    const uint32_t mdw = p.dw >= 32 ? full : ((1u << p.dw) - 1u);
+    const uint32_t mlw = p.lw >= 32 ? full : ((1u << p.lw) - 1u);
+    const uint32_t allN = (N >= 32) ? full : ((1u << N) - 1u);
+
+    for (int tile = blockIdx.x * warps + warp; tile < ntiles; tile += gridDim.x * warps) {
+    const int env = tile * 32 + lane;
+    const bool ok = env < p.B;
+    const size_t ab = (size_t)(ok ? env : 0) * N;
+    const long long env_global = p.env_id_base + env;
+
+    // ---------------------------------------------------------------- env words
+    int4 w0 = make_int4(0, 0, 0, 0), w1 = w0, w2 = w0, w3 = w0;
+    if (ok) {
+        const int4 *ew = p.env_words + (size_t)env * 4;
+        w0 = ew[0]; w1 = ew[1]; w2 = ew[2]; w3 = ew[3];
+    }
+    int step_count = w0.x + 1;  // ENV:475
+    int lock_count = w0.y, lock_prev = w0.z, goals_total = w0.w;
+    int blocking_total = w1.x, dl_events = w1.y, ll_events = w1.z, dl_steps = w1.w;
+    int ll_steps = w2.x;
+    uint32_t rng_counter = (uint32_t)w2.y;
+    int ep_return_x2 = w2.z, wfg_steps = w2.w;
+    int episodes = w3.x;
+    int lock_head = w3.y;
+    const int count_after = lock_count + 1;
+    if (lock_head < 0 || lock_head >= p.lw) lock_head = 0;
+    const int slot_new = lock_head;
+    const int slot_next = (lock_head + 1 == p.lw) ? 0 : lock_head + 1;
+    const bool use_ring = p.lock_enabled && count_after >= p.lw && p.lw > 1;
+
+    // ---------------------------------------------------------------- pre-pass: occupancy board from the old positions
+    for (int r = 0; r < E.board_rows; ++r) board[r * 32] = make_uint2(0u, 0u);
+    for (int q = 0; q < NQ; ++q) {
+        const int i0 = 4 * q;
+        const uint4 pq = ldq32<VEC>(p.positions, ab + i0, i0, N, ok, 0u);
+        uint2 codes = make_uint2(0u, 0u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (i0 + k < N) {
+                const uint32_t code = code_of(qget(pq, k));
+                hset(codes, k, code);
+                if (ok) board[(code >> 5) * 32].x |= 1u << (code & 31u);
+            }
+        }
+        scr_pos[q * 32] = codes;
+    }
+
+    // ---------------------------------------------------------------- pass 1: moves, goals, lock history (agent order, ENV:502-563)
+    uint32_t moved_m = 0, failed_m = 0, gstep_m = 0, ongoal_m = 0;
+    uint32_t reached_m = 0, completed_m = 0, bprev_m = 0;
+    uint32_t Gd = 0, Md = 0, Fd = 0, Gl = 0, Ml = 0;
+    bool reassigned = false;
+    const Philox ph_env(p.seed, env_global);
+    for (int q = 0; q < NQ; ++q) {
+        const int i0 = 4 * q;
+        const uint2 codes = scr_pos[q * 32];
+        uint32_t act4 = p.actions ? ldq8<VEC>(reinterpret_cast<const uint8_t *>(p.actions), ab + i0, i0, N, ok) : 0u;
+        const uint32_t fl4 = ldq8<VEC>(p.agent_flags, ab + i0, i0, N, ok);
+        uint4 gq = ldq32<VEC>(p.goals, ab + i0, i0, N, ok, 0u);
+        uint4 gpq = make_uint4(0, 0, 0, 0), mvq = gpq, fmq = gpq;
+        uint2 ringq = make_uint2(0u, 0u);
+        if (p.lock_enabled) {
+            gpq = ldq32<VEC>(p.lock_gp, ab + i0, i0, N, ok, 0u);
+            mvq = ldq32<VEC>(p.lock_mv, ab + i0, i0, N, ok, 0u);
+            fmq = ldq32<VEC>(p.lock_fm, ab + i0, i0, N, ok, 0u);
+            if (use_ring) ringq = ldq16<VEC>(p.lock_dist, ((size_t)(ok ? env : 0) * p.lw + slot_next) * N + i0, i0, N, ok);
+        }
+        uint2 newcodes = codes, deltas = make_uint2(0u, 0u), dists = make_uint2(0u, 0u);
+        uint4 posq = make_uint4(0, 0, 0, 0);
+        bool goal_changed = false;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (i0 + k >= N) break;
+            const uint32_t bit = 1u << (i0 + k);
+            const uint32_t code = hget(codes, k);
+            int a = (int)(int8_t)(act4 >> (8 * k));
+            if (a < 0 || a > 4) { errs |= MAPF_DEV_ERR_INVALID_ACTION; a = 0; }
+            act4 = (act4 & ~(0xFFu << (8 * k))) | ((uint32_t)a << (8 * k));
+            // ENV:512-526: target cell, obstacle / bounds from the cell's obstacle window, occupancy from the board
+            const int d = (int)(int8_t)__byte_perm(0x2001E000u, 0x000000FFu, (uint32_t)a);   // {0,-32,+1,+32,-1}
+            const uint32_t nbi = __byte_perm((uint32_t)(SR * V + SR) | ((uint32_t)(SR * V + SR - V) << 8) |
+                                             ((uint32_t)(SR * V + SR + 1) << 16) | ((uint32_t)(SR * V + SR + V) << 24),
+                                             (uint32_t)(SR * V + SR - 1), (uint32_t)a) & 0xFFu;
+            const uint32_t obst_lo = (uint32_t)lut[code];
+            const uint32_t tcode = code + (uint32_t)d;
+            bool wants = ok && a != 0 && !((obst_lo >> nbi) & 1u);
+            bool moves = false;
+            if (wants) {
+                uint2 *trow = &board[(tcode >> 5) * 32];
+                const uint32_t tb = 1u << (tcode & 31u);
+                if (!(trow->x & tb)) {
+                    moves = true;
+                    board[(code >> 5) * 32].x &= ~(1u << (code & 31u));
+                    trow->x |= tb;
+                }
+            }
+            const uint32_t ncode = moves ? tcode : code;
+            hset(newcodes, k, ncode);
+            qset(posq, k, packed_of(ncode));
+            if (moves) moved_m |= bit;
+            const bool failed = ok && a != 0 && !moves;  // ENV:583
+            if (failed) failed_m |= bit;
+            // flags of the previous step
+            const uint32_t fl = (fl4 >> (8 * k)) & 0xFFu;
+            if (fl & MAPF_AF_REACHED) reached_m |= bit;
+            if (fl & MAPF_AF_COMPLETED_ONCE) completed_m |= bit;
+            if (fl & MAPF_AF_BLOCKING_PREV) bprev_m |= bit;
+            // ENV:538-563
+            uint32_t gcode = code_of(qget(gq, k));
+            const bool on_goal = ok && ncode == gcode;
+            bool gstep = false;
+            if (ok) board[(gcode >> 5) * 32].y |= 1u << (gcode & 31u);
+            if (!p.lifelong) {
+                if (on_goal && !(fl & MAPF_AF_REACHED)) { reached_m |= bit; completed_m |= bit; gstep = true; }
+            } else if (on_goal) {
+                gstep = true;
+                completed_m |= bit; reached_m &= ~bit;
+                reassigned = true;
+                // ENV:284-304 at agent i's turn: the board IS occupancy snapshot i; goals of later agents
+                // are not on the goal board yet -> add them (idempotent), drop my old goal, pick the k-th candidate
+                const int i = i0 + k;
+                for (int j = i + 1; j < N; ++j) {
+                    const uint32_t gj = code_of(p.goals[ab + j]);
+                    board[(gj >> 5) * 32].y |= 1u << (gj & 31u);
+                }
+                board[(gcode >> 5) * 32].y &= ~(1u << (gcode & 31u));
+                uint32_t ng = 0xFFFFFFFFu;
+                if (p.goal_override) {
+                    const uint32_t ov = p.goal_override[ab + i];
+                    if (prow(ov) >= 0) ng = code_of(ov);
+                }
+                if (ng == 0xFFFFFFFFu) {
+                    int n = 0;
+                    for (int r = 0; r < R; ++r) { const uint2 b = board[r * 32]; n += __popc(freerow[r] & ~b.x & ~b.y); }
+                    int kk = -1;
+                    if (p.goal_rank) kk = p.goal_rank[ab + i];
+                    if (kk < 0 && n > 0) {
+                        const uint4 x = ph_env(rng_counter, (uint32_t)i, 0x474F414Cu /* "GOAL" */, 0);
+                        kk = (int)__umulhi(x.x, (uint32_t)n);
+                        rng_counter++;
+                    }
+                    if (n > 0 && kk < n) {
+                        for (int r = 0; r < R; ++r) {
+                            const uint2 b = board[r * 32];
+                            const uint32_t cand = freerow[r] & ~b.x & ~b.y;
+                            const int c = __popc(cand);
+                            if (kk < c) { ng = (uint32_t)(r * 32) + __fns(cand, 0, kk + 1); break; }
+                            kk -= c;
+                        }
+                    }
+                    if (ng == 0xFFFFFFFFu) errs |= MAPF_DEV_ERR_NO_GOAL_CELL;
+                }
+                if (ng == 0xFFFFFFFFu) ng = gcode;  // error flagged: keep the old goal
+                gcode = ng;
+                board[(gcode >> 5) * 32].y |= 1u << (gcode & 31u);
+                qset(gq, k, packed_of(gcode));
+                goal_changed = true;
+            }
+            if (gstep) gstep_m |= bit;
+            const bool cur_on_goal = ok && ncode == gcode;  // ENV:555: false after a reassignment
+            if (cur_on_goal) ongoal_m |= bit;
+            // ENV:581-594 lock history
+            if (p.lock_enabled) {
+                const bool prev_on_goal = p.lifelong ? false : (code == gcode);
+                const bool gp = p.lifelong ? gstep : (!prev_on_goal && cur_on_goal);
+                const uint32_t g2 = (qget(gpq, k) << 1) | (gp ? 1u : 0u);
+                const uint32_t m2 = (qget(mvq, k) << 1) | (moves ? 1u : 0u);
+                const uint32_t f2 = (qget(fmq, k) << 1) | (failed ? 1u : 0u);
+                qset(gpq, k, g2); qset(mvq, k, m2); qset(fmq, k, f2);
+                if (ok) {
+                    if (g2 & mdw) Gd |= bit;
+                    if (m2 & mdw) Md |= bit;
+                    if (f2 & mdw) Fd |= bit;
+                    if (g2 & mlw) Gl |= bit;
+                    if (m2 & mlw) Ml |= bit;
+                }
+                const int dist = abs((int)(gcode >> 5) - (int)(ncode >> 5)) + abs((int)(gcode & 31u) - (int)(ncode & 31u));
+                hset(dists, k, (uint32_t)dist);
+                if (use_ring && ok) hset(deltas, k, (uint32_t)((int)(int16_t)hget(ringq, k) - dist));
+            }
+        }
+        scr_pos[q * 32] = newcodes;
+        scr_delta[q * 32] = deltas;
+        scr_act[q * 32] = act4;
+        stq32<VEC>(p.positions, ab + i0, i0, N, ok, posq);
+        if (goal_changed) stq32<VEC>(p.goals, ab + i0, i0, N, ok, gq);
+        if (p.lock_enabled) {
+            stq32<VEC>(p.lock_gp, ab + i0, i0, N, ok, gpq);
+            stq32<VEC>(p.lock_mv, ab + i0, i0, N, ok, mvq);
+            stq32<VEC>(p.lock_fm, ab + i0, i0, N, ok, fmq);
+            stq16<VEC>(p.lock_dist, ((size_t)(ok ? env : 0) * p.lw + slot_new) * N + i0, i0, N, ok, dists);
+        }
+    }
+    if (p.lock_enabled) lock_head = slot_next;
+    const int arrivals = __popc(gstep_m);
+    goals_total += arrivals;  // lifelong: every arrival; else first arrivals (ENV:545,562)
+
+    // ---------------------------------------------------------------- pass 2: observations (descending walk with undo)
+    // emit(active, undo): active threads write local_obs / action_mask / goal_delta / blocking_prev / next
+    // actions of their env from the boards; with undo, agent i's move is taken back after its window is
+    // built, so the next (lower) agent sees snapshot i-1.  A thread whose env reassigned
+    // a goal (ENV:565-575) or was just reset shows the final state to everybody: no undo.
+    auto emit = [&](const bool active, const bool undo, const uint32_t mv_m, const uint32_t bp_m) {
+        const unsigned act_w = __ballot_sync(full, active);
+        for (int q = NQ - 1; q >= 0; --q) {
+            const int i0 = 4 * q;
+            const uint2 codes = scr_pos[q * 32];
+            const uint32_t act4 = scr_act[q * 32];
+            const uint4 gq = ldq32<VEC>(p.goals, ab + i0, i0, N, active, 0u);
+            uint4 rnd = make_uint4(0, 0, 0, 0);
+            if (p.sample_mode) rnd = sample_quad(p.seed, env_global, q, p.sample_counter);
+            uint32_t masks4 = 0, next4 = 0, bp4 = 0;
+            float2 gd[4];
+            int patch[4];
+            uint32_t carry = 0;
+#pragma unroll
+            for (int k = 3; k >= 0; --k) {
+                gd[k] = make_float2(0.f, 0.f);
+                patch[k] = -1;
+                if (i0 + k >= N) continue;
+                const uint32_t bit = 1u << (i0 + k);
+                const uint32_t code = hget(codes, k);
+                const int r = (int)(code >> 5), c = (int)(code & 31u);
+                const uint32_t gcode = code_of(qget(gq, k));
+                const WB obst = lut[code];
+                const int sa = c > SR ? c - SR : 0, sb2 = (c < SR ? SR - c : 0) + 2;   // window columns start at c - SR
+                const uint2 *brow = &board[(r - SR) * 32];
+                uint32_t acc[(4 * (V2 + 3) + 31) / 32 + 1];
+#pragma unroll
+                for (int j = 0; j < (int)(sizeof(acc) / sizeof(acc[0])); ++j) acc[j] = 0;
+                uint32_t blk_up = 0, blk_mid = 0, blk_dn = 0;
+#pragma unroll
+                for (int wr = 0; wr < V; ++wr) {
+                    const uint2 b = brow[wr * 32];  // rows outside the map read neighbouring shared memory: masked by the obstacle plane
+                    constexpr uint32_t M4 = VM << 2;
+                    const uint32_t o4 = (wr * V >= 2 ? (uint32_t)(obst >> (wr * V - 2)) : (uint32_t)(obst << 2)) & M4;
+                    uint32_t occ4 = ((b.x >> sa) << sb2) & M4;
+                    if (wr == SR) occ4 &= ~(4u << SR);  // my own cell is not "another agent" (ENV:737)
+                    const uint32_t goal4 = ((b.y >> sa) << sb2) & M4;
+                    const uint32_t agent4 = occ4 & ~o4;
+                    const uint32_t blk4 = occ4 | o4;
+                    const uint32_t g4 = goal4 & ~blk4;
+                    if (wr == SR - 1) blk_up = blk4;
+                    if (wr == SR) blk_mid = blk4;
+                    if (wr == SR + 1) blk_dn = blk4;
+                    const char *tb = reinterpret_cast<const char *>(t1);
+                    const uint32_t t = *reinterpret_cast<const uint32_t *>(tb + o4) +
+                                       (*reinterpret_cast<const uint32_t *>(tb + agent4) << 1) +
+                                       (*reinterpret_cast<const uint32_t *>(tb + g4) << 2);   // ENV:730-745 codes 1 / 2 / 4
+                    const int bitpos = 4 * (V * wr + (k & 3));  // agent k's bytes start k bytes into its first stage word
+                    const int wi = bitpos >> 5, sh = bitpos & 31;
+                    acc[wi] |= t << sh;
+                    if (sh + 4 * V > 32) acc[wi + 1] |= t >> (32 - sh);
+                }
+                // ENV:761-771: a direction is valid iff its neighbour is neither obstacle nor agent
+                const uint32_t am = 1u | ((~blk_up >> (2 + SR)) & 1u) << 1 | ((~blk_mid >> (2 + SR + 1)) & 1u) << 2 |
+                                    ((~blk_dn >> (2 + SR)) & 1u) << 3 | ((~blk_mid >> (2 + SR - 1)) & 1u) << 4;
+                masks4 |= am << (8 * k);
+                // own goal (code 3): the goal plane wrote 4 there; patched after the quad's words are stored
+                {
+                    const int dr = (int)(gcode >> 5) - r + SR, dc = (int)(gcode & 31u) - c + SR;
+                    if ((unsigned)dr < (unsigned)V && (unsigned)dc < (unsigned)V) {
+                        const int ci = dr * V + dc;
+                        const bool occ_other = (ci != SR * V + SR) && ((board[(gcode >> 5) * 32].x >> (gcode & 31u)) & 1u);
+                        if (!((obst >> ci) & 1) && !occ_other) patch[k] = V2 * k + ci;
+                    }
+                }
+                // words of this agent: first word index (V2 * k) / 4, k leading bytes belong to agent k-1
+                constexpr int NWMAX = (V2 + 3 + 3) / 4;
+                const int j0 = (V2 * k) >> 2;
+                const int nw = ((k & 3) + V2 + 3) >> 2;
+#pragma unroll
+                for (int m = NWMAX - 1; m >= 0; --m) {
+                    if (m >= nw) continue;
+                    const uint32_t sel = (m & 1) ? (acc[m >> 1] >> 16) : acc[m >> 1];
+                    uint32_t w = __byte_perm(0x03020100u, 0x00000004u, sel);
+                    if (m == nw - 1 && (((k & 3) + V2) & 3) != 0) w |= carry;   // trailing partial word shared with agent k+1
+                    if (m == 0 && (k & 3) != 0) carry = w;                      // leading partial word: merged by agent k-1
+                    else if (active) my_stage[j0 + m] = w;
+                }
+                // ENV:330-335
+                {
+                    const int gi0 = (int)(gcode >> 5) - r + (R - 1), gi1 = (int)(gcode & 31u) - c + (C - 1) + 2 * R - 1;
+                    gd[k] = make_float2(gdt[gi0], gdt[gi1]);
+                }
+                if (bp_m & bit) bp4 |= 1u << (8 * k);
+                if (p.sample_mode) {
+                    const uint32_t x = qget(rnd, k);
+                    uint32_t na;
+                    if (p.sample_mode == 1) na = kth[am * 8 + __umulhi(x, (uint32_t)__popc(am))];
+                    else na = __umulhi(x, 5u);
+                    next4 |= na << (8 * k);
+                }
+                if (undo && (mv_m & bit)) {   // back to snapshot i-1
+                    const int a = (int)((act4 >> (8 * k)) & 0xFFu);
+                    const int d = (int)(int8_t)__byte_perm(0x2001E000u, 0x000000FFu, (uint32_t)a);
+                    const uint32_t ocode = code - (uint32_t)d;
+                    board[r * 32].x &= ~(1u << c);
+                    board[(ocode >> 5) * 32].x |= 1u << (ocode & 31u);
+                }
+            }
+            if (active) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (patch[k] >= 0) reinterpret_cast<uint8_t *>(my_stage)[patch[k]] = 3;
+                // action masks of the quad: 4 x 5 bytes = 5 words after the observation words
+                uint32_t lo[4], hi[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint32_t m = (masks4 >> (8 * k)) & 0x1Fu;
+                    lo[k] = ((m & 15u) * 0x00204081u) & 0x01010101u;
+                    hi[k] = m >> 4;
+                }
+                my_stage[OBS_W + 0] = lo[0];
+                my_stage[OBS_W + 1] = hi[0] | (lo[1] << 8);
+                my_stage[OBS_W + 2] = (lo[1] >> 24) | (hi[1] << 8) | (lo[2] << 16);
+                my_stage[OBS_W + 3] = (lo[2] >> 16) | (hi[2] << 16) | (lo[3] << 24);
+                my_stage[OBS_W + 4] = (lo[3] >> 8) | (hi[3] << 24);
+                if (p.o_goal_delta) {
+                    if (VEC) {
+                        float4 *g4p = reinterpret_cast<float4 *>(p.o_goal_delta + ab + i0);
+                        g4p[0] = make_float4(gd[0].x, gd[0].y, gd[1].x, gd[1].y);
+                        g4p[1] = make_float4(gd[2].x, gd[2].y, gd[3].x, gd[3].y);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) if (i0 + k < N) p.o_goal_delta[ab + i0 + k] = gd[k];
+                    }
+                }
+                if (p.o_blocking_prev) stq8<VEC>(p.o_blocking_prev, ab + i0, i0, N, true, bp4);
+                if (p.sample_mode) stq8<VEC>(reinterpret_cast<uint8_t *>(p.o_next_actions), ab + i0, i0, N, true, next4);
+            }
+            // ------------------------------------------------ coalesced flush of the quad's byte channels
+            __syncwarp();
+            const size_t env0 = (size_t)tile * 32;
+            if (VEC) {
+                for (int w = lane; w < OBS_W + 5; w += 32) {
+                    const bool is_obs = w < OBS_W;
+                    unsigned char *gp = is_obs ? (p.o_local_obs ? p.o_local_obs + (env0 * N + i0) * V2 + 4 * w : nullptr)
+                                               : (p.o_action_mask ? reinterpret_cast<unsigned char *>(p.o_action_mask) +
+                                                                        (env0 * N + i0) * 5 + 4 * (w - OBS_W) : nullptr);
+                    const int gstride = is_obs ? N * V2 : N * 5;
+                    if (gp) {
+                        if (act_w == full) {
+#pragma unroll 8
+                            for (int e = 0; e < 32; ++e)
+                                *reinterpret_cast<uint32_t *>(gp + (size_t)e * gstride) = stage_w[e * E.stage_stride + w];
+                        } else {
+                            for (int e = 0; e < 32; ++e)
+                                if ((act_w >> e) & 1u)
+                                    *reinterpret_cast<uint32_t *>(gp + (size_t)e * gstride) = stage_w[e * E.stage_stride + w];
+                        }
+                    }
+                }
+            } else {
+                const int na = (N - i0) < 4 ? (N - i0) : 4;
+                for (int e = 0; e < 32; ++e) {
+                    if (!((act_w >> e) & 1u)) continue;
+                    const uint8_t *src = reinterpret_cast<const uint8_t *>(stage_w + e * E.stage_stride);
+                    if (p.o_local_obs) {
+                        uint8_t *dst = p.o_local_obs + ((env0 + e) * N + i0) * V2;
+                        for (int b = lane; b < na * V2; b += 32) dst[b] = src[b];
+                    }
+                    if (p.o_action_mask) {
+                        uint8_t *dst = reinterpret_cast<uint8_t *>(p.o_action_mask) + ((env0 + e) * N + i0) * 5;
+                        for (int b = lane; b < na * 5; b += 32) dst[b] = src[4 * OBS_W + b];
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    };
+    emit(ok, !reassigned, moved_m, bprev_m);
+
+    // ---------------------------------------------------------------- pass 3: owner masks, locks, blocking, wait-for graph
+    // The boards are dead: their memory now holds rowm[r] (.x) / colm[c] (.y): bit a = agent a's final row / column.
+    for (int r = 0; r < E.board_rows; ++r) board[r * 32] = make_uint2(0u, 0u);
+    for (int q = 0; q < NQ; ++q) {
+        const uint2 codes = scr_pos[q * 32];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (4 * q + k >= N || !ok) continue;
+            const uint32_t code = hget(codes, k);
+            board[(code >> 5) * 32].x |= 1u << (4 * q + k);
+            board[(code & 31u) * 32].y |= 1u << (4 * q + k);
+        }
+    }
+    uint32_t blocking_m = 0, coloc_any = 0, wf_alive = 0;
+    bool dl_any = false, ll_any = false;
+    const uint32_t intent_m = allN & ~reached_m;  // ENV:619-621: only agents that have not (sticky-)reached press
+    for (int q = 0; q < NQ; ++q) {
+        const int i0 = 4 * q;
+        const uint2 codes = scr_pos[q * 32];
+        const uint2 deltas = scr_delta[q * 32];
+        const uint32_t act4 = scr_act[q * 32];
+        uint32_t ptr4 = 0xFFFFFFFFu;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (i0 + k >= N || !ok) continue;
+            const int i = i0 + k;
+            const uint32_t bit = 1u << i;
+            const uint32_t code = hget(codes, k);
+            const int r = (int)(code >> 5), c = (int)(code & 31u);
+            const uint32_t here = board[r * 32].x & board[c * 32].y;   // agents on my cell (me included)
+            if (here & ~bit) coloc_any |= bit;
+            // ENV:389-438 neighbours within Manhattan distance `nearby`, via the row / column masks
+            if (p.lock_enabled && !(ongoal_m & bit)) {
+                uint32_t nb = 0, u = 0;
+                for (int w = 0; w <= p.nearby; ++w) {
+                    const int dd = p.nearby - w;
+                    if (c - w >= 0) u |= board[(c - w) * 32].y;
+                    if (c + w < C) u |= board[(c + w) * 32].y;
+                    uint32_t rm = 0;
+                    if (r - dd >= 0) rm |= board[(r - dd) * 32].x;
+                    if (r + dd < R) rm |= board[(r + dd) * 32].x;
+                    nb |= rm & u;
+                }
+                nb &= ~here;
+                if (__popc(nb) >= p.min_nb) {
+                    const uint32_t P = nb | bit;
+                    if (!(P & Gd) && !(P & Md) && (P & Fd)) dl_any = true;
+                    if (!(P & Gl) && (P & Ml)) {
+                        int red = (int)(int16_t)hget(deltas, k);
+                        uint32_t rest = nb;
+                        while (rest) {
+                            const int a = __ffs(rest) - 1;
+                            rest &= rest - 1;
+                            red += (int)(int16_t)hget(scr_delta[(a >> 2) * 32], a & 3);
+                        }
+                        if (red <= p.eps_floor) ll_any = true;
+                    }
+                }
+            }
+            // intended cell (kept even when invalid, ENV:514-515) -> who stands there
+            const int a = (int)((act4 >> (8 * k)) & 0xFFu);
+            const bool mv = (moved_m & bit) != 0;
+            int ir = r, ic = c;
+            if (!mv) { ir += (a == 3) - (a == 1); ic += (a == 2) - (a == 4); }
+            uint32_t owner = 0;
+            if ((unsigned)ir < (unsigned)R && (unsigned)ic < (unsigned)C) owner = board[ir * 32].x & board[ic * 32].y & ~bit;
+            if (!p.lifelong && (intent_m & bit)) blocking_m |= owner;   // ENV:609-623 (filtered below)
+            if ((failed_m & bit) && owner) {   // wait-for edge i -> owner
+                ptr4 = (ptr4 & ~(0xFFu << (8 * k))) | ((uint32_t)(31 - __clz(owner)) << (8 * k));
+                wf_alive |= bit;
+            }
+        }
+        scr_act[q * 32] = ptr4;
+    }
+    blocking_m &= reached_m & ~moved_m;
+    // wait-for cycles: strip agents whose target is gone or that nobody waits for, until stable
+    uint32_t wf_m = 0;
+    if (__any_sync(full, wf_alive != 0)) {
+        uint32_t alive = wf_alive;
+        for (;;) {
+            uint32_t keep = 0, targets = 0, rest = alive;
+            while (rest) {
+                const int i = __ffs(rest) - 1;
+                rest &= rest - 1;
+                const uint32_t t = (scr_act[(i >> 2) * 32] >> (8 * (i & 3))) & 0xFFu;
+                if ((alive >> t) & 1u) { keep |= 1u << i; targets |= 1u << t; }
+            }
+            keep &= targets;
+            const bool changed = keep != alive;
+            alive = keep;
+            if (!__any_sync(full, changed)) break;
+        }
+        wf_m = alive;
+    }
+    const bool wf_any = wf_m != 0;
+    wfg_steps += wf_any;
+    const int blocking_step = __popc(blocking_m);
+    blocking_total += blocking_step;
+
+    // ---------------------------------------------------------------- lock detection result, ENV:595-606
+    bool dl_step = false, ll_step = false, dl_event = false, ll_event = false;
+    if (p.lock_enabled) {
+        dl_step = count_after >= p.dw && dl_any;
+        ll_step = !dl_step && count_after >= p.lw && ll_any;
+        dl_event = dl_step && !(lock_prev & 1);
+        ll_event = ll_step && !(lock_prev & 2);
+        lock_prev = (dl_step ? 1 : 0) | (ll_step ? 2 : 0);
+        dl_steps += dl_step; ll_steps += ll_step; dl_events += dl_event; ll_events += ll_event;
+        lock_count = count_after;
+    }
+
+    // ---------------------------------------------------------------- rewards & termination, ENV:658-690
+    const uint32_t scratch_on = p.lifelong ? 0u : ongoal_m;   // reached_goal scratch (ENV:555)
+    bool terminated = false, truncated = false;
+    uint32_t bonus_m = 0, penalty_m = 0;
+    if (!p.lifelong && __popc(scratch_on) == N) { terminated = true; bonus_m = allN; }
+    else if (step_count >= p.steps_per_episode) {
+        terminated = true; truncated = true;  // F6
+        if (!p.lifelong) penalty_m = allN & ~scratch_on;
+    }
+    const bool done = ok && (terminated || truncated);
+    int rsum = 0;
+    for (int q = 0; q < NQ; ++q) {
+        const int i0 = 4 * q;
+        const uint2 codes = scr_pos[q * 32];
+        float rw[4];
+        uint32_t asf4 = 0, af4 = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            rw[k] = 0.f;
+            if (i0 + k >= N) continue;
+            const uint32_t bit = 1u << (i0 + k);
+            int rx2 = ((gstep_m & bit) ? 1 : 0) + ((bonus_m & bit) ? 2 : 0) - ((penalty_m & bit) ? 2 : 0);
+            if (coloc_any & bit) {   // ENV:658-666, -1 per co-located pair member
+                const uint32_t code = hget(codes, k);
+                rx2 -= 2 * (__popc(board[(code >> 5) * 32].x & board[(code & 31u) * 32].y) - 1);
+            }
+            rsum += rx2;
+            rw[k] = 0.5f * (float)rx2;
+            asf4 |= (uint32_t)(((moved_m & bit) ? MAPF_ASF_MOVED : 0) | ((failed_m & bit) ? MAPF_ASF_FAILED_MOVE : 0) |
+                               ((gstep_m & bit) ? MAPF_ASF_GOAL_REACHED : 0) | ((blocking_m & bit) ? MAPF_ASF_BLOCKING : 0) |
+                               ((wf_m & bit) ? MAPF_ASF_WFG_CYCLE : 0) | ((ongoal_m & bit) ? MAPF_ASF_ON_GOAL : 0)) << (8 * k);
+            af4 |= (uint32_t)(((reached_m & bit) ? MAPF_AF_REACHED : 0) | ((completed_m & bit) ? MAPF_AF_COMPLETED_ONCE : 0) |
+                              ((blocking_m & bit) ? MAPF_AF_BLOCKING_PREV : 0)) << (8 * k);
+        }
+        if (ok) {
+            if (p.o_reward) {
+                if (VEC) *reinterpret_cast<float4 *>(p.o_reward + ab + i0) = make_float4(rw[0], rw[1], rw[2], rw[3]);
+                else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) if (i0 + k < N) p.o_reward[ab + i0 + k] = rw[k];
+                }
+            }
+            if (p.o_agent_step_flags) stq8<VEC>(p.o_agent_step_flags, ab + i0, i0, N, true, asf4);
+            stq8<VEC>(p.agent_flags, ab + i0, i0, N, true, af4);
+        }
+    }
+    ep_return_x2 += rsum;
+    const int n_comp = __popc(completed_m), n_reach = __popc(reached_m);
+    if (ok) {
+        if (p.o_info) {  // integer sources of info["__all__"], ENV:639-656
+            int4 *io = p.o_info + (size_t)env * 4;
+            io[0] = make_int4(arrivals, p.lifelong ? goals_total : n_reach, blocking_step, blocking_total);
+            io[1] = make_int4(dl_step, ll_step, dl_event, ll_event);
+            io[2] = make_int4(dl_events, ll_events, dl_steps, ll_steps);
+            io[3] = make_int4(n_comp, step_count, n_reach, wfg_steps);
+        }
+        if (p.o_terminated) p.o_terminated[env] = terminated;
+        if (p.o_truncated) p.o_truncated[env] = truncated;
+        if (p.o_step_flags)
+            p.o_step_flags[env] = (uint8_t)((terminated ? MAPF_SF_TERMINATED : 0) | (truncated ? MAPF_SF_TRUNCATED : 0) |
+                                            (dl_step ? MAPF_SF_DEADLOCK_STEP : 0) | (ll_step ? MAPF_SF_LIVELOCK_STEP : 0) |
+                                            (dl_event ? MAPF_SF_DEADLOCK_EVENT : 0) | (ll_event ? MAPF_SF_LIVELOCK_EVENT : 0) |
+                                            (reassigned ? MAPF_SF_GOAL_REASSIGNED : 0) | (wf_any ? MAPF_SF_WFG_CYCLE : 0));
+    }
+
+    // ---------------------------------------------------------------- episode end: metrics, auto-reset
+    if (done) {   // episode-end metric sums, src/trainers/callbacks.py:152,173,335-345
+        double *m = p.env_metrics + (size_t)env * MAPF_METRIC_COUNT;
+        const double gt = p.lifelong ? (double)goals_total : (double)n_reach;  // ENV:630-633
+        m[MAPF_M_EPISODES] += 1.0;
+        m[MAPF_M_RETURN_SUM] += 0.5 * (double)ep_return_x2;
+        m[MAPF_M_LENGTH_SUM] += (double)step_count;
+        m[MAPF_M_SUCCESS_SUM] += (terminated && !truncated) ? 1.0 : 0.0;
+        m[MAPF_M_GOALS_REACHED_SUM] += gt;
+        m[MAPF_M_BLOCKING_COUNT_SUM] += (double)blocking_total;
+        m[MAPF_M_DEADLOCK_COUNT_SUM] += (double)dl_events;
+        m[MAPF_M_LIVELOCK_COUNT_SUM] += (double)ll_events;
+        m[MAPF_M_DEADLOCK_STEPS_SUM] += (double)dl_steps;
+        m[MAPF_M_LIVELOCK_STEPS_SUM] += (double)ll_steps;
+        m[MAPF_M_THROUGHPUT_SUM] += gt / (double)(step_count > 1 ? step_count : 1);  // ENV:655
+        m[MAPF_M_COMPLETION_RATIO_SUM] += (double)n_comp / (double)N;                 // ENV:638
+        m[MAPF_M_WFG_CYCLE_STEPS_SUM] += (double)wfg_steps;
+        episodes += 1;
+    }
+    const bool do_reset = done && p.auto_reset;
+    if (__any_sync(full, do_reset)) {   // ENV:440-472 inside the launch (benchmark loop semantics)
+        if (do_reset) {
+            bool sample = !p.deterministic;
+            const int F = p.num_free[0];
+            if (sample && F < 2 * N) { errs |= MAPF_DEV_ERR_TOO_FEW_CELLS; sample = false; }
+            // scratch in the dead board memory: cs[a] in .x, cg[a] in .y of row a (cell-linear ids)
+            if (sample) {
+                // ENV:267-282 by symmetric rejection, the rule of draw_layout<G>: every slot draws uniformly,
+                // a slot equal to a lower-numbered slot (starts before goals) redraws in the next round
+                uint32_t rs = allN, rg = allN, rounds = 0;
+                while (rs | rg) {
+                    for (int a = 0; a < N; ++a) {
+                        if (!(((rs | rg) >> a) & 1u)) continue;
+                        const uint4 x = ph_env(rng_counter + rounds, (uint32_t)a, 0x52455345u /* "RESE" */, 0);
+                        uint2 v = board[a * 32];
+                        if ((rs >> a) & 1u) v.x = (uint32_t)select_kth(freebits, p.fw, (int)__umulhi(x.x, (uint32_t)F));
+                        if ((rg >> a) & 1u) v.y = (uint32_t)select_kth(freebits, p.fw, (int)__umulhi(x.y, (uint32_t)F));
+                        board[a * 32] = v;
+                    }
+                    rs = 0; rg = 0;
+                    for (int g = 0; g < N; ++g) {
+                        const uint2 me = board[g * 32];
+                        for (int a = 0; a < N; ++a) {
+                            const uint2 o = board[a * 32];
+                            if (a < g && o.x == me.x) rs |= 1u << g;
+                            if (o.x == me.y) rg |= 1u << g;
+                            if (a < g && o.y == me.y) rg |= 1u << g;
+                        }
+                    }
+                    rounds++;
+                }
+                rng_counter += rounds;
+            }
+            for (int q = 0; q < NQ; ++q) {
+                const int i0 = 4 * q;
+                uint4 stq = make_uint4(0, 0, 0, 0), ggq = stq;
+                const uint4 curp = ldq32<VEC>(p.positions, ab + i0, i0, N, true, 0u);
+                const uint4 curg = ldq32<VEC>(p.goals, ab + i0, i0, N, true, 0u);
+                uint4 detst = make_uint4(0, 0, 0, 0);
+                if (p.deterministic) detst = ldq32<VEC>(p.starts, ab + i0, i0, N, true, 0u);
+                uint2 codes = make_uint2(0u, 0u);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (i0 + k >= N) continue;
+                    uint32_t st, gg;
+                    if (p.deterministic) { st = qget(detst, k); gg = qget(curg, k); }  // F7
+                    else if (sample) {
+                        const uint2 v = board[(i0 + k) * 32];
+                        st = pack_rc((int)v.x / C, (int)v.x % C);
+                        gg = pack_rc((int)v.y / C, (int)v.y % C);
+                    } else { st = qget(curp, k); gg = qget(curg, k); }
+                    qset(stq, k, st); qset(ggq, k, gg);
+                    hset(codes, k, code_of(st));
+                }
+                scr_pos[q * 32] = codes;
+                stq32<VEC>(p.positions, ab + i0, i0, N, true, stq);
+                if (sample) { stq32<VEC>(p.starts, ab + i0, i0, N, true, stq); stq32<VEC>(p.goals, ab + i0, i0, N, true, ggq); }
+                stq8<VEC>(p.agent_flags, ab + i0, i0, N, true, 0u);
+                if (p.lock_enabled) {
+                    const uint4 z = make_uint4(0, 0, 0, 0);
+                    stq32<VEC>(p.lock_gp, ab + i0, i0, N, true, z);
+                    stq32<VEC>(p.lock_mv, ab + i0, i0, N, true, z);
+                    stq32<VEC>(p.lock_fm, ab + i0, i0, N, true, z);
+                }
+            }
+            step_count = 0; lock_count = 0; lock_head = 0; lock_prev = 0; goals_total = 0; blocking_total = 0;
+            dl_events = ll_events = dl_steps = ll_steps = 0; ep_return_x2 = 0; wfg_steps = 0;
+            // boards of the new layout: first observation of the next episode (final state, no staggering at reset)
+            for (int r = 0; r < E.board_rows; ++r) board[r * 32] = make_uint2(0u, 0u);
+            for (int i = 0; i < N; ++i) {
+                const uint32_t pc = hget(scr_pos[(i >> 2) * 32], i & 3);
+                const uint32_t gc = code_of(p.goals[ab + i]);
+                board[(pc >> 5) * 32].x |= 1u << (pc & 31u);
+                board[(gc >> 5) * 32].y |= 1u << (gc & 31u);
+            }
+        }
+        emit(do_reset, false, 0u, 0u);
+    }
+
+    // ---------------------------------------------------------------- env words write-back
+    if (ok) {
+        int4 *ew = p.env_words + (size_t)env * 4;
+        ew[0] = make_int4(step_count, lock_count, lock_prev, goals_total);
+        ew[1] = make_int4(blocking_total, dl_events, ll_events, dl_steps);
+        ew[2] = make_int4(ll_steps, (int)rng_counter, ep_return_x2, wfg_steps);
+        ew[3] = make_int4(episodes, lock_head, w3.z, w3.w);
+    }
+    __syncwarp();
+    }  // tile loop
+    errs = __reduce_or_sync(full, errs);
+    if (errs && lane == 0) atomicOr(p.err_bits, errs);
+}
+
+}  // namespace mapf

@@ -48,14 +48,17 @@ struct Philox {
     }
 };
 
-// One action draw: Philox keyed by (seed, global env id), counter = (call counter, agent).
+// One action draw: Philox keyed by (seed, global env id), counter = (call counter, agent quad).
 __device__ __forceinline__ int sample_action(unsigned long long seed, long long env_global, int agent,
                                              unsigned long long counter, int mask_bits /* <0: unmasked */) {
     Philox ph(seed ^ 0xA511E9B3ull, env_global);
-    uint4 x = ph((uint32_t)counter, (uint32_t)(counter >> 32), (uint32_t)agent, 0x41435421u);
-    if (mask_bits < 0) return (int)__umulhi(x.x, 5u);  // scripts/benchmark_multi_agent_env.py:38-39
+    // one Philox block serves the 4 agents of a quad: agent a takes word a & 3 of block a >> 2
+    const uint4 x4 = ph((uint32_t)counter, (uint32_t)(counter >> 32), (uint32_t)(agent >> 2), 0x41435421u);
+    const int w = agent & 3;
+    const uint32_t x = w == 0 ? x4.x : w == 1 ? x4.y : w == 2 ? x4.z : x4.w;
+    if (mask_bits < 0) return (int)__umulhi(x, 5u);    // scripts/benchmark_multi_agent_env.py:38-39
     const int n = __popc(mask_bits);                   // scripts/benchmark_multi_agent_env.py:42-57
-    return n ? (int)__fns((unsigned)mask_bits, 0, (int)__umulhi(x.x, (uint32_t)n) + 1) : 0;
+    return n ? (int)__fns((unsigned)mask_bits, 0, (int)__umulhi(x, (uint32_t)n) + 1) : 0;
 }
 
 // ------------------------------------------------------------------ small helpers

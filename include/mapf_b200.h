@@ -69,7 +69,7 @@ typedef struct mapf_config {
     int64_t env_id_base;     /* global id of env 0 (Philox key => results independent of sharding) */
     uint64_t seed;           /* ENV:74 */
     int32_t device;          /* CUDA device ordinal */
-    int32_t reserved;
+    int32_t step_kernel;     /* 0 auto, 1 lane-per-agent kernel, 2 env-per-thread kernel (cols <= 32, shared map) */
 } mapf_config;
 
 /* Words of the per-env int32 state block env_words[B, MAPF_ENV_WORDS]. */
@@ -280,6 +280,10 @@ int mapf_poll_errors(mapf_handle *h, uint32_t *bits, void *stream);
 
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
 int64_t mapf_launch_count(const mapf_handle *h);
+
+/* Which step kernel this handle launches: 1 = lane-per-agent (one agent per lane, sub-warp per env),
+ * 2 = env-per-thread (one env per thread, bitboards in shared memory).  Same results either way. */
+int mapf_step_kernel_kind(const mapf_handle *h);
 
 #ifdef __cplusplus
 }
