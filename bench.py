@@ -37,6 +37,14 @@ sys.path.insert(0, str(REPO))
 
 METRIC = "agent_steps_per_sec"
 UNIT = "agent-steps/s"
+# mapf_step_kernel_kind() -> kernel symbol (include/mapf_b200.h)
+KERNEL_NAMES = {1: "mapf_step_kernel<16,2> (lane-per-agent)", 2: "mapf_step_env_kernel<2,true> (env-per-thread)"}
+
+
+def default_traffic(kind: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the step kernel at the default C3 shape, from the
+    committed `ncu --set full` captures (profiles/README.md); None for other shapes."""
+    return {1: 54.3e6, 2: 84.1e6}.get(kind)
 
 
 def workload(args) -> tuple[dict, np.ndarray]:
@@ -258,6 +266,7 @@ def run_b200(args, rank: int, local_rank: int, world: int):
     sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
     launches = sum(e.launch_count for e in envs) - launches0
+    kind = int(nat.lib().mapf_step_kernel_kind(envs[0]._h))
     ms_total = t_begin.elapsed_time(t_end)
     kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in zip(ev0, ev1)]))
     for e in envs:
@@ -320,13 +329,15 @@ def run_b200(args, rank: int, local_rank: int, world: int):
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int16/u8", "data": "synthetic", "impl": "b200", "config": config_dict(args, world),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": args.traffic_bytes, "kernel": "mapf_step_kernel", "kernel_ms": kernel_ms,
+                         "traffic": args.traffic_bytes if args.traffic_bytes is not None else (
+                             default_traffic(kind) if (B, N, V) == (65536, 16, 5) else None),
+                         "kernel": KERNEL_NAMES[kind], "kernel_ms": kernel_ms,
                          "algorithmic_bytes_per_launch": alg_bytes, "bytes_per_agent_step": bytes_per_as,
                          "peak_source": peak_src},
             "e2e": {"value": world * B * N * Ke / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": Ke, "api": "mapf_step_host (C ABI, pinned host buffers)",
                     "actions": "uniform random from pinned host buffers", "checksum": checksum},
-            "gpu_launches": int(launches), "clocks": clocks,
+            "gpu_launches": int(launches), "clocks": clocks, "step_kernel": {1: "lane", 2: "env"}.get(kind),
             "episode_metrics": {k: metrics[k] for k in ("episodes", "goals_reached_mean", "deadlock_steps_mean",
                                                         "livelock_steps_mean", "throughput_mean")},
         }

@@ -107,6 +107,7 @@ struct mapf_handle {
     int env_threads, env_grid;
     bool use_env_kernel;
     uint32_t *d_map_rows, *d_free_bits;
+    uint32_t *d_env_tables;
     int32_t *d_num_free;
     bool map_set;
     uint32_t *d_err;
@@ -222,6 +223,7 @@ void fill_params(const mapf_handle *h, mapf::KParams &p) {
     p.den0 = (float)(c.rows - 1 > 1 ? c.rows - 1 : 1);  // ENV:152-155
     p.den1 = (float)(c.cols - 1 > 1 ? c.cols - 1 : 1);
     p.map_rows = h->d_map_rows; p.free_bits = h->d_free_bits; p.num_free = h->d_num_free;
+    p.env_tables = h->d_env_tables;
     p.wpr = h->wpr; p.map_words = h->map_words; p.fw = h->fw;
     p.positions = reinterpret_cast<uint32_t *>(h->st.positions);
     p.goals = reinterpret_cast<uint32_t *>(h->st.goals);
@@ -386,10 +388,10 @@ int mapf_create(const mapf_config *cfg, mapf_handle **out) {
     // variable MAPF_STEP_KERNEL=lane|env overrides "auto").  Both are sm_100a kernels with identical results.
     h->env_threads = 0;
     h->use_env_kernel = false;
-    if (e1 == cudaSuccess && c.cols <= 32 && c.rows <= 64 && !c.per_env_maps) {
+    if (e1 == cudaSuccess && c.cols <= 32 && c.rows <= mapf::ENV_MAX_ROWS && !c.per_env_maps) {
         const int ntiles = (c.num_envs + 31) / 32;
         int want = (ntiles + (nsm > 0 ? nsm : 1) - 1) / (nsm > 0 ? nsm : 1);  // warps per CTA for one resident wave
-        if (want > 16) want = 16;
+        if (want > 14) want = 14;  // __launch_bounds__(448) of mapf_step_env_kernel
         if (want < 1) want = 1;
         for (int w = want; w >= 1; --w) {
             mapf::EnvLayout E = mapf::make_env_layout(c.num_agents, c.rows, c.cols, h->SR, h->fw, w);
@@ -414,13 +416,17 @@ int mapf_create(const mapf_config *cfg, mapf_handle **out) {
         if (want_kernel == 0) {
             if (const char *ov = getenv("MAPF_STEP_KERNEL")) want_kernel = (ov[0] == 'l') ? 1 : (ov[0] == 'e') ? 2 : 0;
         }
-        if (want_kernel == 2 && !h->env_threads) {
+        if (c.step_kernel == 2 && !h->env_threads) {   // explicit request only; the environment variable is a preference
             delete h;
             return fail(MAPF_ERR_UNSUPPORTED,
                         "env-per-thread step kernel needs cols <= 32, rows <= 64 and a shared map (got %dx%d, per_env_maps=%d)",
                         c.rows, c.cols, c.per_env_maps);
         }
-        h->use_env_kernel = h->env_threads && want_kernel != 1;
+        // auto: the env-per-thread kernel is one latency chain per warp (~50 us on B200, whatever the batch), so it only
+        // pays once the batch fills the GPU several times over (measured cross-over ~50k envs of 16 agents on 148 SMs);
+        // below that the lane-per-agent kernel has 16x more warps in flight and wins.
+        const long long ntiles = (c.num_envs + 31) / 32;
+        h->use_env_kernel = h->env_threads && (want_kernel == 2 || (want_kernel == 0 && ntiles >= 12LL * (nsm > 0 ? nsm : 1)));
     }
     cudaError_t e3 = cudaMalloc(&h->d_err, 4);
     if (e3 == cudaSuccess) e3 = cudaMemset(h->d_err, 0, 4);
@@ -447,6 +453,7 @@ int mapf_destroy(mapf_handle *h) {
     }
     if (h->hstream) cudaStreamDestroy(h->hstream);
     cudaFree(h->d_map_rows); cudaFree(h->d_free_bits); cudaFree(h->d_num_free); cudaFree(h->d_err);
+    cudaFree(h->d_env_tables);
     delete h;
     return MAPF_OK;
 }
@@ -489,6 +496,16 @@ int mapf_set_map(mapf_handle *h, const uint8_t *grid) {
     CUDA_TRY(cudaMemcpy(h->d_map_rows, rows.data(), rows.size() * 4, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(h->d_free_bits, freeb.data(), freeb.size() * 4, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(h->d_num_free, nfree.data(), nfree.size() * 4, cudaMemcpyHostToDevice));
+    cudaFree(h->d_env_tables);
+    h->d_env_tables = nullptr;
+    if (h->env_threads) {   // table image of the env-per-thread kernel (obstacle windows, free rows, quotient tables)
+        const mapf::EnvLayout &E = h->env_layout;
+        std::vector<unsigned char> img((size_t)E.tables_bytes, 0);
+        mapf::build_env_tables(h->SR, R, C, h->wpr, h->fw, rows.data(), freeb.data(), h->cfg.normalize_goal_delta != 0,
+                               (float)(R - 1 > 1 ? R - 1 : 1), (float)(C - 1 > 1 ? C - 1 : 1), img.data());
+        CUDA_TRY(cudaMalloc(&h->d_env_tables, img.size()));
+        CUDA_TRY(cudaMemcpy(h->d_env_tables, img.data(), img.size(), cudaMemcpyHostToDevice));
+    }
     h->map_set = true;
     return MAPF_OK;
 }

@@ -28,47 +28,45 @@
 
 namespace mapf {
 
-// Shared-memory carve-up of the env-per-thread kernel (byte offsets, computed on the host).
+// Shared-memory carve-up of the env-per-thread kernel.  Everything the hot loops address is at a
+// compile-time offset (folded into the LDS/STS immediates); only the per-warp stride is a run-time value.
+// The CTA-wide tables [0, tables_bytes) are built once on the host (mapf_set_map) and copied in.
+constexpr int ENV_MAX_ROWS = 64;       // map rows the env-per-thread kernel accepts (columns: 32)
+constexpr int ENV_T1_OFF = 0;          // u32[1 << V]: bit j -> nibble j
+constexpr int ENV_KTH_OFF = 512;       // u8[32*8]: position of the (k+1)-th set bit of a 5-bit mask
+constexpr int ENV_FREEROW_OFF = 768;   // u32[R]: bit c = cell (r, c) is free
+constexpr int ENV_FREEBITS_OFF = 1024; // u32[fw]: cell-linear free bitmap (reset draws, ENV:267-282)
+constexpr int ENV_GDT_OFF = 1280;      // float[(2R-1)+(2C-1)] goal-delta quotients (ENV:330-335)
+constexpr int ENV_LUT_OFF = 2048;      // obstacle window of every cell: u32[R*32] (V <= 5) or u64[R*32] (V = 7)
+constexpr int ENV_ROW_PAD = 2;         // zero rows around the owner masks of the epilogue (lock_nearby_manhattan <= 2)
+
+// stage row of one env and quad: 4 * V2 observation bytes + 20 action-mask bytes, odd word stride
+__host__ __device__ constexpr int env_stage_stride(int V2) { return ((4 * V2 + 20 + 3) / 4) | 1; }
+
 struct EnvLayout {
-    int lut_off;       // obstacle window of every cell: u32[R*32] (V <= 5) or u64[R*32] (V = 7)
-    int freerow_off;   // u32[R]: bit c = cell (r, c) is free
-    int freebits_off;  // u32[fw]: cell-linear free bitmap (reset draws, ENV:267-282)
-    int gdt_off;       // float[(2R-1)+(2C-1)] goal-delta quotients (ENV:330-335)
-    int t1_off;        // u32[1 << V]: bit j -> nibble j
-    int kth_off;       // u8[32*8]: position of the (k+1)-th set bit of a 5-bit mask
-    int warp_off, warp_bytes;                 // per-warp block
-    int board_off, scratch_off, stage_off;    // inside a warp block
-    int board_rows;    // max(R, C)
+    int tables_bytes;  // multiple of 16
+    int warp_bytes;    // per-warp block: [stage][boards][agent records]
+    int board_rows;    // max(R, C, N) + 2 * ENV_ROW_PAD
     int nq;            // ceil(N / 4)
-    int stage_stride;  // words per lane (odd => conflict-free)
     int total_bytes;
 };
 
 __host__ __device__ inline EnvLayout make_env_layout(int N, int R, int C, int SR, int fw, int warps) {
     const int V = 2 * SR + 1, V2 = V * V;
     EnvLayout E;
-    int o = 0;
-    E.lut_off = o; o += R * 32 * (V > 5 ? 8 : 4);
-    E.freerow_off = o; o += R * 4;
-    E.freebits_off = o; o += fw * 4;
-    E.gdt_off = o; o += ((2 * R - 1) + (2 * C - 1)) * 4;
-    E.t1_off = o; o += (1 << V) * 4;
-    E.kth_off = o; o += 32 * 8;
-    o = (o + 15) & ~15;
+    E.tables_bytes = (ENV_LUT_OFF + R * 32 * (V > 5 ? 8 : 4) + 15) & ~15;
     E.board_rows = R > C ? R : C;
     if (N > E.board_rows) E.board_rows = N;  // reset draws park 2N cell ids in the dead boards
+    E.board_rows += 2 * ENV_ROW_PAD;
     E.nq = (N + 3) / 4;
-    int w = 0;
-    E.board_off = w; w += E.board_rows * 32 * 8;
-    E.scratch_off = w; w += E.nq * 32 * 20;  // per quad and lane: 4 x u16 cell, 4 x i16 delta, 4 x u8 action
-    int sw = (4 * V2 + 20 + 3) / 4;
-    if (!(sw & 1)) sw += 1;
-    E.stage_stride = sw;
-    E.stage_off = w; w += 32 * sw * 4;
+    int w = 32 * env_stage_stride(V2) * 4;   // stage
+    w += E.board_rows * 32 * 8;              // boards: uint2 [row][lane]
+    w += 4 * E.nq * 32 * 4;                  // agent records: u32 [agent][lane]
     w = (w + 15) & ~15;
     E.warp_bytes = w;
-    E.warp_off = o; o += w * warps;
-    E.total_bytes = o;
+    // window rows above / below the map read up to 3 board rows beyond a warp's boards: keep that inside the allocation
+    E.total_bytes = E.tables_bytes + w * warps + 1024;
+    (void)fw;
     return E;
 }
 
@@ -158,63 +156,179 @@ __device__ __forceinline__ uint4 sample_quad(unsigned long long seed, long long 
     return ph((uint32_t)counter, (uint32_t)(counter >> 32), (uint32_t)quad, 0x41435421u);
 }
 
+// Host-side image of the CTA-wide tables (mapf_set_map); `rows` are the padded obstacle bit-rows of
+// the lane-per-agent kernel (bit c + PAD of row r + PAD = obstacle or out of bounds, ENV:718).
+inline void build_env_tables(int SR, int R, int C, int wpr, int fw, const uint32_t *rows,
+                             const uint32_t *free_bits, int normalize, float den0, float den1, unsigned char *img) {
+    const int V = 2 * SR + 1;
+    auto rowbits = [&](int r, int c0, int n) {  // n bits starting at map column c0 of map row r (padding = 1)
+        unsigned long long x = 0;
+        for (int j = 0; j < n; ++j) {
+            const int bit = c0 + j + PAD;
+            if ((rows[(r + PAD) * wpr + (bit >> 5)] >> (bit & 31)) & 1u) x |= 1ull << j;
+        }
+        return x;
+    };
+    uint32_t *t1 = reinterpret_cast<uint32_t *>(img + ENV_T1_OFF);
+    for (int x = 0; x < (1 << V); ++x) {
+        uint32_t s = 0;
+        for (int j = 0; j < V; ++j) s |= ((uint32_t)(x >> j) & 1u) << (4 * j);
+        t1[x] = s;
+    }
+    uint8_t *kth = img + ENV_KTH_OFF;
+    for (int m = 0; m < 32; ++m)
+        for (int k = 0; k < 8; ++k) {
+            int pos = 0, seen = 0;
+            for (int b = 0; b < 5; ++b)
+                if ((m >> b) & 1) { if (seen == k) pos = b; ++seen; }
+            kth[m * 8 + k] = (uint8_t)(k < seen ? pos : 0);
+        }
+    for (int cell = 0; cell < R * 32; ++cell) {
+        const int r = cell >> 5, c = cell & 31;
+        unsigned long long w = 0;
+        if (c < C)
+            for (int wr = 0; wr < V; ++wr) w |= rowbits(r - SR + wr, c - SR, V) << (wr * V);
+        if (V > 5) reinterpret_cast<unsigned long long *>(img + ENV_LUT_OFF)[cell] = w;
+        else reinterpret_cast<uint32_t *>(img + ENV_LUT_OFF)[cell] = (uint32_t)w;
+    }
+    uint32_t *freerow = reinterpret_cast<uint32_t *>(img + ENV_FREEROW_OFF);
+    for (int r = 0; r < R; ++r) freerow[r] = (uint32_t)(~rowbits(r, 0, C) & (C >= 32 ? 0xFFFFFFFFull : ((1ull << C) - 1ull)));
+    uint32_t *fb = reinterpret_cast<uint32_t *>(img + ENV_FREEBITS_OFF);
+    for (int i = 0; i < fw; ++i) fb[i] = free_bits[i];
+    float *gdt = reinterpret_cast<float *>(img + ENV_GDT_OFF);
+    const int nr = 2 * R - 1, n = nr + 2 * C - 1;
+    for (int i = 0; i < n; ++i) {   // ENV:330-335: one IEEE division per distinct (goal - pos) value
+        const bool row = i < nr;
+        const float d = (float)(row ? i - (R - 1) : i - nr - (C - 1));
+        gdt[i] = normalize ? d / (row ? den0 : den1) : d;
+    }
+}
+
+// ENV:284-304 at agent i's turn (rare path, kept out of line): the occupancy board IS snapshot i and the goal
+// board holds everybody's current goal.  Returns the new goal code (the old one if no cell is available).
+// .y of the result: bit 0 = one Philox draw consumed, bit 1 = MAPF_DEV_ERR_NO_GOAL_CELL.
+__device__ __noinline__ uint2 env_assign_new_goal(uint2 *board, const uint32_t *freerow, int R,
+                                                  const uint32_t *goal_override, const int32_t *goal_rank,
+                                                  size_t agent_index, int i, uint32_t gcode,
+                                                  unsigned long long seed, long long env_global,
+                                                  uint32_t rng_counter) {
+    uint32_t flags = 0;
+    board[(gcode >> 5) * 32].y &= ~(1u << (gcode & 31u));   // ENV:288 clear the old goal owner
+    uint32_t ng = 0xFFFFFFFFu;
+    if (goal_override) {
+        const uint32_t ov = goal_override[agent_index];
+        if (prow(ov) >= 0) ng = code_of(ov);
+    }
+    if (ng == 0xFFFFFFFFu) {
+        int n = 0;
+        for (int r = 0; r < R; ++r) { const uint2 b = board[r * 32]; n += __popc(freerow[r] & ~b.x & ~b.y); }
+        int kk = -1;
+        if (goal_rank) kk = goal_rank[agent_index];
+        if (kk < 0 && n > 0) {
+            const Philox ph(seed, env_global);
+            const uint4 x = ph(rng_counter, (uint32_t)i, 0x474F414Cu /* "GOAL" */, 0);
+            kk = (int)__umulhi(x.x, (uint32_t)n);
+            flags |= 1u;
+        }
+        if (n > 0 && kk < n) {
+            for (int r = 0; r < R; ++r) {
+                const uint2 b = board[r * 32];
+                const uint32_t cand = freerow[r] & ~b.x & ~b.y;
+                const int c = __popc(cand);
+                if (kk < c) { ng = (uint32_t)(r * 32) + __fns(cand, 0, kk + 1); break; }
+                kk -= c;
+            }
+        }
+        if (ng == 0xFFFFFFFFu) flags |= 2u;
+    }
+    if (ng == 0xFFFFFFFFu) ng = gcode;  // error flagged: keep the old goal
+    board[(ng >> 5) * 32].y |= 1u << (ng & 31u);
+    return make_uint2(ng, flags);
+}
+
+// ENV:267-282 for one env (rare path): symmetric rejection with the rule of draw_layout<G> -- every slot
+// draws uniformly, a slot equal to a lower-numbered slot (starts before goals) redraws in the next round.
+// The drawn cell ids are parked in the dead board memory: start of agent a in .x, goal in .y of row a.
+// Returns the number of rounds (= Philox counter values) consumed.
+__device__ __noinline__ uint32_t env_draw_layout(uint2 *board, const uint32_t *freebits, int fw, int F, int N,
+                                                 unsigned long long seed, long long env_global, uint32_t rng_counter) {
+    const Philox ph(seed, env_global);
+    const uint32_t allN = (N >= 32) ? 0xFFFFFFFFu : ((1u << N) - 1u);
+    uint32_t rs = allN, rg = allN, rounds = 0;
+    while (rs | rg) {
+        for (int a = 0; a < N; ++a) {
+            if (!(((rs | rg) >> a) & 1u)) continue;
+            const uint4 x = ph(rng_counter + rounds, (uint32_t)a, 0x52455345u /* "RESE" */, 0);
+            uint2 v = board[a * 32];
+            if ((rs >> a) & 1u) v.x = (uint32_t)select_kth(freebits, fw, (int)__umulhi(x.x, (uint32_t)F));
+            if ((rg >> a) & 1u) v.y = (uint32_t)select_kth(freebits, fw, (int)__umulhi(x.y, (uint32_t)F));
+            board[a * 32] = v;
+        }
+        rs = 0; rg = 0;
+        for (int g = 0; g < N; ++g) {
+            const uint2 me = board[g * 32];
+            for (int a = 0; a < N; ++a) {
+                const uint2 o = board[a * 32];
+                if (a < g && o.x == me.x) rs |= 1u << g;
+                if (o.x == me.y) rg |= 1u << g;
+                if (a < g && o.y == me.y) rg |= 1u << g;
+            }
+        }
+        rounds++;
+    }
+    return rounds;
+}
+
+// nibble j of `sel` (values 0..4) -> byte j: one PRMT against the byte table {0,1,2,3,4}
+__device__ __forceinline__ uint32_t nibbles_to_bytes(uint32_t sel) {
+    uint32_t w;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(w) : "r"(0x03020100u), "r"(0x00000004u), "r"(sel));
+    return w;
+}
+// bits 0..3 of m -> bytes 0/1
+__device__ __forceinline__ uint32_t spread4(uint32_t m) { return ((m & 15u) * 0x00204081u) & 0x01010101u; }
+// bit `b` of each of the 4 bytes of w -> nibble
+__device__ __forceinline__ uint32_t gather4(uint32_t w, int b) { return ((((w >> b) & 0x01010101u) * 0x01020408u) >> 24) & 15u; }
+
+// agent record in shared memory, rec[agent * 32] per lane:
+//   bits 0..10 cell code | 11..13 action | 14 target blocked (obstacle / out of bounds) | 16..31 int16 distance delta
+constexpr uint32_t REC_CODE = 0x7FFu;
+
 template <int SR, bool VEC>
-__global__ void __launch_bounds__(512, 1) mapf_step_env_kernel(const KParams p, const EnvLayout E) {
+__global__ void __launch_bounds__(448, 1) mapf_step_env_kernel(const KParams p, const EnvLayout E) {
     constexpr int V = 2 * SR + 1, V2 = V * V;
     constexpr uint32_t VM = (1u << V) - 1u;
-    constexpr int OBS_W = V2;                 // obs words per quad and env (4 * V2 bytes)
+    constexpr uint32_t M4 = VM << 2;          // a window row, pre-scaled by 4 (byte offset into t1)
+    constexpr int OBS_W = V2;                 // observation words per quad and env (4 * V2 bytes)
+    constexpr int STRIDE = env_stage_stride(V2);
+    constexpr int STAGE_BYTES = 32 * STRIDE * 4;
+    constexpr int CTR = SR * V + SR;
+    constexpr int PADR = ENV_ROW_PAD;
     using WB = typename WinBits<V>::type;
     extern __shared__ __align__(16) unsigned char esm[];
     const unsigned full = 0xFFFFFFFFu;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, warps = blockDim.x >> 5;
     const int N = p.N, R = p.R, C = p.C, NQ = E.nq;
 
-    // ------------------------------------------------------------------ CTA-wide tables
-    WB *lut = reinterpret_cast<WB *>(esm + E.lut_off);
-    uint32_t *freerow = reinterpret_cast<uint32_t *>(esm + E.freerow_off);
-    uint32_t *freebits = reinterpret_cast<uint32_t *>(esm + E.freebits_off);
-    float *gdt = reinterpret_cast<float *>(esm + E.gdt_off);
-    uint32_t *t1 = reinterpret_cast<uint32_t *>(esm + E.t1_off);
-    uint8_t *kth = esm + E.kth_off;
-    for (int cell = tid; cell < R * 32; cell += blockDim.x) {
-        const int r = cell >> 5, c = cell & 31;
-        WB w = 0;
-        if (c < C) {
-            const int sb = c - SR + PAD, word = sb >> 5, sh = sb & 31;
-#pragma unroll
-            for (int wr = 0; wr < V; ++wr) {
-                const uint32_t *rw = p.map_rows + (r - SR + wr + PAD) * p.wpr + word;
-                w |= (WB)(__funnelshift_r(rw[0], rw[1], sh) & VM) << (wr * V);
-            }
-        }
-        lut[cell] = w;
-    }
-    for (int r = tid; r < R; r += blockDim.x) {
-        const uint32_t *rw = p.map_rows + (r + PAD) * p.wpr;
-        const uint32_t bits = __funnelshift_r(rw[0], rw[1], PAD);  // bit c = obstacle at column c (c < 32)
-        freerow[r] = ~bits & (C >= 32 ? 0xFFFFFFFFu : ((1u << C) - 1u));
-    }
-    for (int i = tid; i < p.fw; i += blockDim.x) freebits[i] = p.free_bits[i];
-    fill_goal_delta_table(gdt, R, C, p.normalize, p.den0, p.den1, tid, blockDim.x);
-    for (int x = tid; x < (1 << V); x += blockDim.x) {
-        uint32_t s = 0;
-#pragma unroll
-        for (int j = 0; j < V; ++j) s |= ((x >> j) & 1u) << (4 * j);
-        t1[x] = s;
-    }
-    for (int x = tid; x < 256; x += blockDim.x) {
-        const int m = x >> 3, k = x & 7;
-        kth[x] = (uint8_t)((k < __popc(m)) ? __fns((unsigned)m, 0, k + 1) : 0);
+    // ------------------------------------------------------------------ CTA-wide tables (built on the host)
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(p.env_tables);
+        uint4 *dst = reinterpret_cast<uint4 *>(esm);
+        for (int i = tid; i < (E.tables_bytes >> 4); i += blockDim.x) dst[i] = src[i];
     }
     __syncthreads();
+    const char *t1b = reinterpret_cast<const char *>(esm + ENV_T1_OFF);
+    const uint8_t *kth = esm + ENV_KTH_OFF;
+    const WB *lut = reinterpret_cast<const WB *>(esm + ENV_LUT_OFF);
+    const uint32_t *freerow = reinterpret_cast<const uint32_t *>(esm + ENV_FREEROW_OFF);
+    const uint32_t *freebits = reinterpret_cast<const uint32_t *>(esm + ENV_FREEBITS_OFF);
+    const float *gdt = reinterpret_cast<const float *>(esm + ENV_GDT_OFF);
 
-    unsigned char *wsm = esm + E.warp_off + warp * E.warp_bytes;
-    uint2 *board = reinterpret_cast<uint2 *>(wsm + E.board_off) + lane;       // row r at board[r * 32]: .x occupancy, .y goals
-    uint2 *scr_pos = reinterpret_cast<uint2 *>(wsm + E.scratch_off) + lane;   // quad q at [q * 32]: 4 x u16 cell codes
-    uint2 *scr_delta = scr_pos + NQ * 32;                                     // 4 x i16 distance deltas
-    uint32_t *scr_act = reinterpret_cast<uint32_t *>(scr_delta + NQ * 32 - lane) + lane;  // 4 x u8 action / wait-for pointer
-    uint32_t *stage_w = reinterpret_cast<uint32_t *>(wsm + E.stage_off);      // [lane][stage_stride] words
-    uint32_t *my_stage = stage_w + lane * E.stage_stride;
+    unsigned char *wsm = esm + E.tables_bytes + warp * E.warp_bytes;
+    uint32_t *stage_w = reinterpret_cast<uint32_t *>(wsm);                        // [lane][STRIDE] words
+    uint32_t *my_stage = stage_w + lane * STRIDE;
+    uint2 *board = reinterpret_cast<uint2 *>(wsm + STAGE_BYTES) + lane;           // row r at board[r * 32]: .x occupancy, .y goals
+    uint32_t *rec = reinterpret_cast<uint32_t *>(wsm + STAGE_BYTES + E.board_rows * 256) + lane;  // agent a at rec[a * 32]
     const int ntiles = (p.B + 31) >> 5;
     uint32_t errs = 0;
     const uint32_t mdw = p.dw >= 32 ? full : ((1u << p.dw) - 1u);
@@ -226,6 +340,7 @@ __global__ void __launch_bounds__(512, 1) mapf_step_env_kernel(const KParams p, 
     const bool ok = env < p.B;
     const size_t ab = (size_t)(ok ? env : 0) * N;
     const long long env_global = p.env_id_base + env;
+    const size_t env0 = (size_t)tile * 32;
 
     // ---------------------------------------------------------------- env words
     int4 w0 = make_int4(0, 0, 0, 0), w1 = w0, w2 = w0, w3 = w0;
@@ -247,200 +362,398 @@ __global__ void __launch_bounds__(512, 1) mapf_step_env_kernel(const KParams p, 
     const int slot_next = (lock_head + 1 == p.lw) ? 0 : lock_head + 1;
     const bool use_ring = p.lock_enabled && count_after >= p.lw && p.lw > 1;
 
-    // ---------------------------------------------------------------- pre-pass: occupancy board from the old positions
+    // ---------------------------------------------------------------- pre-pass: owner boards of the state before the step
     for (int r = 0; r < E.board_rows; ++r) board[r * 32] = make_uint2(0u, 0u);
     for (int q = 0; q < NQ; ++q) {
         const int i0 = 4 * q;
         const uint4 pq = ldq32<VEC>(p.positions, ab + i0, i0, N, ok, 0u);
-        uint2 codes = make_uint2(0u, 0u);
+        const uint4 gq = ldq32<VEC>(p.goals, ab + i0, i0, N, ok, 0u);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             if (i0 + k < N) {
-                const uint32_t code = code_of(qget(pq, k));
-                hset(codes, k, code);
-                if (ok) board[(code >> 5) * 32].x |= 1u << (code & 31u);
+                const uint32_t code = code_of(qget(pq, k)), gcode = code_of(qget(gq, k));
+                rec[(i0 + k) * 32] = code;
+                if (ok) {
+                    board[(code >> 5) * 32].x |= 1u << (code & 31u);
+                    board[(gcode >> 5) * 32].y |= 1u << (gcode & 31u);
+                }
             }
         }
-        scr_pos[q * 32] = codes;
     }
 
-    // ---------------------------------------------------------------- pass 1: moves, goals, lock history (agent order, ENV:502-563)
     uint32_t moved_m = 0, failed_m = 0, gstep_m = 0, ongoal_m = 0;
     uint32_t reached_m = 0, completed_m = 0, bprev_m = 0;
     uint32_t Gd = 0, Md = 0, Fd = 0, Gl = 0, Ml = 0;
-    bool reassigned = false;
-    const Philox ph_env(p.seed, env_global);
-    for (int q = 0; q < NQ; ++q) {
-        const int i0 = 4 * q;
-        const uint2 codes = scr_pos[q * 32];
-        uint32_t act4 = p.actions ? ldq8<VEC>(reinterpret_cast<const uint8_t *>(p.actions), ab + i0, i0, N, ok) : 0u;
-        const uint32_t fl4 = ldq8<VEC>(p.agent_flags, ab + i0, i0, N, ok);
-        uint4 gq = ldq32<VEC>(p.goals, ab + i0, i0, N, ok, 0u);
-        uint4 gpq = make_uint4(0, 0, 0, 0), mvq = gpq, fmq = gpq;
-        uint2 ringq = make_uint2(0u, 0u);
-        if (p.lock_enabled) {
-            gpq = ldq32<VEC>(p.lock_gp, ab + i0, i0, N, ok, 0u);
-            mvq = ldq32<VEC>(p.lock_mv, ab + i0, i0, N, ok, 0u);
-            fmq = ldq32<VEC>(p.lock_fm, ab + i0, i0, N, ok, 0u);
-            if (use_ring) ringq = ldq16<VEC>(p.lock_dist, ((size_t)(ok ? env : 0) * p.lw + slot_next) * N + i0, i0, N, ok);
+    uint32_t wf_m = 0, blocking_m = 0;
+    bool reassigned = false, terminated = false, truncated = false, done = false, do_reset = false;
+    bool dl_step = false, ll_step = false, dl_event = false, ll_event = false;
+    int arrivals = 0;
+
+    // Round 0 walks the agents in index order: move, goal handling, lock history AND the agent's observation
+    // right after its own move (ENV:528-536: the boards are exactly snapshot i then).  Round 1
+    // re-emits the observations of envs that reassigned a goal from the final state (ENV:565-575); round 2
+    // comes after the env-level epilogue and emits the first observation of envs that were reset in this launch.
+    for (int round = 0; round < 3; ++round) {
+        bool active = ok;
+        if (round == 1) {
+            if (!__any_sync(full, reassigned)) continue;
+            active = reassigned;
         }
-        uint2 newcodes = codes, deltas = make_uint2(0u, 0u), dists = make_uint2(0u, 0u);
-        uint4 posq = make_uint4(0, 0, 0, 0);
-        bool goal_changed = false;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (i0 + k >= N) break;
-            const uint32_t bit = 1u << (i0 + k);
-            const uint32_t code = hget(codes, k);
-            int a = (int)(int8_t)(act4 >> (8 * k));
-            if (a < 0 || a > 4) { errs |= MAPF_DEV_ERR_INVALID_ACTION; a = 0; }
-            act4 = (act4 & ~(0xFFu << (8 * k))) | ((uint32_t)a << (8 * k));
-            // ENV:512-526: target cell, obstacle / bounds from the cell's obstacle window, occupancy from the board
-            const int d = (int)(int8_t)__byte_perm(0x2001E000u, 0x000000FFu, (uint32_t)a);   // {0,-32,+1,+32,-1}
-            const uint32_t nbi = __byte_perm((uint32_t)(SR * V + SR) | ((uint32_t)(SR * V + SR - V) << 8) |
-                                             ((uint32_t)(SR * V + SR + 1) << 16) | ((uint32_t)(SR * V + SR + V) << 24),
-                                             (uint32_t)(SR * V + SR - 1), (uint32_t)a) & 0xFFu;
-            const uint32_t obst_lo = (uint32_t)lut[code];
-            const uint32_t tcode = code + (uint32_t)d;
-            bool wants = ok && a != 0 && !((obst_lo >> nbi) & 1u);
-            bool moves = false;
-            if (wants) {
-                uint2 *trow = &board[(tcode >> 5) * 32];
-                const uint32_t tb = 1u << (tcode & 31u);
-                if (!(trow->x & tb)) {
-                    moves = true;
-                    board[(code >> 5) * 32].x &= ~(1u << (code & 31u));
-                    trow->x |= tb;
+        if (round == 2) {
+            // ------------------------------------------------------------ epilogue: owner masks, locks, blocking, wait-for graph
+            // The boards are dead: their memory now holds rowm[r] (.x of row r + PADR) / colm[c] (.y of row c + PADR):
+            // bit a = agent a's final row / column; PADR zero rows on both sides.
+            for (int r = 0; r < E.board_rows; ++r) board[r * 32] = make_uint2(0u, 0u);
+            if (ok) {
+                for (int i = 0; i < N; ++i) {
+                    const uint32_t code = rec[i * 32] & REC_CODE;
+                    board[((code >> 5) + PADR) * 32].x |= 1u << i;
+                    board[((code & 31u) + PADR) * 32].y |= 1u << i;
                 }
             }
-            const uint32_t ncode = moves ? tcode : code;
-            hset(newcodes, k, ncode);
-            qset(posq, k, packed_of(ncode));
-            if (moves) moved_m |= bit;
-            const bool failed = ok && a != 0 && !moves;  // ENV:583
-            if (failed) failed_m |= bit;
-            // flags of the previous step
-            const uint32_t fl = (fl4 >> (8 * k)) & 0xFFu;
-            if (fl & MAPF_AF_REACHED) reached_m |= bit;
-            if (fl & MAPF_AF_COMPLETED_ONCE) completed_m |= bit;
-            if (fl & MAPF_AF_BLOCKING_PREV) bprev_m |= bit;
-            // ENV:538-563
-            uint32_t gcode = code_of(qget(gq, k));
-            const bool on_goal = ok && ncode == gcode;
-            bool gstep = false;
-            if (ok) board[(gcode >> 5) * 32].y |= 1u << (gcode & 31u);
-            if (!p.lifelong) {
-                if (on_goal && !(fl & MAPF_AF_REACHED)) { reached_m |= bit; completed_m |= bit; gstep = true; }
-            } else if (on_goal) {
-                gstep = true;
-                completed_m |= bit; reached_m &= ~bit;
-                reassigned = true;
-                // ENV:284-304 at agent i's turn: the board IS occupancy snapshot i; goals of later agents
-                // are not on the goal board yet -> add them (idempotent), drop my old goal, pick the k-th candidate
-                const int i = i0 + k;
-                for (int j = i + 1; j < N; ++j) {
-                    const uint32_t gj = code_of(p.goals[ab + j]);
-                    board[(gj >> 5) * 32].y |= 1u << (gj & 31u);
-                }
-                board[(gcode >> 5) * 32].y &= ~(1u << (gcode & 31u));
-                uint32_t ng = 0xFFFFFFFFu;
-                if (p.goal_override) {
-                    const uint32_t ov = p.goal_override[ab + i];
-                    if (prow(ov) >= 0) ng = code_of(ov);
-                }
-                if (ng == 0xFFFFFFFFu) {
-                    int n = 0;
-                    for (int r = 0; r < R; ++r) { const uint2 b = board[r * 32]; n += __popc(freerow[r] & ~b.x & ~b.y); }
-                    int kk = -1;
-                    if (p.goal_rank) kk = p.goal_rank[ab + i];
-                    if (kk < 0 && n > 0) {
-                        const uint4 x = ph_env(rng_counter, (uint32_t)i, 0x474F414Cu /* "GOAL" */, 0);
-                        kk = (int)__umulhi(x.x, (uint32_t)n);
-                        rng_counter++;
-                    }
-                    if (n > 0 && kk < n) {
-                        for (int r = 0; r < R; ++r) {
-                            const uint2 b = board[r * 32];
-                            const uint32_t cand = freerow[r] & ~b.x & ~b.y;
-                            const int c = __popc(cand);
-                            if (kk < c) { ng = (uint32_t)(r * 32) + __fns(cand, 0, kk + 1); break; }
-                            kk -= c;
+            uint32_t coloc_any = 0, wf_alive = 0;
+            bool dl_any = false, ll_any = false;
+            const uint32_t intent_m = allN & ~reached_m;  // ENV:619-621: only agents that have not (sticky-)reached press
+            for (int i = 0; i < N; ++i) {
+                if (!ok) break;
+                const uint32_t bit = 1u << i;
+                const uint32_t rv = rec[i * 32];
+                const uint32_t code = rv & REC_CODE;
+                const int r = (int)(code >> 5), c = (int)(code & 31u);
+                const uint2 *prow_ = &board[(r + PADR) * 32], *pcol_ = &board[(c + PADR) * 32];
+                const uint32_t here = prow_->x & pcol_->y;   // agents on my cell (me included)
+                if (here & ~bit) coloc_any |= bit;
+                // ENV:389-438 neighbours within Manhattan distance `nearby`, via the row / column masks
+                if (p.lock_enabled && !(ongoal_m & bit)) {
+                    uint32_t nb = 0;
+                    if (p.nearby == 2) {
+                        const uint32_t c0 = pcol_->y;
+                        const uint32_t c1 = c0 | pcol_[-32].y | pcol_[32].y;
+                        const uint32_t c2 = c1 | pcol_[-64].y | pcol_[64].y;
+                        nb = (prow_->x & c2) | ((prow_[-32].x | prow_[32].x) & c1) | ((prow_[-64].x | prow_[64].x) & c0);
+                    } else {
+                        uint32_t u = 0;
+                        for (int w = 0; w <= p.nearby; ++w) {
+                            const int dd = p.nearby - w;
+                            if (c - w >= 0) u |= pcol_[-w * 32].y;
+                            if (c + w < C) u |= pcol_[w * 32].y;
+                            uint32_t rm = 0;
+                            if (r - dd >= 0) rm |= prow_[-dd * 32].x;
+                            if (r + dd < R) rm |= prow_[dd * 32].x;
+                            nb |= rm & u;
                         }
                     }
-                    if (ng == 0xFFFFFFFFu) errs |= MAPF_DEV_ERR_NO_GOAL_CELL;
+                    nb &= ~here;
+                    if (__popc(nb) >= p.min_nb) {
+                        const uint32_t P = nb | bit;
+                        if (!(P & Gd) && !(P & Md) && (P & Fd)) dl_any = true;
+                        if (!(P & Gl) && (P & Ml)) {
+                            uint32_t rest = nb;
+                            int red = (int)rv >> 16;
+                            while (rest) {
+                                const int a = __ffs(rest) - 1;
+                                rest &= rest - 1;
+                                red += (int)rec[a * 32] >> 16;
+                            }
+                            if (red <= p.eps_floor) ll_any = true;
+                        }
+                    }
                 }
-                if (ng == 0xFFFFFFFFu) ng = gcode;  // error flagged: keep the old goal
-                gcode = ng;
-                board[(gcode >> 5) * 32].y |= 1u << (gcode & 31u);
-                qset(gq, k, packed_of(gcode));
-                goal_changed = true;
-            }
-            if (gstep) gstep_m |= bit;
-            const bool cur_on_goal = ok && ncode == gcode;  // ENV:555: false after a reassignment
-            if (cur_on_goal) ongoal_m |= bit;
-            // ENV:581-594 lock history
-            if (p.lock_enabled) {
-                const bool prev_on_goal = p.lifelong ? false : (code == gcode);
-                const bool gp = p.lifelong ? gstep : (!prev_on_goal && cur_on_goal);
-                const uint32_t g2 = (qget(gpq, k) << 1) | (gp ? 1u : 0u);
-                const uint32_t m2 = (qget(mvq, k) << 1) | (moves ? 1u : 0u);
-                const uint32_t f2 = (qget(fmq, k) << 1) | (failed ? 1u : 0u);
-                qset(gpq, k, g2); qset(mvq, k, m2); qset(fmq, k, f2);
-                if (ok) {
-                    if (g2 & mdw) Gd |= bit;
-                    if (m2 & mdw) Md |= bit;
-                    if (f2 & mdw) Fd |= bit;
-                    if (g2 & mlw) Gl |= bit;
-                    if (m2 & mlw) Ml |= bit;
+                // intended cell (kept even when invalid, ENV:514-515) -> who stands there.  A blocked target is an
+                // obstacle or out of bounds: nobody can stand there.
+                uint32_t owner = here & ~bit;
+                if (!(moved_m & bit)) {
+                    owner = 0;
+                    if (!(rv & 0x4000u)) {
+                        const uint32_t tcode = code + (uint32_t)(int)(int8_t)__byte_perm(0x2001E000u, 0x000000FFu, (rv >> 11) & 7u);
+                        owner = board[((tcode >> 5) + PADR) * 32].x & board[((tcode & 31u) + PADR) * 32].y & ~bit;
+                    }
                 }
-                const int dist = abs((int)(gcode >> 5) - (int)(ncode >> 5)) + abs((int)(gcode & 31u) - (int)(ncode & 31u));
-                hset(dists, k, (uint32_t)dist);
-                if (use_ring && ok) hset(deltas, k, (uint32_t)((int)(int16_t)hget(ringq, k) - dist));
+                if (intent_m & bit) blocking_m |= owner;   // ENV:609-623 (filtered below)
+                if ((failed_m & bit) && owner) {   // wait-for edge i -> owner (kept in the action bits of the record)
+                    rec[i * 32] = (rv & ~0xF800u) | ((uint32_t)(31 - __clz(owner)) << 11);
+                    wf_alive |= bit;
+                }
             }
-        }
-        scr_pos[q * 32] = newcodes;
-        scr_delta[q * 32] = deltas;
-        scr_act[q * 32] = act4;
-        stq32<VEC>(p.positions, ab + i0, i0, N, ok, posq);
-        if (goal_changed) stq32<VEC>(p.goals, ab + i0, i0, N, ok, gq);
-        if (p.lock_enabled) {
-            stq32<VEC>(p.lock_gp, ab + i0, i0, N, ok, gpq);
-            stq32<VEC>(p.lock_mv, ab + i0, i0, N, ok, mvq);
-            stq32<VEC>(p.lock_fm, ab + i0, i0, N, ok, fmq);
-            stq16<VEC>(p.lock_dist, ((size_t)(ok ? env : 0) * p.lw + slot_new) * N + i0, i0, N, ok, dists);
-        }
-    }
-    if (p.lock_enabled) lock_head = slot_next;
-    const int arrivals = __popc(gstep_m);
-    goals_total += arrivals;  // lifelong: every arrival; else first arrivals (ENV:545,562)
+            blocking_m &= reached_m & ~moved_m;
+            // wait-for cycles: strip agents whose target is gone or that nobody waits for, until stable
+            if (__any_sync(full, wf_alive != 0)) {
+                uint32_t alive = wf_alive;
+                for (;;) {
+                    uint32_t keep = 0, targets = 0, rest = alive;
+                    while (rest) {
+                        const int i = __ffs(rest) - 1;
+                        rest &= rest - 1;
+                        const uint32_t t = (rec[i * 32] >> 11) & 31u;
+                        if ((alive >> t) & 1u) { keep |= 1u << i; targets |= 1u << t; }
+                    }
+                    keep &= targets;
+                    const bool changed = keep != alive;
+                    alive = keep;
+                    if (!__any_sync(full, changed)) break;
+                }
+                wf_m = alive;
+            }
+            const bool wf_any = wf_m != 0;
+            wfg_steps += wf_any;
+            const int blocking_step = __popc(blocking_m);
+            blocking_total += blocking_step;
 
-    // ---------------------------------------------------------------- pass 2: observations (descending walk with undo)
-    // emit(active, undo): active threads write local_obs / action_mask / goal_delta / blocking_prev / next
-    // actions of their env from the boards; with undo, agent i's move is taken back after its window is
-    // built, so the next (lower) agent sees snapshot i-1.  A thread whose env reassigned
-    // a goal (ENV:565-575) or was just reset shows the final state to everybody: no undo.
-    auto emit = [&](const bool active, const bool undo, const uint32_t mv_m, const uint32_t bp_m) {
+            // ------------------------------------------------------------ lock detection result, ENV:595-606
+            if (p.lock_enabled) {
+                dl_step = count_after >= p.dw && dl_any;
+                ll_step = !dl_step && count_after >= p.lw && ll_any;
+                dl_event = dl_step && !(lock_prev & 1);
+                ll_event = ll_step && !(lock_prev & 2);
+                lock_prev = (dl_step ? 1 : 0) | (ll_step ? 2 : 0);
+                dl_steps += dl_step; ll_steps += ll_step; dl_events += dl_event; ll_events += ll_event;
+                lock_count = count_after;
+            }
+
+            // ------------------------------------------------------------ rewards & termination, ENV:658-690
+            const uint32_t scratch_on = p.lifelong ? 0u : ongoal_m;   // reached_goal scratch (ENV:555)
+            uint32_t bonus_m = 0, penalty_m = 0;
+            if (!p.lifelong && __popc(scratch_on) == N) { terminated = true; bonus_m = allN; }
+            else if (step_count >= p.steps_per_episode) {
+                terminated = true; truncated = true;  // F6
+                if (!p.lifelong) penalty_m = allN & ~scratch_on;
+            }
+            done = ok && (terminated || truncated);
+            int rsum = __popc(gstep_m) + 2 * __popc(bonus_m) - 2 * __popc(penalty_m);
+            for (int q = 0; q < NQ; ++q) {
+                const int i0 = 4 * q;
+                const uint32_t gs = spread4(gstep_m >> i0), bl = spread4(blocking_m >> i0);
+                const uint32_t asf4 = spread4(moved_m >> i0) * MAPF_ASF_MOVED + spread4(failed_m >> i0) * MAPF_ASF_FAILED_MOVE +
+                                      gs * MAPF_ASF_GOAL_REACHED + bl * MAPF_ASF_BLOCKING +
+                                      spread4(wf_m >> i0) * MAPF_ASF_WFG_CYCLE + spread4(ongoal_m >> i0) * MAPF_ASF_ON_GOAL;
+                const uint32_t af4 = spread4(reached_m >> i0) * MAPF_AF_REACHED + spread4(completed_m >> i0) * MAPF_AF_COMPLETED_ONCE +
+                                     bl * MAPF_AF_BLOCKING_PREV;
+                // reward * 2 per agent (exact small integers): +1 arrival, +2 all-on-goal bonus, -2 truncation penalty
+                const uint32_t pos4 = gs + 2u * spread4(bonus_m >> i0), neg4 = 2u * spread4(penalty_m >> i0);
+                float rw[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    int rx2 = (int)((pos4 >> (8 * k)) & 0xFFu) - (int)((neg4 >> (8 * k)) & 0xFFu);
+                    if ((coloc_any >> (i0 + k)) & 1u) {   // ENV:658-666, -1 per co-located pair member (injected states only)
+                        const uint32_t code = rec[(i0 + k) * 32] & REC_CODE;
+                        const int others = __popc(board[((code >> 5) + PADR) * 32].x & board[((code & 31u) + PADR) * 32].y) - 1;
+                        rx2 -= 2 * others;
+                        rsum -= 2 * others;
+                    }
+                    rw[k] = 0.5f * (float)rx2;
+                }
+                if (ok) {
+                    if (p.o_reward) {
+                        if (VEC) *reinterpret_cast<float4 *>(p.o_reward + ab + i0) = make_float4(rw[0], rw[1], rw[2], rw[3]);
+                        else {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) if (i0 + k < N) p.o_reward[ab + i0 + k] = rw[k];
+                        }
+                    }
+                    if (p.o_agent_step_flags) stq8<VEC>(p.o_agent_step_flags, ab + i0, i0, N, true, asf4);
+                    stq8<VEC>(p.agent_flags, ab + i0, i0, N, true, af4);
+                }
+            }
+            ep_return_x2 += rsum;
+            const int n_comp = __popc(completed_m), n_reach = __popc(reached_m);
+            if (ok) {
+                if (p.o_info) {  // integer sources of info["__all__"], ENV:639-656
+                    int4 *io = p.o_info + (size_t)env * 4;
+                    io[0] = make_int4(arrivals, p.lifelong ? goals_total : n_reach, blocking_step, blocking_total);
+                    io[1] = make_int4(dl_step, ll_step, dl_event, ll_event);
+                    io[2] = make_int4(dl_events, ll_events, dl_steps, ll_steps);
+                    io[3] = make_int4(n_comp, step_count, n_reach, wfg_steps);
+                }
+                if (p.o_terminated) p.o_terminated[env] = terminated;
+                if (p.o_truncated) p.o_truncated[env] = truncated;
+                if (p.o_step_flags)
+                    p.o_step_flags[env] = (uint8_t)((terminated ? MAPF_SF_TERMINATED : 0) | (truncated ? MAPF_SF_TRUNCATED : 0) |
+                                                    (dl_step ? MAPF_SF_DEADLOCK_STEP : 0) | (ll_step ? MAPF_SF_LIVELOCK_STEP : 0) |
+                                                    (dl_event ? MAPF_SF_DEADLOCK_EVENT : 0) | (ll_event ? MAPF_SF_LIVELOCK_EVENT : 0) |
+                                                    (reassigned ? MAPF_SF_GOAL_REASSIGNED : 0) | (wf_any ? MAPF_SF_WFG_CYCLE : 0));
+            }
+
+            // ------------------------------------------------------------ episode end: metrics, auto-reset
+            if (done) {   // episode-end metric sums, src/trainers/callbacks.py:152,173,335-345
+                double *m = p.env_metrics + (size_t)env * MAPF_METRIC_COUNT;
+                const double gt = p.lifelong ? (double)goals_total : (double)n_reach;  // ENV:630-633
+                m[MAPF_M_EPISODES] += 1.0;
+                m[MAPF_M_RETURN_SUM] += 0.5 * (double)ep_return_x2;
+                m[MAPF_M_LENGTH_SUM] += (double)step_count;
+                m[MAPF_M_SUCCESS_SUM] += (terminated && !truncated) ? 1.0 : 0.0;
+                m[MAPF_M_GOALS_REACHED_SUM] += gt;
+                m[MAPF_M_BLOCKING_COUNT_SUM] += (double)blocking_total;
+                m[MAPF_M_DEADLOCK_COUNT_SUM] += (double)dl_events;
+                m[MAPF_M_LIVELOCK_COUNT_SUM] += (double)ll_events;
+                m[MAPF_M_DEADLOCK_STEPS_SUM] += (double)dl_steps;
+                m[MAPF_M_LIVELOCK_STEPS_SUM] += (double)ll_steps;
+                m[MAPF_M_THROUGHPUT_SUM] += gt / (double)(step_count > 1 ? step_count : 1);  // ENV:655
+                m[MAPF_M_COMPLETION_RATIO_SUM] += (double)n_comp / (double)N;                 // ENV:638
+                m[MAPF_M_WFG_CYCLE_STEPS_SUM] += (double)wfg_steps;
+                episodes += 1;
+            }
+            do_reset = done && p.auto_reset;
+            if (!__any_sync(full, do_reset)) break;
+            if (do_reset) {   // ENV:440-472 inside the launch (benchmark loop semantics)
+                bool sample = !p.deterministic;
+                const int F = p.num_free[0];
+                if (sample && F < 2 * N) { errs |= MAPF_DEV_ERR_TOO_FEW_CELLS; sample = false; }
+                if (sample) rng_counter += env_draw_layout(board, freebits, p.fw, F, N, p.seed, env_global, rng_counter);
+                for (int q = 0; q < NQ; ++q) {
+                    const int i0 = 4 * q;
+                    uint4 stq = make_uint4(0, 0, 0, 0), ggq = stq;
+                    const uint4 curp = ldq32<VEC>(p.positions, ab + i0, i0, N, true, 0u);
+                    const uint4 curg = ldq32<VEC>(p.goals, ab + i0, i0, N, true, 0u);
+                    uint4 detst = make_uint4(0, 0, 0, 0);
+                    if (p.deterministic) detst = ldq32<VEC>(p.starts, ab + i0, i0, N, true, 0u);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (i0 + k >= N) continue;
+                        uint32_t st, gg;
+                        if (p.deterministic) { st = qget(detst, k); gg = qget(curg, k); }  // F7
+                        else if (sample) {
+                            const uint2 v = board[(i0 + k) * 32];
+                            st = pack_rc((int)v.x / C, (int)v.x % C);
+                            gg = pack_rc((int)v.y / C, (int)v.y % C);
+                        } else { st = qget(curp, k); gg = qget(curg, k); }
+                        qset(stq, k, st); qset(ggq, k, gg);
+                        rec[(i0 + k) * 32] = code_of(st);
+                    }
+                    stq32<VEC>(p.positions, ab + i0, i0, N, true, stq);
+                    if (sample) { stq32<VEC>(p.starts, ab + i0, i0, N, true, stq); stq32<VEC>(p.goals, ab + i0, i0, N, true, ggq); }
+                    stq8<VEC>(p.agent_flags, ab + i0, i0, N, true, 0u);
+                    if (p.lock_enabled) {
+                        const uint4 z = make_uint4(0, 0, 0, 0);
+                        stq32<VEC>(p.lock_gp, ab + i0, i0, N, true, z);
+                        stq32<VEC>(p.lock_mv, ab + i0, i0, N, true, z);
+                        stq32<VEC>(p.lock_fm, ab + i0, i0, N, true, z);
+                    }
+                }
+                step_count = 0; lock_count = 0; lock_head = 0; lock_prev = 0; goals_total = 0; blocking_total = 0;
+                dl_events = ll_events = dl_steps = ll_steps = 0; ep_return_x2 = 0; wfg_steps = 0;
+                bprev_m = 0;
+                // boards of the new layout: first observation of the next episode (final state, no staggering at reset)
+                for (int r = 0; r < E.board_rows; ++r) board[r * 32] = make_uint2(0u, 0u);
+                for (int i = 0; i < N; ++i) {
+                    const uint32_t pc = rec[i * 32] & REC_CODE;
+                    const uint32_t gc = code_of(p.goals[ab + i]);
+                    board[(pc >> 5) * 32].x |= 1u << (pc & 31u);
+                    board[(gc >> 5) * 32].y |= 1u << (gc & 31u);
+                }
+            }
+            active = do_reset;
+        }
+
+        // ---------------------------------------------------------------- the agent walk
+        const bool stepmode = round == 0;
         const unsigned act_w = __ballot_sync(full, active);
-        for (int q = NQ - 1; q >= 0; --q) {
+        for (int q = 0; q < NQ; ++q) {
             const int i0 = 4 * q;
-            const uint2 codes = scr_pos[q * 32];
-            const uint32_t act4 = scr_act[q * 32];
-            const uint4 gq = ldq32<VEC>(p.goals, ab + i0, i0, N, active, 0u);
+            uint32_t cd[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) cd[k] = (i0 + k < N) ? (rec[(i0 + k) * 32] & REC_CODE) : 0u;
+            uint4 gq = ldq32<VEC>(p.goals, ab + i0, i0, N, active, 0u);
+            uint32_t act4 = 0;
+            uint4 gpq = make_uint4(0, 0, 0, 0), mvq = gpq, fmq = gpq;
+            uint2 ringq = make_uint2(0u, 0u);
+            if (stepmode) {
+                if (p.actions) act4 = ldq8<VEC>(reinterpret_cast<const uint8_t *>(p.actions), ab + i0, i0, N, ok);
+                const uint32_t fl4 = ldq8<VEC>(p.agent_flags, ab + i0, i0, N, ok);
+                reached_m |= gather4(fl4, 0) << i0;      // MAPF_AF_REACHED
+                completed_m |= gather4(fl4, 1) << i0;    // MAPF_AF_COMPLETED_ONCE
+                bprev_m |= gather4(fl4, 2) << i0;        // MAPF_AF_BLOCKING_PREV
+                if (p.lock_enabled) {
+                    gpq = ldq32<VEC>(p.lock_gp, ab + i0, i0, N, ok, 0u);
+                    mvq = ldq32<VEC>(p.lock_mv, ab + i0, i0, N, ok, 0u);
+                    fmq = ldq32<VEC>(p.lock_fm, ab + i0, i0, N, ok, 0u);
+                    if (use_ring) ringq = ldq16<VEC>(p.lock_dist, ((size_t)(ok ? env : 0) * p.lw + slot_next) * N + i0, i0, N, ok);
+                }
+            }
             uint4 rnd = make_uint4(0, 0, 0, 0);
             if (p.sample_mode) rnd = sample_quad(p.seed, env_global, q, p.sample_counter);
-            uint32_t masks4 = 0, next4 = 0, bp4 = 0;
+            uint32_t ds[4] = {0, 0, 0, 0};
+            uint32_t masks4 = 0, next4 = 0;
+            bool goal_changed = false;
             float2 gd[4];
             int patch[4];
             uint32_t carry = 0;
 #pragma unroll
-            for (int k = 3; k >= 0; --k) {
+            for (int k = 0; k < 4; ++k) {
                 gd[k] = make_float2(0.f, 0.f);
                 patch[k] = -1;
                 if (i0 + k >= N) continue;
                 const uint32_t bit = 1u << (i0 + k);
-                const uint32_t code = hget(codes, k);
+                uint32_t code = cd[k];
+                uint32_t gcode = code_of(qget(gq, k));
+                if (stepmode) {
+                    const uint32_t ocode = code;
+                    int a = (int)(int8_t)(act4 >> (8 * k));
+                    if (a < 0 || a > 4) { errs |= MAPF_DEV_ERR_INVALID_ACTION; a = 0; }
+                    // ENV:512-526: target cell, obstacle / bounds from the cell's obstacle window, occupancy from the board
+                    const int d = (int)(int8_t)__byte_perm(0x2001E000u, 0x000000FFu, (uint32_t)a);   // {0,-32,+1,+32,-1}
+                    const uint32_t nbi = __byte_perm((uint32_t)CTR | ((uint32_t)(CTR - V) << 8) | ((uint32_t)(CTR + 1) << 16) |
+                                                     ((uint32_t)(CTR + V) << 24), (uint32_t)(CTR - 1), (uint32_t)a) & 0xFFu;
+                    const bool tblocked = ((uint32_t)lut[code] >> nbi) & 1u;
+                    const uint32_t tcode = code + (uint32_t)d;
+                    const bool wants = ok && a != 0 && !tblocked;
+                    bool moves = false;
+                    if (wants) {
+                        uint2 *trow = &board[(tcode >> 5) * 32];
+                        const uint32_t tb = 1u << (tcode & 31u);
+                        if (!(trow->x & tb)) {
+                            moves = true;
+                            board[(code >> 5) * 32].x &= ~(1u << (code & 31u));
+                            trow->x |= tb;
+                        }
+                    }
+                    const bool failed = ok && a != 0 && !moves;  // ENV:583
+                    if (moves) { moved_m |= bit; code = tcode; cd[k] = tcode; }
+                    if (failed) failed_m |= bit;
+                    // ENV:538-563
+                    const uint32_t gcode_before = gcode;
+                    const bool on_goal = ok && code == gcode;
+                    bool gstep = false;
+                    if (!p.lifelong) {
+                        if (on_goal && !(reached_m & bit)) { reached_m |= bit; completed_m |= bit; gstep = true; }
+                    } else if (on_goal) {
+                        gstep = true;
+                        completed_m |= bit; reached_m &= ~bit;
+                        reassigned = true;
+                        const uint2 ng = env_assign_new_goal(board, freerow, R, p.goal_override, p.goal_rank, ab + i0 + k,
+                                                             i0 + k, gcode, p.seed, env_global, rng_counter);
+                        gcode = ng.x;
+                        rng_counter += ng.y & 1u;
+                        if (ng.y & 2u) errs |= MAPF_DEV_ERR_NO_GOAL_CELL;
+                        qset(gq, k, packed_of(gcode));
+                        goal_changed = true;
+                    }
+                    if (gstep) gstep_m |= bit;
+                    const bool cur_on_goal = ok && code == gcode;  // ENV:555: false after a reassignment
+                    if (cur_on_goal) ongoal_m |= bit;
+                    // ENV:581-594 lock history
+                    uint32_t delta16 = 0;
+                    if (p.lock_enabled) {
+                        const bool prev_on_goal = p.lifelong ? false : (ocode == gcode_before);
+                        const bool gp = p.lifelong ? gstep : (!prev_on_goal && cur_on_goal);
+                        const uint32_t g2 = (qget(gpq, k) << 1) | (gp ? 1u : 0u);
+                        const uint32_t m2 = (qget(mvq, k) << 1) | (moves ? 1u : 0u);
+                        const uint32_t f2 = (qget(fmq, k) << 1) | (failed ? 1u : 0u);
+                        qset(gpq, k, g2); qset(mvq, k, m2); qset(fmq, k, f2);
+                        if (ok) {
+                            if (g2 & mdw) Gd |= bit;
+                            if (m2 & mdw) Md |= bit;
+                            if (f2 & mdw) Fd |= bit;
+                            if (g2 & mlw) Gl |= bit;
+                            if (m2 & mlw) Ml |= bit;
+                        }
+                        const int dist = abs((int)(gcode >> 5) - (int)(code >> 5)) + abs((int)(gcode & 31u) - (int)(code & 31u));
+                        ds[k] = (uint32_t)dist;
+                        if (use_ring && ok) delta16 = (uint32_t)((int)(int16_t)hget(ringq, k) - dist) << 16;
+                    }
+                    rec[(i0 + k) * 32] = code | ((uint32_t)a << 11) | (tblocked ? 0x4000u : 0u) | delta16;
+                }
+                // ---------------------------------------------------- observation of agent i on the boards as they are now
                 const int r = (int)(code >> 5), c = (int)(code & 31u);
-                const uint32_t gcode = code_of(qget(gq, k));
                 const WB obst = lut[code];
                 const int sa = c > SR ? c - SR : 0, sb2 = (c < SR ? SR - c : 0) + 2;   // window columns start at c - SR
                 const uint2 *brow = &board[(r - SR) * 32];
@@ -451,21 +764,18 @@ __global__ void __launch_bounds__(512, 1) mapf_step_env_kernel(const KParams p, 
 #pragma unroll
                 for (int wr = 0; wr < V; ++wr) {
                     const uint2 b = brow[wr * 32];  // rows outside the map read neighbouring shared memory: masked by the obstacle plane
-                    constexpr uint32_t M4 = VM << 2;
                     const uint32_t o4 = (wr * V >= 2 ? (uint32_t)(obst >> (wr * V - 2)) : (uint32_t)(obst << 2)) & M4;
-                    uint32_t occ4 = ((b.x >> sa) << sb2) & M4;
-                    if (wr == SR) occ4 &= ~(4u << SR);  // my own cell is not "another agent" (ENV:737)
-                    const uint32_t goal4 = ((b.y >> sa) << sb2) & M4;
+                    const uint32_t MC = (wr == SR) ? (M4 & ~(4u << SR)) : M4;   // my own cell is not "another agent" (ENV:737)
+                    const uint32_t occ4 = ((b.x >> sa) << sb2) & MC;
                     const uint32_t agent4 = occ4 & ~o4;
                     const uint32_t blk4 = occ4 | o4;
-                    const uint32_t g4 = goal4 & ~blk4;
+                    const uint32_t g4 = ((b.y >> sa) << sb2) & M4 & ~blk4;
                     if (wr == SR - 1) blk_up = blk4;
                     if (wr == SR) blk_mid = blk4;
                     if (wr == SR + 1) blk_dn = blk4;
-                    const char *tb = reinterpret_cast<const char *>(t1);
-                    const uint32_t t = *reinterpret_cast<const uint32_t *>(tb + o4) +
-                                       (*reinterpret_cast<const uint32_t *>(tb + agent4) << 1) +
-                                       (*reinterpret_cast<const uint32_t *>(tb + g4) << 2);   // ENV:730-745 codes 1 / 2 / 4
+                    const uint32_t t = *reinterpret_cast<const uint32_t *>(t1b + o4) +
+                                       (*reinterpret_cast<const uint32_t *>(t1b + agent4) << 1) +
+                                       (*reinterpret_cast<const uint32_t *>(t1b + g4) << 2);   // ENV:730-745 codes 1 / 2 / 4
                     const int bitpos = 4 * (V * wr + (k & 3));  // agent k's bytes start k bytes into its first stage word
                     const int wi = bitpos >> 5, sh = bitpos & 31;
                     acc[wi] |= t << sh;
@@ -480,29 +790,28 @@ __global__ void __launch_bounds__(512, 1) mapf_step_env_kernel(const KParams p, 
                     const int dr = (int)(gcode >> 5) - r + SR, dc = (int)(gcode & 31u) - c + SR;
                     if ((unsigned)dr < (unsigned)V && (unsigned)dc < (unsigned)V) {
                         const int ci = dr * V + dc;
-                        const bool occ_other = (ci != SR * V + SR) && ((board[(gcode >> 5) * 32].x >> (gcode & 31u)) & 1u);
+                        const bool occ_other = (ci != CTR) && ((board[(gcode >> 5) * 32].x >> (gcode & 31u)) & 1u);
                         if (!((obst >> ci) & 1) && !occ_other) patch[k] = V2 * k + ci;
                     }
                 }
-                // words of this agent: first word index (V2 * k) / 4, k leading bytes belong to agent k-1
+                // words of this agent: first word index (V2 * k) / 4; its k leading bytes belong to agent k-1
                 constexpr int NWMAX = (V2 + 3 + 3) / 4;
                 const int j0 = (V2 * k) >> 2;
                 const int nw = ((k & 3) + V2 + 3) >> 2;
 #pragma unroll
-                for (int m = NWMAX - 1; m >= 0; --m) {
+                for (int m = 0; m < NWMAX; ++m) {
                     if (m >= nw) continue;
-                    const uint32_t sel = (m & 1) ? (acc[m >> 1] >> 16) : acc[m >> 1];
-                    uint32_t w = __byte_perm(0x03020100u, 0x00000004u, sel);
-                    if (m == nw - 1 && (((k & 3) + V2) & 3) != 0) w |= carry;   // trailing partial word shared with agent k+1
-                    if (m == 0 && (k & 3) != 0) carry = w;                      // leading partial word: merged by agent k-1
+                    uint32_t w = nibbles_to_bytes((m & 1) ? (acc[m >> 1] >> 16) : acc[m >> 1]);
+                    if (m == 0 && (k & 3) != 0) w |= carry;                                  // leading partial word shared with agent k-1
+                    if (m == nw - 1 && (((k & 3) + V2) & 3) != 0) carry = w;                 // trailing partial word: stored by agent k+1
                     else if (active) my_stage[j0 + m] = w;
                 }
+                if (!VEC && i0 + k == N - 1 && (((k & 3) + V2) & 3) != 0 && active) my_stage[j0 + nw - 1] = carry;
                 // ENV:330-335
                 {
                     const int gi0 = (int)(gcode >> 5) - r + (R - 1), gi1 = (int)(gcode & 31u) - c + (C - 1) + 2 * R - 1;
                     gd[k] = make_float2(gdt[gi0], gdt[gi1]);
                 }
-                if (bp_m & bit) bp4 |= 1u << (8 * k);
                 if (p.sample_mode) {
                     const uint32_t x = qget(rnd, k);
                     uint32_t na;
@@ -510,12 +819,17 @@ __global__ void __launch_bounds__(512, 1) mapf_step_env_kernel(const KParams p, 
                     else na = __umulhi(x, 5u);
                     next4 |= na << (8 * k);
                 }
-                if (undo && (mv_m & bit)) {   // back to snapshot i-1
-                    const int a = (int)((act4 >> (8 * k)) & 0xFFu);
-                    const int d = (int)(int8_t)__byte_perm(0x2001E000u, 0x000000FFu, (uint32_t)a);
-                    const uint32_t ocode = code - (uint32_t)d;
-                    board[r * 32].x &= ~(1u << c);
-                    board[(ocode >> 5) * 32].x |= 1u << (ocode & 31u);
+            }
+            if (stepmode) {
+                stq32<VEC>(p.positions, ab + i0, i0, N, ok,
+                           make_uint4(packed_of(cd[0]), packed_of(cd[1]), packed_of(cd[2]), packed_of(cd[3])));
+                if (goal_changed) stq32<VEC>(p.goals, ab + i0, i0, N, ok, gq);
+                if (p.lock_enabled) {
+                    stq32<VEC>(p.lock_gp, ab + i0, i0, N, ok, gpq);
+                    stq32<VEC>(p.lock_mv, ab + i0, i0, N, ok, mvq);
+                    stq32<VEC>(p.lock_fm, ab + i0, i0, N, ok, fmq);
+                    stq16<VEC>(p.lock_dist, ((size_t)(ok ? env : 0) * p.lw + slot_new) * N + i0, i0, N, ok,
+                               make_uint2(ds[0] | (ds[1] << 16), ds[2] | (ds[3] << 16)));
                 }
             }
             if (active) {
@@ -527,7 +841,7 @@ __global__ void __launch_bounds__(512, 1) mapf_step_env_kernel(const KParams p, 
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const uint32_t m = (masks4 >> (8 * k)) & 0x1Fu;
-                    lo[k] = ((m & 15u) * 0x00204081u) & 0x01010101u;
+                    lo[k] = spread4(m);
                     hi[k] = m >> 4;
                 }
                 my_stage[OBS_W + 0] = lo[0];
@@ -545,28 +859,29 @@ __global__ void __launch_bounds__(512, 1) mapf_step_env_kernel(const KParams p, 
                         for (int k = 0; k < 4; ++k) if (i0 + k < N) p.o_goal_delta[ab + i0 + k] = gd[k];
                     }
                 }
-                if (p.o_blocking_prev) stq8<VEC>(p.o_blocking_prev, ab + i0, i0, N, true, bp4);
+                if (p.o_blocking_prev) stq8<VEC>(p.o_blocking_prev, ab + i0, i0, N, true, spread4(bprev_m >> i0));
                 if (p.sample_mode) stq8<VEC>(reinterpret_cast<uint8_t *>(p.o_next_actions), ab + i0, i0, N, true, next4);
             }
             // ------------------------------------------------ coalesced flush of the quad's byte channels
             __syncwarp();
-            const size_t env0 = (size_t)tile * 32;
             if (VEC) {
                 for (int w = lane; w < OBS_W + 5; w += 32) {
                     const bool is_obs = w < OBS_W;
                     unsigned char *gp = is_obs ? (p.o_local_obs ? p.o_local_obs + (env0 * N + i0) * V2 + 4 * w : nullptr)
                                                : (p.o_action_mask ? reinterpret_cast<unsigned char *>(p.o_action_mask) +
                                                                         (env0 * N + i0) * 5 + 4 * (w - OBS_W) : nullptr);
-                    const int gstride = is_obs ? N * V2 : N * 5;
+                    const uint32_t gstride = (uint32_t)(is_obs ? N * V2 : N * 5);
+                    const uint32_t *src = stage_w + w;
                     if (gp) {
                         if (act_w == full) {
-#pragma unroll 8
+#pragma unroll
                             for (int e = 0; e < 32; ++e)
-                                *reinterpret_cast<uint32_t *>(gp + (size_t)e * gstride) = stage_w[e * E.stage_stride + w];
+                                *reinterpret_cast<uint32_t *>(gp + (size_t)e * gstride) = src[e * STRIDE];
                         } else {
+#pragma unroll 1
                             for (int e = 0; e < 32; ++e)
                                 if ((act_w >> e) & 1u)
-                                    *reinterpret_cast<uint32_t *>(gp + (size_t)e * gstride) = stage_w[e * E.stage_stride + w];
+                                    *reinterpret_cast<uint32_t *>(gp + (size_t)e * gstride) = src[e * STRIDE];
                         }
                     }
                 }
@@ -574,7 +889,7 @@ __global__ void __launch_bounds__(512, 1) mapf_step_env_kernel(const KParams p, 
                 const int na = (N - i0) < 4 ? (N - i0) : 4;
                 for (int e = 0; e < 32; ++e) {
                     if (!((act_w >> e) & 1u)) continue;
-                    const uint8_t *src = reinterpret_cast<const uint8_t *>(stage_w + e * E.stage_stride);
+                    const uint8_t *src = reinterpret_cast<const uint8_t *>(stage_w + e * STRIDE);
                     if (p.o_local_obs) {
                         uint8_t *dst = p.o_local_obs + ((env0 + e) * N + i0) * V2;
                         for (int b = lane; b < na * V2; b += 32) dst[b] = src[b];
@@ -587,282 +902,11 @@ __global__ void __launch_bounds__(512, 1) mapf_step_env_kernel(const KParams p, 
             }
             __syncwarp();
         }
-    };
-    emit(ok, !reassigned, moved_m, bprev_m);
-
-    // ---------------------------------------------------------------- pass 3: owner masks, locks, blocking, wait-for graph
-    // The boards are dead: their memory now holds rowm[r] (.x) / colm[c] (.y): bit a = agent a's final row / column.
-    for (int r = 0; r < E.board_rows; ++r) board[r * 32] = make_uint2(0u, 0u);
-    for (int q = 0; q < NQ; ++q) {
-        const uint2 codes = scr_pos[q * 32];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (4 * q + k >= N || !ok) continue;
-            const uint32_t code = hget(codes, k);
-            board[(code >> 5) * 32].x |= 1u << (4 * q + k);
-            board[(code & 31u) * 32].y |= 1u << (4 * q + k);
+        if (stepmode) {
+            if (p.lock_enabled) lock_head = slot_next;
+            arrivals = __popc(gstep_m);
+            goals_total += arrivals;  // lifelong: every arrival; else first arrivals (ENV:545,562)
         }
-    }
-    uint32_t blocking_m = 0, coloc_any = 0, wf_alive = 0;
-    bool dl_any = false, ll_any = false;
-    const uint32_t intent_m = allN & ~reached_m;  // ENV:619-621: only agents that have not (sticky-)reached press
-    for (int q = 0; q < NQ; ++q) {
-        const int i0 = 4 * q;
-        const uint2 codes = scr_pos[q * 32];
-        const uint2 deltas = scr_delta[q * 32];
-        const uint32_t act4 = scr_act[q * 32];
-        uint32_t ptr4 = 0xFFFFFFFFu;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (i0 + k >= N || !ok) continue;
-            const int i = i0 + k;
-            const uint32_t bit = 1u << i;
-            const uint32_t code = hget(codes, k);
-            const int r = (int)(code >> 5), c = (int)(code & 31u);
-            const uint32_t here = board[r * 32].x & board[c * 32].y;   // agents on my cell (me included)
-            if (here & ~bit) coloc_any |= bit;
-            // ENV:389-438 neighbours within Manhattan distance `nearby`, via the row / column masks
-            if (p.lock_enabled && !(ongoal_m & bit)) {
-                uint32_t nb = 0, u = 0;
-                for (int w = 0; w <= p.nearby; ++w) {
-                    const int dd = p.nearby - w;
-                    if (c - w >= 0) u |= board[(c - w) * 32].y;
-                    if (c + w < C) u |= board[(c + w) * 32].y;
-                    uint32_t rm = 0;
-                    if (r - dd >= 0) rm |= board[(r - dd) * 32].x;
-                    if (r + dd < R) rm |= board[(r + dd) * 32].x;
-                    nb |= rm & u;
-                }
-                nb &= ~here;
-                if (__popc(nb) >= p.min_nb) {
-                    const uint32_t P = nb | bit;
-                    if (!(P & Gd) && !(P & Md) && (P & Fd)) dl_any = true;
-                    if (!(P & Gl) && (P & Ml)) {
-                        int red = (int)(int16_t)hget(deltas, k);
-                        uint32_t rest = nb;
-                        while (rest) {
-                            const int a = __ffs(rest) - 1;
-                            rest &= rest - 1;
-                            red += (int)(int16_t)hget(scr_delta[(a >> 2) * 32], a & 3);
-                        }
-                        if (red <= p.eps_floor) ll_any = true;
-                    }
-                }
-            }
-            // intended cell (kept even when invalid, ENV:514-515) -> who stands there
-            const int a = (int)((act4 >> (8 * k)) & 0xFFu);
-            const bool mv = (moved_m & bit) != 0;
-            int ir = r, ic = c;
-            if (!mv) { ir += (a == 3) - (a == 1); ic += (a == 2) - (a == 4); }
-            uint32_t owner = 0;
-            if ((unsigned)ir < (unsigned)R && (unsigned)ic < (unsigned)C) owner = board[ir * 32].x & board[ic * 32].y & ~bit;
-            if (!p.lifelong && (intent_m & bit)) blocking_m |= owner;   // ENV:609-623 (filtered below)
-            if ((failed_m & bit) && owner) {   // wait-for edge i -> owner
-                ptr4 = (ptr4 & ~(0xFFu << (8 * k))) | ((uint32_t)(31 - __clz(owner)) << (8 * k));
-                wf_alive |= bit;
-            }
-        }
-        scr_act[q * 32] = ptr4;
-    }
-    blocking_m &= reached_m & ~moved_m;
-    // wait-for cycles: strip agents whose target is gone or that nobody waits for, until stable
-    uint32_t wf_m = 0;
-    if (__any_sync(full, wf_alive != 0)) {
-        uint32_t alive = wf_alive;
-        for (;;) {
-            uint32_t keep = 0, targets = 0, rest = alive;
-            while (rest) {
-                const int i = __ffs(rest) - 1;
-                rest &= rest - 1;
-                const uint32_t t = (scr_act[(i >> 2) * 32] >> (8 * (i & 3))) & 0xFFu;
-                if ((alive >> t) & 1u) { keep |= 1u << i; targets |= 1u << t; }
-            }
-            keep &= targets;
-            const bool changed = keep != alive;
-            alive = keep;
-            if (!__any_sync(full, changed)) break;
-        }
-        wf_m = alive;
-    }
-    const bool wf_any = wf_m != 0;
-    wfg_steps += wf_any;
-    const int blocking_step = __popc(blocking_m);
-    blocking_total += blocking_step;
-
-    // ---------------------------------------------------------------- lock detection result, ENV:595-606
-    bool dl_step = false, ll_step = false, dl_event = false, ll_event = false;
-    if (p.lock_enabled) {
-        dl_step = count_after >= p.dw && dl_any;
-        ll_step = !dl_step && count_after >= p.lw && ll_any;
-        dl_event = dl_step && !(lock_prev & 1);
-        ll_event = ll_step && !(lock_prev & 2);
-        lock_prev = (dl_step ? 1 : 0) | (ll_step ? 2 : 0);
-        dl_steps += dl_step; ll_steps += ll_step; dl_events += dl_event; ll_events += ll_event;
-        lock_count = count_after;
-    }
-
-    // ---------------------------------------------------------------- rewards & termination, ENV:658-690
-    const uint32_t scratch_on = p.lifelong ? 0u : ongoal_m;   // reached_goal scratch (ENV:555)
-    bool terminated = false, truncated = false;
-    uint32_t bonus_m = 0, penalty_m = 0;
-    if (!p.lifelong && __popc(scratch_on) == N) { terminated = true; bonus_m = allN; }
-    else if (step_count >= p.steps_per_episode) {
-        terminated = true; truncated = true;  // F6
-        if (!p.lifelong) penalty_m = allN & ~scratch_on;
-    }
-    const bool done = ok && (terminated || truncated);
-    int rsum = 0;
-    for (int q = 0; q < NQ; ++q) {
-        const int i0 = 4 * q;
-        const uint2 codes = scr_pos[q * 32];
-        float rw[4];
-        uint32_t asf4 = 0, af4 = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            rw[k] = 0.f;
-            if (i0 + k >= N) continue;
-            const uint32_t bit = 1u << (i0 + k);
-            int rx2 = ((gstep_m & bit) ? 1 : 0) + ((bonus_m & bit) ? 2 : 0) - ((penalty_m & bit) ? 2 : 0);
-            if (coloc_any & bit) {   // ENV:658-666, -1 per co-located pair member
-                const uint32_t code = hget(codes, k);
-                rx2 -= 2 * (__popc(board[(code >> 5) * 32].x & board[(code & 31u) * 32].y) - 1);
-            }
-            rsum += rx2;
-            rw[k] = 0.5f * (float)rx2;
-            asf4 |= (uint32_t)(((moved_m & bit) ? MAPF_ASF_MOVED : 0) | ((failed_m & bit) ? MAPF_ASF_FAILED_MOVE : 0) |
-                               ((gstep_m & bit) ? MAPF_ASF_GOAL_REACHED : 0) | ((blocking_m & bit) ? MAPF_ASF_BLOCKING : 0) |
-                               ((wf_m & bit) ? MAPF_ASF_WFG_CYCLE : 0) | ((ongoal_m & bit) ? MAPF_ASF_ON_GOAL : 0)) << (8 * k);
-            af4 |= (uint32_t)(((reached_m & bit) ? MAPF_AF_REACHED : 0) | ((completed_m & bit) ? MAPF_AF_COMPLETED_ONCE : 0) |
-                              ((blocking_m & bit) ? MAPF_AF_BLOCKING_PREV : 0)) << (8 * k);
-        }
-        if (ok) {
-            if (p.o_reward) {
-                if (VEC) *reinterpret_cast<float4 *>(p.o_reward + ab + i0) = make_float4(rw[0], rw[1], rw[2], rw[3]);
-                else {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) if (i0 + k < N) p.o_reward[ab + i0 + k] = rw[k];
-                }
-            }
-            if (p.o_agent_step_flags) stq8<VEC>(p.o_agent_step_flags, ab + i0, i0, N, true, asf4);
-            stq8<VEC>(p.agent_flags, ab + i0, i0, N, true, af4);
-        }
-    }
-    ep_return_x2 += rsum;
-    const int n_comp = __popc(completed_m), n_reach = __popc(reached_m);
-    if (ok) {
-        if (p.o_info) {  // integer sources of info["__all__"], ENV:639-656
-            int4 *io = p.o_info + (size_t)env * 4;
-            io[0] = make_int4(arrivals, p.lifelong ? goals_total : n_reach, blocking_step, blocking_total);
-            io[1] = make_int4(dl_step, ll_step, dl_event, ll_event);
-            io[2] = make_int4(dl_events, ll_events, dl_steps, ll_steps);
-            io[3] = make_int4(n_comp, step_count, n_reach, wfg_steps);
-        }
-        if (p.o_terminated) p.o_terminated[env] = terminated;
-        if (p.o_truncated) p.o_truncated[env] = truncated;
-        if (p.o_step_flags)
-            p.o_step_flags[env] = (uint8_t)((terminated ? MAPF_SF_TERMINATED : 0) | (truncated ? MAPF_SF_TRUNCATED : 0) |
-                                            (dl_step ? MAPF_SF_DEADLOCK_STEP : 0) | (ll_step ? MAPF_SF_LIVELOCK_STEP : 0) |
-                                            (dl_event ? MAPF_SF_DEADLOCK_EVENT : 0) | (ll_event ? MAPF_SF_LIVELOCK_EVENT : 0) |
-                                            (reassigned ? MAPF_SF_GOAL_REASSIGNED : 0) | (wf_any ? MAPF_SF_WFG_CYCLE : 0));
-    }
-
-    // ---------------------------------------------------------------- episode end: metrics, auto-reset
-    if (done) {   // episode-end metric sums, src/trainers/callbacks.py:152,173,335-345
-        double *m = p.env_metrics + (size_t)env * MAPF_METRIC_COUNT;
-        const double gt = p.lifelong ? (double)goals_total : (double)n_reach;  // ENV:630-633
-        m[MAPF_M_EPISODES] += 1.0;
-        m[MAPF_M_RETURN_SUM] += 0.5 * (double)ep_return_x2;
-        m[MAPF_M_LENGTH_SUM] += (double)step_count;
-        m[MAPF_M_SUCCESS_SUM] += (terminated && !truncated) ? 1.0 : 0.0;
-        m[MAPF_M_GOALS_REACHED_SUM] += gt;
-        m[MAPF_M_BLOCKING_COUNT_SUM] += (double)blocking_total;
-        m[MAPF_M_DEADLOCK_COUNT_SUM] += (double)dl_events;
-        m[MAPF_M_LIVELOCK_COUNT_SUM] += (double)ll_events;
-        m[MAPF_M_DEADLOCK_STEPS_SUM] += (double)dl_steps;
-        m[MAPF_M_LIVELOCK_STEPS_SUM] += (double)ll_steps;
-        m[MAPF_M_THROUGHPUT_SUM] += gt / (double)(step_count > 1 ? step_count : 1);  // ENV:655
-        m[MAPF_M_COMPLETION_RATIO_SUM] += (double)n_comp / (double)N;                 // ENV:638
-        m[MAPF_M_WFG_CYCLE_STEPS_SUM] += (double)wfg_steps;
-        episodes += 1;
-    }
-    const bool do_reset = done && p.auto_reset;
-    if (__any_sync(full, do_reset)) {   // ENV:440-472 inside the launch (benchmark loop semantics)
-        if (do_reset) {
-            bool sample = !p.deterministic;
-            const int F = p.num_free[0];
-            if (sample && F < 2 * N) { errs |= MAPF_DEV_ERR_TOO_FEW_CELLS; sample = false; }
-            // scratch in the dead board memory: cs[a] in .x, cg[a] in .y of row a (cell-linear ids)
-            if (sample) {
-                // ENV:267-282 by symmetric rejection, the rule of draw_layout<G>: every slot draws uniformly,
-                // a slot equal to a lower-numbered slot (starts before goals) redraws in the next round
-                uint32_t rs = allN, rg = allN, rounds = 0;
-                while (rs | rg) {
-                    for (int a = 0; a < N; ++a) {
-                        if (!(((rs | rg) >> a) & 1u)) continue;
-                        const uint4 x = ph_env(rng_counter + rounds, (uint32_t)a, 0x52455345u /* "RESE" */, 0);
-                        uint2 v = board[a * 32];
-                        if ((rs >> a) & 1u) v.x = (uint32_t)select_kth(freebits, p.fw, (int)__umulhi(x.x, (uint32_t)F));
-                        if ((rg >> a) & 1u) v.y = (uint32_t)select_kth(freebits, p.fw, (int)__umulhi(x.y, (uint32_t)F));
-                        board[a * 32] = v;
-                    }
-                    rs = 0; rg = 0;
-                    for (int g = 0; g < N; ++g) {
-                        const uint2 me = board[g * 32];
-                        for (int a = 0; a < N; ++a) {
-                            const uint2 o = board[a * 32];
-                            if (a < g && o.x == me.x) rs |= 1u << g;
-                            if (o.x == me.y) rg |= 1u << g;
-                            if (a < g && o.y == me.y) rg |= 1u << g;
-                        }
-                    }
-                    rounds++;
-                }
-                rng_counter += rounds;
-            }
-            for (int q = 0; q < NQ; ++q) {
-                const int i0 = 4 * q;
-                uint4 stq = make_uint4(0, 0, 0, 0), ggq = stq;
-                const uint4 curp = ldq32<VEC>(p.positions, ab + i0, i0, N, true, 0u);
-                const uint4 curg = ldq32<VEC>(p.goals, ab + i0, i0, N, true, 0u);
-                uint4 detst = make_uint4(0, 0, 0, 0);
-                if (p.deterministic) detst = ldq32<VEC>(p.starts, ab + i0, i0, N, true, 0u);
-                uint2 codes = make_uint2(0u, 0u);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    if (i0 + k >= N) continue;
-                    uint32_t st, gg;
-                    if (p.deterministic) { st = qget(detst, k); gg = qget(curg, k); }  // F7
-                    else if (sample) {
-                        const uint2 v = board[(i0 + k) * 32];
-                        st = pack_rc((int)v.x / C, (int)v.x % C);
-                        gg = pack_rc((int)v.y / C, (int)v.y % C);
-                    } else { st = qget(curp, k); gg = qget(curg, k); }
-                    qset(stq, k, st); qset(ggq, k, gg);
-                    hset(codes, k, code_of(st));
-                }
-                scr_pos[q * 32] = codes;
-                stq32<VEC>(p.positions, ab + i0, i0, N, true, stq);
-                if (sample) { stq32<VEC>(p.starts, ab + i0, i0, N, true, stq); stq32<VEC>(p.goals, ab + i0, i0, N, true, ggq); }
-                stq8<VEC>(p.agent_flags, ab + i0, i0, N, true, 0u);
-                if (p.lock_enabled) {
-                    const uint4 z = make_uint4(0, 0, 0, 0);
-                    stq32<VEC>(p.lock_gp, ab + i0, i0, N, true, z);
-                    stq32<VEC>(p.lock_mv, ab + i0, i0, N, true, z);
-                    stq32<VEC>(p.lock_fm, ab + i0, i0, N, true, z);
-                }
-            }
-            step_count = 0; lock_count = 0; lock_head = 0; lock_prev = 0; goals_total = 0; blocking_total = 0;
-            dl_events = ll_events = dl_steps = ll_steps = 0; ep_return_x2 = 0; wfg_steps = 0;
-            // boards of the new layout: first observation of the next episode (final state, no staggering at reset)
-            for (int r = 0; r < E.board_rows; ++r) board[r * 32] = make_uint2(0u, 0u);
-            for (int i = 0; i < N; ++i) {
-                const uint32_t pc = hget(scr_pos[(i >> 2) * 32], i & 3);
-                const uint32_t gc = code_of(p.goals[ab + i]);
-                board[(pc >> 5) * 32].x |= 1u << (pc & 31u);
-                board[(gc >> 5) * 32].y |= 1u << (gc & 31u);
-            }
-        }
-        emit(do_reset, false, 0u, 0u);
     }
 
     // ---------------------------------------------------------------- env words write-back

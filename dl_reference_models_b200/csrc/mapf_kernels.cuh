@@ -117,6 +117,7 @@ struct KParams {
     const uint32_t *map_rows;   // [(R+2*PAD) * wpr] bit (c+PAD) of padded row (r+PAD) = obstacle/OOB
     const uint32_t *free_bits;  // [fw] bit (r*C+c) = free cell
     const int32_t *num_free;    // [1] or [B]
+    const uint32_t *env_tables; // CTA-wide table image of the env-per-thread kernel (EnvLayout, shared map only)
     int wpr, map_words, fw;
     // state
     uint32_t *positions, *goals, *starts;  // int16 pairs viewed as u32: row | col << 16
