@@ -77,14 +77,19 @@ constexpr size_t kMaxSmem = 200 * 1024;
 constexpr size_t kMaxSmemEnv = 227 * 1024;  // opt-in limit of one sm_100 CTA
 
 using EnvKernelFn = void (*)(const mapf::KParams, const mapf::EnvLayout);
-template <bool VEC>
+template <bool VEC, int LPE>
 EnvKernelFn env_step_for_sr(int sr) {
     switch (sr) {
-        case 1: return mapf::mapf_step_env_kernel<1, VEC>;
-        case 2: return mapf::mapf_step_env_kernel<2, VEC>;
-        case 3: return mapf::mapf_step_env_kernel<3, VEC>;
+        case 1: return mapf::mapf_step_env_kernel<1, VEC, LPE>;
+        case 2: return mapf::mapf_step_env_kernel<2, VEC, LPE>;
+        case 3: return mapf::mapf_step_env_kernel<3, VEC, LPE>;
     }
     return nullptr;
+}
+EnvKernelFn pick_env_step(int sr, bool vec, int lpe) {
+    if (lpe == 4) return env_step_for_sr<true, 4>(sr);
+    if (lpe == 2) return env_step_for_sr<true, 2>(sr);
+    return vec ? env_step_for_sr<true, 1>(sr) : env_step_for_sr<false, 1>(sr);
 }
 
 }  // namespace
@@ -389,12 +394,17 @@ int mapf_create(const mapf_config *cfg, mapf_handle **out) {
     h->env_threads = 0;
     h->use_env_kernel = false;
     if (e1 == cudaSuccess && c.cols <= 32 && c.rows <= mapf::ENV_MAX_ROWS && !c.per_env_maps) {
-        const int ntiles = (c.num_envs + 31) / 32;
+        int lpe_mode = 1;   // MAPF_ENV_LPE=0: several lanes per env where the shape allows (experimental)
+        if (const char *ov = getenv("MAPF_ENV_LPE")) lpe_mode = atoi(ov) == 0 ? 0 : 1;
+        const int lpe = mapf::make_env_layout(c.num_agents, c.rows, c.cols, h->SR, h->fw, 1, lpe_mode).lpe;
+        const int epw = 32 / lpe, max_warps = lpe == 1 ? 14 : 16;   // __launch_bounds__ of mapf_step_env_kernel
+        const int ntiles = (c.num_envs + epw - 1) / epw;
         int want = (ntiles + (nsm > 0 ? nsm : 1) - 1) / (nsm > 0 ? nsm : 1);  // warps per CTA for one resident wave
-        if (want > 14) want = 14;  // __launch_bounds__(448) of mapf_step_env_kernel
+        if (want > max_warps) want = max_warps;
         if (want < 1) want = 1;
+        if (const char *ov = getenv("MAPF_ENV_WARPS")) { const int v = atoi(ov); if (v >= 1 && v <= max_warps) want = v; }
         for (int w = want; w >= 1; --w) {
-            mapf::EnvLayout E = mapf::make_env_layout(c.num_agents, c.rows, c.cols, h->SR, h->fw, w);
+            mapf::EnvLayout E = mapf::make_env_layout(c.num_agents, c.rows, c.cols, h->SR, h->fw, w, lpe_mode);
             if ((size_t)E.total_bytes <= kMaxSmemEnv) {
                 h->env_threads = 32 * w;
                 h->env_layout = E;
@@ -402,7 +412,7 @@ int mapf_create(const mapf_config *cfg, mapf_handle **out) {
             }
         }
         if (h->env_threads) {
-            h->env_fn = (c.num_agents % 4 == 0) ? env_step_for_sr<true>(h->SR) : env_step_for_sr<false>(h->SR);
+            h->env_fn = pick_env_step(h->SR, c.num_agents % 4 == 0, lpe);
             e1 = cudaFuncSetAttribute(reinterpret_cast<const void *>(h->env_fn),
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmemEnv);
             const int w = h->env_threads / 32;
@@ -427,6 +437,7 @@ int mapf_create(const mapf_config *cfg, mapf_handle **out) {
         // below that the lane-per-agent kernel has 16x more warps in flight and wins.
         const long long ntiles = (c.num_envs + 31) / 32;
         h->use_env_kernel = h->env_threads && (want_kernel == 2 || (want_kernel == 0 && ntiles >= 12LL * (nsm > 0 ? nsm : 1)));
+        (void)ntiles;
     }
     cudaError_t e3 = cudaMalloc(&h->d_err, 4);
     if (e3 == cudaSuccess) e3 = cudaMemset(h->d_err, 0, 4);

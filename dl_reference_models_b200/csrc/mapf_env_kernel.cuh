@@ -45,13 +45,22 @@ __host__ __device__ constexpr int env_stage_stride(int V2) { return ((4 * V2 + 2
 
 struct EnvLayout {
     int tables_bytes;  // multiple of 16
-    int warp_bytes;    // per-warp block: [stage][boards][agent records]
+    int warp_bytes;    // per-warp block: [stage][occupancy boards][goal boards][agent records]
     int board_rows;    // max(R, C, N) + 2 * ENV_ROW_PAD
     int nq;            // ceil(N / 4)
+    int lpe;           // lanes per env: 1, 2 or 4 (each lane owns one quad of agents when > 1)
     int total_bytes;
 };
 
-__host__ __device__ inline EnvLayout make_env_layout(int N, int R, int C, int SR, int fw, int warps) {
+// Lanes per env.  With more than one lane every lane owns exactly one quad (N == 4 * lanes), keeps a private
+// occupancy board and replays the moves of the quads before its own; the goal board and the agent records
+// are shared by the env's lanes.
+__host__ __device__ inline int env_lanes_per_env(int N) { return N == 16 ? 4 : N == 8 ? 2 : 1; }
+
+// `lanes_per_env` = 1: one thread per env (the default); 0: env_lanes_per_env(N) (measured slower on B200 at the
+// C3 shape: 86 us against 82 us per launch -- the replayed moves and the per-lane board copies eat the extra
+// occupancy -- and kept selectable with MAPF_ENV_LPE=0 for the next round of tuning).
+__host__ __device__ inline EnvLayout make_env_layout(int N, int R, int C, int SR, int fw, int warps, int lanes_per_env = 1) {
     const int V = 2 * SR + 1, V2 = V * V;
     EnvLayout E;
     E.tables_bytes = (ENV_LUT_OFF + R * 32 * (V > 5 ? 8 : 4) + 15) & ~15;
@@ -59,9 +68,14 @@ __host__ __device__ inline EnvLayout make_env_layout(int N, int R, int C, int SR
     if (N > E.board_rows) E.board_rows = N;  // reset draws park 2N cell ids in the dead boards
     E.board_rows += 2 * ENV_ROW_PAD;
     E.nq = (N + 3) / 4;
-    int w = 32 * env_stage_stride(V2) * 4;   // stage
-    w += E.board_rows * 32 * 8;              // boards: uint2 [row][lane]
-    w += 4 * E.nq * 32 * 4;                  // agent records: u32 [agent][lane]
+    E.lpe = lanes_per_env == 0 ? env_lanes_per_env(N) : 1;
+    // the shared old-occupancy board of the pre-pass lives in the (idle) stage: [board_rows][envs per warp] words
+    if (E.lpe > 1 && E.board_rows * (32 / E.lpe) > 32 * env_stage_stride(V2)) E.lpe = 1;
+    const int epw = 32 / E.lpe;              // envs per warp
+    int w = 32 * env_stage_stride(V2) * 4;   // stage: one row per lane
+    w += E.board_rows * 32 * 4;              // occupancy boards: u32 [row][lane], private per lane
+    w += E.board_rows * epw * 4;             // goal boards: u32 [row][env], shared by an env's lanes
+    w += 4 * E.nq * epw * 4;                 // agent records: u32 [agent][env]
     w = (w + 15) & ~15;
     E.warp_bytes = w;
     // window rows above / below the map read up to 3 board rows beyond a warp's boards: keep that inside the allocation
@@ -204,16 +218,17 @@ inline void build_env_tables(int SR, int R, int C, int wpr, int fw, const uint32
     }
 }
 
-// ENV:284-304 at agent i's turn (rare path, kept out of line): the occupancy board IS snapshot i and the goal
-// board holds everybody's current goal.  Returns the new goal code (the old one if no cell is available).
-// .y of the result: bit 0 = one Philox draw consumed, bit 1 = MAPF_DEV_ERR_NO_GOAL_CELL.
-__device__ __noinline__ uint2 env_assign_new_goal(uint2 *board, const uint32_t *freerow, int R,
+// ENV:284-304 for agent i (rare path, kept out of line).  `occ` is the caller's occupancy board rolled back to
+// snapshot i (row stride 32 words), `goalb` the env's goal board (row stride `gs` words) holding everybody's
+// current goal.  Returns the new goal code (the old one if no cell is available) in .x;
+// .y: bit 0 = one Philox draw consumed, bit 1 = MAPF_DEV_ERR_NO_GOAL_CELL.
+__device__ __noinline__ uint2 env_assign_new_goal(const uint32_t *occ, uint32_t *goalb, int gs, const uint32_t *freerow, int R,
                                                   const uint32_t *goal_override, const int32_t *goal_rank,
                                                   size_t agent_index, int i, uint32_t gcode,
                                                   unsigned long long seed, long long env_global,
                                                   uint32_t rng_counter) {
     uint32_t flags = 0;
-    board[(gcode >> 5) * 32].y &= ~(1u << (gcode & 31u));   // ENV:288 clear the old goal owner
+    goalb[(gcode >> 5) * gs] &= ~(1u << (gcode & 31u));   // ENV:288 clear the old goal owner
     uint32_t ng = 0xFFFFFFFFu;
     if (goal_override) {
         const uint32_t ov = goal_override[agent_index];
@@ -221,7 +236,7 @@ __device__ __noinline__ uint2 env_assign_new_goal(uint2 *board, const uint32_t *
     }
     if (ng == 0xFFFFFFFFu) {
         int n = 0;
-        for (int r = 0; r < R; ++r) { const uint2 b = board[r * 32]; n += __popc(freerow[r] & ~b.x & ~b.y); }
+        for (int r = 0; r < R; ++r) n += __popc(freerow[r] & ~occ[r * 32] & ~goalb[r * gs]);
         int kk = -1;
         if (goal_rank) kk = goal_rank[agent_index];
         if (kk < 0 && n > 0) {
@@ -232,8 +247,7 @@ __device__ __noinline__ uint2 env_assign_new_goal(uint2 *board, const uint32_t *
         }
         if (n > 0 && kk < n) {
             for (int r = 0; r < R; ++r) {
-                const uint2 b = board[r * 32];
-                const uint32_t cand = freerow[r] & ~b.x & ~b.y;
+                const uint32_t cand = freerow[r] & ~occ[r * 32] & ~goalb[r * gs];
                 const int c = __popc(cand);
                 if (kk < c) { ng = (uint32_t)(r * 32) + __fns(cand, 0, kk + 1); break; }
                 kk -= c;
@@ -242,16 +256,17 @@ __device__ __noinline__ uint2 env_assign_new_goal(uint2 *board, const uint32_t *
         if (ng == 0xFFFFFFFFu) flags |= 2u;
     }
     if (ng == 0xFFFFFFFFu) ng = gcode;  // error flagged: keep the old goal
-    board[(ng >> 5) * 32].y |= 1u << (ng & 31u);
+    goalb[(ng >> 5) * gs] |= 1u << (ng & 31u);
     return make_uint2(ng, flags);
 }
 
 // ENV:267-282 for one env (rare path): symmetric rejection with the rule of draw_layout<G> -- every slot
 // draws uniformly, a slot equal to a lower-numbered slot (starts before goals) redraws in the next round.
-// The drawn cell ids are parked in the dead board memory: start of agent a in .x, goal in .y of row a.
+// The drawn cell ids are parked in dead board memory: start of agent a in cs[a * 32], goal in cg[a * cgs].
 // Returns the number of rounds (= Philox counter values) consumed.
-__device__ __noinline__ uint32_t env_draw_layout(uint2 *board, const uint32_t *freebits, int fw, int F, int N,
-                                                 unsigned long long seed, long long env_global, uint32_t rng_counter) {
+__device__ __noinline__ uint32_t env_draw_layout(uint32_t *cs, uint32_t *cg, int cgs, const uint32_t *freebits, int fw,
+                                                 int F, int N, unsigned long long seed, long long env_global,
+                                                 uint32_t rng_counter) {
     const Philox ph(seed, env_global);
     const uint32_t allN = (N >= 32) ? 0xFFFFFFFFu : ((1u << N) - 1u);
     uint32_t rs = allN, rg = allN, rounds = 0;
@@ -259,19 +274,17 @@ __device__ __noinline__ uint32_t env_draw_layout(uint2 *board, const uint32_t *f
         for (int a = 0; a < N; ++a) {
             if (!(((rs | rg) >> a) & 1u)) continue;
             const uint4 x = ph(rng_counter + rounds, (uint32_t)a, 0x52455345u /* "RESE" */, 0);
-            uint2 v = board[a * 32];
-            if ((rs >> a) & 1u) v.x = (uint32_t)select_kth(freebits, fw, (int)__umulhi(x.x, (uint32_t)F));
-            if ((rg >> a) & 1u) v.y = (uint32_t)select_kth(freebits, fw, (int)__umulhi(x.y, (uint32_t)F));
-            board[a * 32] = v;
+            if ((rs >> a) & 1u) cs[a * 32] = (uint32_t)select_kth(freebits, fw, (int)__umulhi(x.x, (uint32_t)F));
+            if ((rg >> a) & 1u) cg[a * cgs] = (uint32_t)select_kth(freebits, fw, (int)__umulhi(x.y, (uint32_t)F));
         }
         rs = 0; rg = 0;
         for (int g = 0; g < N; ++g) {
-            const uint2 me = board[g * 32];
+            const uint32_t ms = cs[g * 32], mg = cg[g * cgs];
             for (int a = 0; a < N; ++a) {
-                const uint2 o = board[a * 32];
-                if (a < g && o.x == me.x) rs |= 1u << g;
-                if (o.x == me.y) rg |= 1u << g;
-                if (a < g && o.y == me.y) rg |= 1u << g;
+                const uint32_t os = cs[a * 32], og = cg[a * cgs];
+                if (a < g && os == ms) rs |= 1u << g;
+                if (os == mg) rg |= 1u << g;
+                if (a < g && og == mg) rg |= 1u << g;
             }
         }
         rounds++;
@@ -289,13 +302,25 @@ __device__ __forceinline__ uint32_t nibbles_to_bytes(uint32_t sel) {
 __device__ __forceinline__ uint32_t spread4(uint32_t m) { return ((m & 15u) * 0x00204081u) & 0x01010101u; }
 // bit `b` of each of the 4 bytes of w -> nibble
 __device__ __forceinline__ uint32_t gather4(uint32_t w, int b) { return ((((w >> b) & 0x01010101u) * 0x01020408u) >> 24) & 15u; }
+// cell delta of an action {0, -32, +1, +32, -1} (ENV:104-113 on cell codes)
+__device__ __forceinline__ int action_delta(uint32_t a) { return (int)(int8_t)__byte_perm(0x2001E000u, 0x000000FFu, a); }
+// OR over the lanes of one env
+template <int LPE>
+__device__ __forceinline__ uint32_t group_or(uint32_t v) {
+#pragma unroll
+    for (int s = 1; s < LPE; s <<= 1) v |= __shfl_xor_sync(0xFFFFFFFFu, v, s);
+    return v;
+}
 
-// agent record in shared memory, rec[agent * 32] per lane:
+// agent record in shared memory, rec[agent * EPW] per env:
 //   bits 0..10 cell code | 11..13 action | 14 target blocked (obstacle / out of bounds) | 16..31 int16 distance delta
 constexpr uint32_t REC_CODE = 0x7FFu;
 
-template <int SR, bool VEC>
-__global__ void __launch_bounds__(448, 1) mapf_step_env_kernel(const KParams p, const EnvLayout E) {
+// One env per LPE lanes.  LPE = 1: the thread walks all quads of its env.  LPE = 2 / 4 (N = 8 / 16): lane `sub`
+// owns quad `sub`; it first replays the moves of quads < sub on its private occupancy board (moves only: a move
+// needs nothing but the board, ENV:516-526), then all lanes walk their own quad at the same time.
+template <int SR, bool VEC, int LPE>
+__global__ void __launch_bounds__(LPE == 1 ? 448 : 512, 1) mapf_step_env_kernel(const KParams p, const EnvLayout E) {
     constexpr int V = 2 * SR + 1, V2 = V * V;
     constexpr uint32_t VM = (1u << V) - 1u;
     constexpr uint32_t M4 = VM << 2;          // a window row, pre-scaled by 4 (byte offset into t1)
@@ -304,10 +329,12 @@ __global__ void __launch_bounds__(448, 1) mapf_step_env_kernel(const KParams p, 
     constexpr int STAGE_BYTES = 32 * STRIDE * 4;
     constexpr int CTR = SR * V + SR;
     constexpr int PADR = ENV_ROW_PAD;
+    constexpr int EPW = 32 / LPE;             // envs per warp
     using WB = typename WinBits<V>::type;
     extern __shared__ __align__(16) unsigned char esm[];
     const unsigned full = 0xFFFFFFFFu;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, warps = blockDim.x >> 5;
+    const int sub = lane % LPE, ew = lane / LPE, g0 = lane - sub;
     const int N = p.N, R = p.R, C = p.C, NQ = E.nq;
 
     // ------------------------------------------------------------------ CTA-wide tables (built on the host)
@@ -325,28 +352,37 @@ __global__ void __launch_bounds__(448, 1) mapf_step_env_kernel(const KParams p, 
     const float *gdt = reinterpret_cast<const float *>(esm + ENV_GDT_OFF);
 
     unsigned char *wsm = esm + E.tables_bytes + warp * E.warp_bytes;
-    uint32_t *stage_w = reinterpret_cast<uint32_t *>(wsm);                        // [lane][STRIDE] words
+    uint32_t *stage_w = reinterpret_cast<uint32_t *>(wsm);                              // [lane][STRIDE] words
     uint32_t *my_stage = stage_w + lane * STRIDE;
-    uint2 *board = reinterpret_cast<uint2 *>(wsm + STAGE_BYTES) + lane;           // row r at board[r * 32]: .x occupancy, .y goals
-    uint32_t *rec = reinterpret_cast<uint32_t *>(wsm + STAGE_BYTES + E.board_rows * 256) + lane;  // agent a at rec[a * 32]
-    const int ntiles = (p.B + 31) >> 5;
+    uint32_t *occ_w = reinterpret_cast<uint32_t *>(wsm + STAGE_BYTES);                  // [row][32]
+    uint32_t *occ = occ_w + lane;                                                       // my occupancy board: row r at occ[r * 32]
+    uint32_t *goalb = occ_w + E.board_rows * 32 + ew;                                   // env's goal board: row r at goalb[r * EPW]
+    uint32_t *rec = occ_w + E.board_rows * 32 + E.board_rows * EPW + ew;                // agent a at rec[a * EPW]
+    // owner masks of the epilogue (dead board memory, row stride 32 words): bit a of rowm[r] / colm[c] = agent a's row / column
+    uint32_t *rowm = (LPE == 1) ? occ : occ_w + g0;
+    uint32_t *colm = (LPE == 1) ? goalb : occ_w + g0 + 1;
+    const int ntiles = (p.B + EPW - 1) / EPW;
     uint32_t errs = 0;
     const uint32_t mdw = p.dw >= 32 ? full : ((1u << p.dw) - 1u);
     const uint32_t mlw = p.lw >= 32 ? full : ((1u << p.lw) - 1u);
     const uint32_t allN = (N >= 32) ? full : ((1u << N) - 1u);
+    // agents of the quads this lane owns
+    uint32_t own_m = 0;
+    for (int q = sub; q < NQ; q += LPE) own_m |= 0xFu << (4 * q);
+    own_m &= allN;
 
     for (int tile = blockIdx.x * warps + warp; tile < ntiles; tile += gridDim.x * warps) {
-    const int env = tile * 32 + lane;
+    const int env = tile * EPW + ew;
     const bool ok = env < p.B;
     const size_t ab = (size_t)(ok ? env : 0) * N;
     const long long env_global = p.env_id_base + env;
-    const size_t env0 = (size_t)tile * 32;
+    const size_t env0 = (size_t)tile * EPW;
 
     // ---------------------------------------------------------------- env words
     int4 w0 = make_int4(0, 0, 0, 0), w1 = w0, w2 = w0, w3 = w0;
     if (ok) {
-        const int4 *ew = p.env_words + (size_t)env * 4;
-        w0 = ew[0]; w1 = ew[1]; w2 = ew[2]; w3 = ew[3];
+        const int4 *ew4 = p.env_words + (size_t)env * 4;
+        w0 = ew4[0]; w1 = ew4[1]; w2 = ew4[2]; w3 = ew4[3];
     }
     int step_count = w0.x + 1;  // ENV:475
     int lock_count = w0.y, lock_prev = w0.z, goals_total = w0.w;
@@ -362,23 +398,56 @@ __global__ void __launch_bounds__(448, 1) mapf_step_env_kernel(const KParams p, 
     const int slot_next = (lock_head + 1 == p.lw) ? 0 : lock_head + 1;
     const bool use_ring = p.lock_enabled && count_after >= p.lw && p.lw > 1;
 
-    // ---------------------------------------------------------------- pre-pass: owner boards of the state before the step
-    for (int r = 0; r < E.board_rows; ++r) board[r * 32] = make_uint2(0u, 0u);
-    for (int q = 0; q < NQ; ++q) {
+    // ---------------------------------------------------------------- pre-pass: agent records and owner boards of the state before the step
+    for (int j = lane; j < E.board_rows * EPW; j += 32) (goalb - ew)[j] = 0u;
+    if (LPE > 1) { for (int j = lane; j < E.board_rows * EPW; j += 32) stage_w[j] = 0u; }   // shared old-occupancy board (stage is idle)
+    else { for (int r = 0; r < E.board_rows; ++r) occ[r * 32] = 0u; }
+    __syncwarp();
+    for (int q = sub; q < NQ; q += LPE) {
         const int i0 = 4 * q;
         const uint4 pq = ldq32<VEC>(p.positions, ab + i0, i0, N, ok, 0u);
         const uint4 gq = ldq32<VEC>(p.goals, ab + i0, i0, N, ok, 0u);
+        const uint32_t act4 = p.actions ? ldq8<VEC>(reinterpret_cast<const uint8_t *>(p.actions), ab + i0, i0, N, ok) : 0u;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             if (i0 + k < N) {
                 const uint32_t code = code_of(qget(pq, k)), gcode = code_of(qget(gq, k));
-                rec[(i0 + k) * 32] = code;
+                int a = (int)(int8_t)(act4 >> (8 * k));
+                if (a < 0 || a > 4) { errs |= MAPF_DEV_ERR_INVALID_ACTION; a = 0; }
+                // target obstacle / bounds from the cell's obstacle window (ENV:516-521)
+                const uint32_t nbi = __byte_perm((uint32_t)CTR | ((uint32_t)(CTR - V) << 8) | ((uint32_t)(CTR + 1) << 16) |
+                                                 ((uint32_t)(CTR + V) << 24), (uint32_t)(CTR - 1), (uint32_t)a) & 0xFFu;
+                const uint32_t tblocked = ((uint32_t)lut[code] >> nbi) & 1u;
+                rec[(i0 + k) * EPW] = code | ((uint32_t)a << 11) | (tblocked << 14);
                 if (ok) {
-                    board[(code >> 5) * 32].x |= 1u << (code & 31u);
-                    board[(gcode >> 5) * 32].y |= 1u << (gcode & 31u);
+                    if (LPE > 1) {
+                        atomicOr(&stage_w[(code >> 5) * EPW + ew], 1u << (code & 31u));
+                        atomicOr(&goalb[(gcode >> 5) * EPW], 1u << (gcode & 31u));
+                    } else {
+                        occ[(code >> 5) * 32] |= 1u << (code & 31u);
+                        goalb[(gcode >> 5) * EPW] |= 1u << (gcode & 31u);
+                    }
                 }
             }
         }
+    }
+    if (LPE > 1) {
+        __syncwarp();
+        for (int r = 0; r < E.board_rows; ++r) occ[r * 32] = stage_w[r * EPW + ew];   // private copy of the old occupancy
+        // replay the moves of the quads before mine (ENV:516-526 needs the board only)
+        for (int i = 0; i < 4 * (LPE - 1); ++i) {
+            const uint32_t rv = rec[i * EPW];
+            if (i < 4 * sub && ok && (rv & 0x3800u) && !(rv & 0x4000u)) {
+                const uint32_t code = rv & REC_CODE, tcode = code + (uint32_t)action_delta((rv >> 11) & 7u);
+                uint32_t *trow = &occ[(tcode >> 5) * 32];
+                const uint32_t tb = 1u << (tcode & 31u);
+                if (!(*trow & tb)) {
+                    occ[(code >> 5) * 32] &= ~(1u << (code & 31u));
+                    *trow |= tb;
+                }
+            }
+        }
+        __syncwarp();   // everybody has copied the shared board and read the old records before walks overwrite them
     }
 
     uint32_t moved_m = 0, failed_m = 0, gstep_m = 0, ongoal_m = 0;
@@ -396,66 +465,138 @@ __global__ void __launch_bounds__(448, 1) mapf_step_env_kernel(const KParams p, 
     for (int round = 0; round < 3; ++round) {
         bool active = ok;
         if (round == 1) {
+            // ------------------------------------------------------------ env-level masks; lifelong goal reassignment (ENV:284-304)
+            if (LPE > 1) {
+                moved_m = group_or<LPE>(moved_m); failed_m = group_or<LPE>(failed_m); gstep_m = group_or<LPE>(gstep_m);
+                ongoal_m = group_or<LPE>(ongoal_m); reached_m = group_or<LPE>(reached_m); completed_m = group_or<LPE>(completed_m);
+                Gd = group_or<LPE>(Gd); Md = group_or<LPE>(Md); Fd = group_or<LPE>(Fd); Gl = group_or<LPE>(Gl); Ml = group_or<LPE>(Ml);
+            }
+            if (p.lock_enabled) lock_head = slot_next;
+            arrivals = __popc(gstep_m);
+            goals_total += arrivals;  // lifelong: every arrival; else first arrivals (ENV:545,562)
+            uint32_t pend = p.lifelong ? gstep_m : 0u;
+            reassigned = pend != 0;
             if (!__any_sync(full, reassigned)) continue;
+            // Arrivals are served in agent order.  The owner of agent i rolls its occupancy board back to snapshot i
+            // (its own later moves undone), draws the new goal against the env's goal board, rolls forward again and
+            // re-does the one piece of lock history that depends on the goal: the distance.
+            while (__any_sync(full, pend != 0)) {
+                const int i = pend ? __ffs(pend) - 1 : 0;
+                const bool mine = pend != 0 && ((own_m >> i) & 1u);
+                uint32_t fl = 0;
+                if (mine) {
+                    const uint32_t later = moved_m & own_m & ~((2u << i) - 1u);
+                    for (uint32_t m = later; m;) {   // undo, highest index first
+                        const int j = 31 - __clz(m);
+                        m &= ~(1u << j);
+                        const uint32_t rv = rec[j * EPW], nc = rv & REC_CODE, oc = nc - (uint32_t)action_delta((rv >> 11) & 7u);
+                        occ[(nc >> 5) * 32] &= ~(1u << (nc & 31u));
+                        occ[(oc >> 5) * 32] |= 1u << (oc & 31u);
+                    }
+                    const uint32_t gcode = code_of(p.goals[ab + i]);
+                    const uint2 ng = env_assign_new_goal(occ, goalb, EPW, freerow, R, p.goal_override, p.goal_rank, ab + i, i, gcode,
+                                                         p.seed, env_global, rng_counter);
+                    fl = ng.y | 4u;
+                    for (uint32_t m = later; m;) {   // redo, lowest index first
+                        const int j = __ffs(m) - 1;
+                        m &= m - 1;
+                        const uint32_t rv = rec[j * EPW], nc = rv & REC_CODE, oc = nc - (uint32_t)action_delta((rv >> 11) & 7u);
+                        occ[(oc >> 5) * 32] &= ~(1u << (oc & 31u));
+                        occ[(nc >> 5) * 32] |= 1u << (nc & 31u);
+                    }
+                    p.goals[ab + i] = packed_of(ng.x);
+                    if (p.lock_enabled) {   // ENV:591: distance to the NEW goal
+                        const uint32_t rv = rec[i * EPW], code = rv & REC_CODE;
+                        const int dist = abs((int)(ng.x >> 5) - (int)(code >> 5)) + abs((int)(ng.x & 31u) - (int)(code & 31u));
+                        p.lock_dist[((size_t)env * p.lw + slot_new) * N + i] = (int16_t)dist;
+                        if (use_ring) {
+                            const int ring_old = (int)p.lock_dist[((size_t)env * p.lw + slot_next) * N + i];
+                            rec[i * EPW] = (rv & 0xFFFFu) | ((uint32_t)(ring_old - dist) << 16);
+                        }
+                    }
+                }
+                if (LPE > 1) fl = group_or<LPE>(fl);
+                rng_counter += fl & 1u;
+                if (fl & 2u) { errs |= MAPF_DEV_ERR_NO_GOAL_CELL; ongoal_m |= 1u << i; }   // no cell: the old goal stays, the agent is on it
+                pend &= pend - 1;
+                __syncwarp();
+            }
+            if (LPE > 1) {   // everybody shows the final state: take the board of the env's last lane
+                __syncwarp();
+                const uint32_t *fin = occ_w + g0 + (LPE - 1);
+                if (sub != LPE - 1) for (int r = 0; r < E.board_rows; ++r) occ[r * 32] = fin[r * 32];
+                __syncwarp();
+            }
             active = reassigned;
         }
         if (round == 2) {
             // ------------------------------------------------------------ epilogue: owner masks, locks, blocking, wait-for graph
-            // The boards are dead: their memory now holds rowm[r] (.x of row r + PADR) / colm[c] (.y of row c + PADR):
-            // bit a = agent a's final row / column; PADR zero rows on both sides.
-            for (int r = 0; r < E.board_rows; ++r) board[r * 32] = make_uint2(0u, 0u);
+            // The boards are dead: rowm[r + PADR] / colm[c + PADR] get bit a for agent a's final row / column
+            // (PADR zero rows on both sides).
+            __syncwarp();
+            for (int r = 0; r < E.board_rows; ++r) occ[r * 32] = 0u;
+            if (LPE == 1) for (int r = 0; r < E.board_rows; ++r) goalb[r * EPW] = 0u;
+            __syncwarp();
             if (ok) {
-                for (int i = 0; i < N; ++i) {
-                    const uint32_t code = rec[i * 32] & REC_CODE;
-                    board[((code >> 5) + PADR) * 32].x |= 1u << i;
-                    board[((code & 31u) + PADR) * 32].y |= 1u << i;
+                for (uint32_t m = own_m; m;) {
+                    const int i = __ffs(m) - 1;
+                    m &= m - 1;
+                    const uint32_t code = rec[i * EPW] & REC_CODE;
+                    if (LPE > 1) {
+                        atomicOr(&rowm[((code >> 5) + PADR) * 32], 1u << i);
+                        atomicOr(&colm[((code & 31u) + PADR) * 32], 1u << i);
+                    } else {
+                        rowm[((code >> 5) + PADR) * 32] |= 1u << i;
+                        colm[((code & 31u) + PADR) * 32] |= 1u << i;
+                    }
                 }
             }
-            uint32_t coloc_any = 0, wf_alive = 0;
-            bool dl_any = false, ll_any = false;
+            __syncwarp();
+            uint32_t coloc_any = 0, wf_alive = 0, flags_any = 0;   // flags_any: bit 0 deadlock, bit 1 livelock participant set found
             const uint32_t intent_m = allN & ~reached_m;  // ENV:619-621: only agents that have not (sticky-)reached press
-            for (int i = 0; i < N; ++i) {
-                if (!ok) break;
+            for (uint32_t om = ok ? own_m : 0u; om;) {
+                const int i = __ffs(om) - 1;
+                om &= om - 1;
                 const uint32_t bit = 1u << i;
-                const uint32_t rv = rec[i * 32];
+                const uint32_t rv = rec[i * EPW];
                 const uint32_t code = rv & REC_CODE;
                 const int r = (int)(code >> 5), c = (int)(code & 31u);
-                const uint2 *prow_ = &board[(r + PADR) * 32], *pcol_ = &board[(c + PADR) * 32];
-                const uint32_t here = prow_->x & pcol_->y;   // agents on my cell (me included)
+                const uint32_t *prow_ = &rowm[(r + PADR) * 32], *pcol_ = &colm[(c + PADR) * 32];
+                const uint32_t here = *prow_ & *pcol_;   // agents on my cell (me included)
                 if (here & ~bit) coloc_any |= bit;
                 // ENV:389-438 neighbours within Manhattan distance `nearby`, via the row / column masks
                 if (p.lock_enabled && !(ongoal_m & bit)) {
                     uint32_t nb = 0;
                     if (p.nearby == 2) {
-                        const uint32_t c0 = pcol_->y;
-                        const uint32_t c1 = c0 | pcol_[-32].y | pcol_[32].y;
-                        const uint32_t c2 = c1 | pcol_[-64].y | pcol_[64].y;
-                        nb = (prow_->x & c2) | ((prow_[-32].x | prow_[32].x) & c1) | ((prow_[-64].x | prow_[64].x) & c0);
+                        const uint32_t c0 = *pcol_;
+                        const uint32_t c1 = c0 | pcol_[-32] | pcol_[32];
+                        const uint32_t c2 = c1 | pcol_[-64] | pcol_[64];
+                        nb = (*prow_ & c2) | ((prow_[-32] | prow_[32]) & c1) | ((prow_[-64] | prow_[64]) & c0);
                     } else {
                         uint32_t u = 0;
                         for (int w = 0; w <= p.nearby; ++w) {
                             const int dd = p.nearby - w;
-                            if (c - w >= 0) u |= pcol_[-w * 32].y;
-                            if (c + w < C) u |= pcol_[w * 32].y;
+                            if (c - w >= 0) u |= pcol_[-w * 32];
+                            if (c + w < C) u |= pcol_[w * 32];
                             uint32_t rm = 0;
-                            if (r - dd >= 0) rm |= prow_[-dd * 32].x;
-                            if (r + dd < R) rm |= prow_[dd * 32].x;
+                            if (r - dd >= 0) rm |= prow_[-dd * 32];
+                            if (r + dd < R) rm |= prow_[dd * 32];
                             nb |= rm & u;
                         }
                     }
                     nb &= ~here;
                     if (__popc(nb) >= p.min_nb) {
                         const uint32_t P = nb | bit;
-                        if (!(P & Gd) && !(P & Md) && (P & Fd)) dl_any = true;
+                        if (!(P & Gd) && !(P & Md) && (P & Fd)) flags_any |= 1u;
                         if (!(P & Gl) && (P & Ml)) {
                             uint32_t rest = nb;
                             int red = (int)rv >> 16;
                             while (rest) {
                                 const int a = __ffs(rest) - 1;
                                 rest &= rest - 1;
-                                red += (int)rec[a * 32] >> 16;
+                                red += (int)rec[a * EPW] >> 16;
                             }
-                            if (red <= p.eps_floor) ll_any = true;
+                            if (red <= p.eps_floor) flags_any |= 2u;
                         }
                     }
                 }
@@ -465,16 +606,22 @@ __global__ void __launch_bounds__(448, 1) mapf_step_env_kernel(const KParams p, 
                 if (!(moved_m & bit)) {
                     owner = 0;
                     if (!(rv & 0x4000u)) {
-                        const uint32_t tcode = code + (uint32_t)(int)(int8_t)__byte_perm(0x2001E000u, 0x000000FFu, (rv >> 11) & 7u);
-                        owner = board[((tcode >> 5) + PADR) * 32].x & board[((tcode & 31u) + PADR) * 32].y & ~bit;
+                        const uint32_t tcode = code + (uint32_t)action_delta((rv >> 11) & 7u);
+                        owner = rowm[((tcode >> 5) + PADR) * 32] & colm[((tcode & 31u) + PADR) * 32] & ~bit;
                     }
                 }
                 if (intent_m & bit) blocking_m |= owner;   // ENV:609-623 (filtered below)
                 if ((failed_m & bit) && owner) {   // wait-for edge i -> owner (kept in the action bits of the record)
-                    rec[i * 32] = (rv & ~0xF800u) | ((uint32_t)(31 - __clz(owner)) << 11);
+                    rec[i * EPW] = (rv & ~0xF800u) | ((uint32_t)(31 - __clz(owner)) << 11);
                     wf_alive |= bit;
                 }
             }
+            if (LPE > 1) {
+                coloc_any = group_or<LPE>(coloc_any); wf_alive = group_or<LPE>(wf_alive); flags_any = group_or<LPE>(flags_any);
+                blocking_m = group_or<LPE>(blocking_m);
+                __syncwarp();
+            }
+            const bool dl_any = flags_any & 1u, ll_any = (flags_any & 2u) != 0;
             blocking_m &= reached_m & ~moved_m;
             // wait-for cycles: strip agents whose target is gone or that nobody waits for, until stable
             if (__any_sync(full, wf_alive != 0)) {
@@ -484,7 +631,7 @@ __global__ void __launch_bounds__(448, 1) mapf_step_env_kernel(const KParams p, 
                     while (rest) {
                         const int i = __ffs(rest) - 1;
                         rest &= rest - 1;
-                        const uint32_t t = (rec[i * 32] >> 11) & 31u;
+                        const uint32_t t = (rec[i * EPW] >> 11) & 31u;
                         if ((alive >> t) & 1u) { keep |= 1u << i; targets |= 1u << t; }
                     }
                     keep &= targets;
@@ -520,7 +667,8 @@ __global__ void __launch_bounds__(448, 1) mapf_step_env_kernel(const KParams p, 
             }
             done = ok && (terminated || truncated);
             int rsum = __popc(gstep_m) + 2 * __popc(bonus_m) - 2 * __popc(penalty_m);
-            for (int q = 0; q < NQ; ++q) {
+            uint32_t coloc_pairs2 = 0;   // 2 * (co-located others), summed over my agents
+            for (int q = sub; q < NQ; q += LPE) {
                 const int i0 = 4 * q;
                 const uint32_t gs = spread4(gstep_m >> i0), bl = spread4(blocking_m >> i0);
                 const uint32_t asf4 = spread4(moved_m >> i0) * MAPF_ASF_MOVED + spread4(failed_m >> i0) * MAPF_ASF_FAILED_MOVE +
@@ -535,10 +683,10 @@ __global__ void __launch_bounds__(448, 1) mapf_step_env_kernel(const KParams p, 
                 for (int k = 0; k < 4; ++k) {
                     int rx2 = (int)((pos4 >> (8 * k)) & 0xFFu) - (int)((neg4 >> (8 * k)) & 0xFFu);
                     if ((coloc_any >> (i0 + k)) & 1u) {   // ENV:658-666, -1 per co-located pair member (injected states only)
-                        const uint32_t code = rec[(i0 + k) * 32] & REC_CODE;
-                        const int others = __popc(board[((code >> 5) + PADR) * 32].x & board[((code & 31u) + PADR) * 32].y) - 1;
+                        const uint32_t code = rec[(i0 + k) * EPW] & REC_CODE;
+                        const int others = __popc(rowm[((code >> 5) + PADR) * 32] & colm[((code & 31u) + PADR) * 32]) - 1;
                         rx2 -= 2 * others;
-                        rsum -= 2 * others;
+                        coloc_pairs2 += 2u * (uint32_t)others;
                     }
                     rw[k] = 0.5f * (float)rx2;
                 }
@@ -554,9 +702,16 @@ __global__ void __launch_bounds__(448, 1) mapf_step_env_kernel(const KParams p, 
                     stq8<VEC>(p.agent_flags, ab + i0, i0, N, true, af4);
                 }
             }
+            if (__any_sync(full, coloc_any != 0)) {
+                if (LPE > 1) {   // sum over the env's lanes (values < 2^16)
+#pragma unroll
+                    for (int s = 1; s < LPE; s <<= 1) coloc_pairs2 += __shfl_xor_sync(full, coloc_pairs2, s);
+                }
+                rsum -= (int)coloc_pairs2;
+            }
             ep_return_x2 += rsum;
             const int n_comp = __popc(completed_m), n_reach = __popc(reached_m);
-            if (ok) {
+            if (ok && sub == 0) {
                 if (p.o_info) {  // integer sources of info["__all__"], ENV:639-656
                     int4 *io = p.o_info + (size_t)env * 4;
                     io[0] = make_int4(arrivals, p.lifelong ? goals_total : n_reach, blocking_step, blocking_total);
@@ -574,7 +729,7 @@ __global__ void __launch_bounds__(448, 1) mapf_step_env_kernel(const KParams p, 
             }
 
             // ------------------------------------------------------------ episode end: metrics, auto-reset
-            if (done) {   // episode-end metric sums, src/trainers/callbacks.py:152,173,335-345
+            if (done && sub == 0) {   // episode-end metric sums, src/trainers/callbacks.py:152,173,335-345
                 double *m = p.env_metrics + (size_t)env * MAPF_METRIC_COUNT;
                 const double gt = p.lifelong ? (double)goals_total : (double)n_reach;  // ENV:630-633
                 m[MAPF_M_EPISODES] += 1.0;
@@ -590,16 +745,23 @@ __global__ void __launch_bounds__(448, 1) mapf_step_env_kernel(const KParams p, 
                 m[MAPF_M_THROUGHPUT_SUM] += gt / (double)(step_count > 1 ? step_count : 1);  // ENV:655
                 m[MAPF_M_COMPLETION_RATIO_SUM] += (double)n_comp / (double)N;                 // ENV:638
                 m[MAPF_M_WFG_CYCLE_STEPS_SUM] += (double)wfg_steps;
-                episodes += 1;
             }
+            if (done) episodes += 1;
             do_reset = done && p.auto_reset;
             if (!__any_sync(full, do_reset)) break;
-            if (do_reset) {   // ENV:440-472 inside the launch (benchmark loop semantics)
-                bool sample = !p.deterministic;
-                const int F = p.num_free[0];
-                if (sample && F < 2 * N) { errs |= MAPF_DEV_ERR_TOO_FEW_CELLS; sample = false; }
-                if (sample) rng_counter += env_draw_layout(board, freebits, p.fw, F, N, p.seed, env_global, rng_counter);
-                for (int q = 0; q < NQ; ++q) {
+            // ENV:440-472 inside the launch (benchmark loop semantics)
+            bool sample = do_reset && !p.deterministic;
+            const int F = p.num_free[0];
+            if (sample && F < 2 * N) { errs |= MAPF_DEV_ERR_TOO_FEW_CELLS; sample = false; }
+            __syncwarp();
+            uint32_t rounds = 0;
+            if (sample && sub == 0)   // the drawn cell ids are parked in the (dead) owner masks: starts in rowm, goals in colm
+                rounds = env_draw_layout(rowm, colm, 32, freebits, p.fw, F, N, p.seed, env_global, rng_counter);
+            if (LPE > 1) rounds = group_or<LPE>(rounds);
+            rng_counter += rounds;
+            __syncwarp();
+            if (do_reset) {
+                for (int q = sub; q < NQ; q += LPE) {
                     const int i0 = 4 * q;
                     uint4 stq = make_uint4(0, 0, 0, 0), ggq = stq;
                     const uint4 curp = ldq32<VEC>(p.positions, ab + i0, i0, N, true, 0u);
@@ -612,12 +774,11 @@ __global__ void __launch_bounds__(448, 1) mapf_step_env_kernel(const KParams p, 
                         uint32_t st, gg;
                         if (p.deterministic) { st = qget(detst, k); gg = qget(curg, k); }  // F7
                         else if (sample) {
-                            const uint2 v = board[(i0 + k) * 32];
-                            st = pack_rc((int)v.x / C, (int)v.x % C);
-                            gg = pack_rc((int)v.y / C, (int)v.y % C);
+                            const uint32_t vs = rowm[(i0 + k) * 32], vg = colm[(i0 + k) * 32];
+                            st = pack_rc((int)vs / C, (int)vs % C);
+                            gg = pack_rc((int)vg / C, (int)vg % C);
                         } else { st = qget(curp, k); gg = qget(curg, k); }
                         qset(stq, k, st); qset(ggq, k, gg);
-                        rec[(i0 + k) * 32] = code_of(st);
                     }
                     stq32<VEC>(p.positions, ab + i0, i0, N, true, stq);
                     if (sample) { stq32<VEC>(p.starts, ab + i0, i0, N, true, stq); stq32<VEC>(p.goals, ab + i0, i0, N, true, ggq); }
@@ -628,36 +789,43 @@ __global__ void __launch_bounds__(448, 1) mapf_step_env_kernel(const KParams p, 
                         stq32<VEC>(p.lock_mv, ab + i0, i0, N, true, z);
                         stq32<VEC>(p.lock_fm, ab + i0, i0, N, true, z);
                     }
+                    // records of the new episode: position only
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) if (i0 + k < N) rec[(i0 + k) * EPW] = code_of(qget(stq, k)) | (code_of(qget(ggq, k)) << 16);
                 }
                 step_count = 0; lock_count = 0; lock_head = 0; lock_prev = 0; goals_total = 0; blocking_total = 0;
                 dl_events = ll_events = dl_steps = ll_steps = 0; ep_return_x2 = 0; wfg_steps = 0;
                 bprev_m = 0;
-                // boards of the new layout: first observation of the next episode (final state, no staggering at reset)
-                for (int r = 0; r < E.board_rows; ++r) board[r * 32] = make_uint2(0u, 0u);
+            }
+            __syncwarp();
+            // boards of the new layout: first observation of the next episode (final state, no staggering at reset)
+            for (int r = 0; r < E.board_rows; ++r) occ[r * 32] = 0u;
+            if (sub == 0) for (int r = 0; r < E.board_rows; ++r) goalb[r * EPW] = 0u;
+            __syncwarp();
+            if (do_reset) {
                 for (int i = 0; i < N; ++i) {
-                    const uint32_t pc = rec[i * 32] & REC_CODE;
-                    const uint32_t gc = code_of(p.goals[ab + i]);
-                    board[(pc >> 5) * 32].x |= 1u << (pc & 31u);
-                    board[(gc >> 5) * 32].y |= 1u << (gc & 31u);
+                    const uint32_t rv = rec[i * EPW], pc = rv & REC_CODE, gc = rv >> 16;
+                    occ[(pc >> 5) * 32] |= 1u << (pc & 31u);
+                    if (sub == 0) goalb[(gc >> 5) * EPW] |= 1u << (gc & 31u);
                 }
             }
+            __syncwarp();
             active = do_reset;
         }
 
-        // ---------------------------------------------------------------- the agent walk
+        // ---------------------------------------------------------------- the agent walk (my quads)
         const bool stepmode = round == 0;
         const unsigned act_w = __ballot_sync(full, active);
-        for (int q = 0; q < NQ; ++q) {
+        int qq = 0;
+        for (int q = sub; q < NQ; q += LPE, ++qq) {
             const int i0 = 4 * q;
-            uint32_t cd[4];
+            uint32_t rv4[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) cd[k] = (i0 + k < N) ? (rec[(i0 + k) * 32] & REC_CODE) : 0u;
+            for (int k = 0; k < 4; ++k) rv4[k] = (i0 + k < N) ? rec[(i0 + k) * EPW] : 0u;
             uint4 gq = ldq32<VEC>(p.goals, ab + i0, i0, N, active, 0u);
-            uint32_t act4 = 0;
             uint4 gpq = make_uint4(0, 0, 0, 0), mvq = gpq, fmq = gpq;
             uint2 ringq = make_uint2(0u, 0u);
             if (stepmode) {
-                if (p.actions) act4 = ldq8<VEC>(reinterpret_cast<const uint8_t *>(p.actions), ab + i0, i0, N, ok);
                 const uint32_t fl4 = ldq8<VEC>(p.agent_flags, ab + i0, i0, N, ok);
                 reached_m |= gather4(fl4, 0) << i0;      // MAPF_AF_REACHED
                 completed_m |= gather4(fl4, 1) << i0;    // MAPF_AF_COMPLETED_ONCE
@@ -671,9 +839,8 @@ __global__ void __launch_bounds__(448, 1) mapf_step_env_kernel(const KParams p, 
             }
             uint4 rnd = make_uint4(0, 0, 0, 0);
             if (p.sample_mode) rnd = sample_quad(p.seed, env_global, q, p.sample_counter);
-            uint32_t ds[4] = {0, 0, 0, 0};
+            uint32_t ds[4] = {0, 0, 0, 0}, cd[4] = {0, 0, 0, 0};
             uint32_t masks4 = 0, next4 = 0;
-            bool goal_changed = false;
             float2 gd[4];
             int patch[4];
             uint32_t carry = 0;
@@ -683,57 +850,43 @@ __global__ void __launch_bounds__(448, 1) mapf_step_env_kernel(const KParams p, 
                 patch[k] = -1;
                 if (i0 + k >= N) continue;
                 const uint32_t bit = 1u << (i0 + k);
-                uint32_t code = cd[k];
-                uint32_t gcode = code_of(qget(gq, k));
+                uint32_t code = rv4[k] & REC_CODE;
+                const uint32_t gcode = code_of(qget(gq, k));
                 if (stepmode) {
                     const uint32_t ocode = code;
-                    int a = (int)(int8_t)(act4 >> (8 * k));
-                    if (a < 0 || a > 4) { errs |= MAPF_DEV_ERR_INVALID_ACTION; a = 0; }
-                    // ENV:512-526: target cell, obstacle / bounds from the cell's obstacle window, occupancy from the board
-                    const int d = (int)(int8_t)__byte_perm(0x2001E000u, 0x000000FFu, (uint32_t)a);   // {0,-32,+1,+32,-1}
-                    const uint32_t nbi = __byte_perm((uint32_t)CTR | ((uint32_t)(CTR - V) << 8) | ((uint32_t)(CTR + 1) << 16) |
-                                                     ((uint32_t)(CTR + V) << 24), (uint32_t)(CTR - 1), (uint32_t)a) & 0xFFu;
-                    const bool tblocked = ((uint32_t)lut[code] >> nbi) & 1u;
-                    const uint32_t tcode = code + (uint32_t)d;
-                    const bool wants = ok && a != 0 && !tblocked;
+                    const uint32_t a = (rv4[k] >> 11) & 7u;
+                    // ENV:512-526: target cell; obstacle / bounds were resolved by the pre-pass, occupancy comes from the board
+                    const uint32_t tcode = code + (uint32_t)action_delta(a);
+                    const bool wants = ok && a != 0 && !(rv4[k] & 0x4000u);
                     bool moves = false;
                     if (wants) {
-                        uint2 *trow = &board[(tcode >> 5) * 32];
+                        uint32_t *trow = &occ[(tcode >> 5) * 32];
                         const uint32_t tb = 1u << (tcode & 31u);
-                        if (!(trow->x & tb)) {
+                        if (!(*trow & tb)) {
                             moves = true;
-                            board[(code >> 5) * 32].x &= ~(1u << (code & 31u));
-                            trow->x |= tb;
+                            occ[(code >> 5) * 32] &= ~(1u << (code & 31u));
+                            *trow |= tb;
                         }
                     }
                     const bool failed = ok && a != 0 && !moves;  // ENV:583
-                    if (moves) { moved_m |= bit; code = tcode; cd[k] = tcode; }
+                    if (moves) { moved_m |= bit; code = tcode; }
                     if (failed) failed_m |= bit;
-                    // ENV:538-563
-                    const uint32_t gcode_before = gcode;
+                    // ENV:538-563.  A lifelong arrival gets its new goal after the walk (round 1), in agent order.
                     const bool on_goal = ok && code == gcode;
-                    bool gstep = false;
+                    bool gstep = false, cur_on_goal = on_goal;
                     if (!p.lifelong) {
                         if (on_goal && !(reached_m & bit)) { reached_m |= bit; completed_m |= bit; gstep = true; }
                     } else if (on_goal) {
                         gstep = true;
                         completed_m |= bit; reached_m &= ~bit;
-                        reassigned = true;
-                        const uint2 ng = env_assign_new_goal(board, freerow, R, p.goal_override, p.goal_rank, ab + i0 + k,
-                                                             i0 + k, gcode, p.seed, env_global, rng_counter);
-                        gcode = ng.x;
-                        rng_counter += ng.y & 1u;
-                        if (ng.y & 2u) errs |= MAPF_DEV_ERR_NO_GOAL_CELL;
-                        qset(gq, k, packed_of(gcode));
-                        goal_changed = true;
+                        cur_on_goal = false;   // ENV:555
                     }
                     if (gstep) gstep_m |= bit;
-                    const bool cur_on_goal = ok && code == gcode;  // ENV:555: false after a reassignment
                     if (cur_on_goal) ongoal_m |= bit;
                     // ENV:581-594 lock history
                     uint32_t delta16 = 0;
                     if (p.lock_enabled) {
-                        const bool prev_on_goal = p.lifelong ? false : (ocode == gcode_before);
+                        const bool prev_on_goal = p.lifelong ? false : (ocode == gcode);
                         const bool gp = p.lifelong ? gstep : (!prev_on_goal && cur_on_goal);
                         const uint32_t g2 = (qget(gpq, k) << 1) | (gp ? 1u : 0u);
                         const uint32_t m2 = (qget(mvq, k) << 1) | (moves ? 1u : 0u);
@@ -750,26 +903,28 @@ __global__ void __launch_bounds__(448, 1) mapf_step_env_kernel(const KParams p, 
                         ds[k] = (uint32_t)dist;
                         if (use_ring && ok) delta16 = (uint32_t)((int)(int16_t)hget(ringq, k) - dist) << 16;
                     }
-                    rec[(i0 + k) * 32] = code | ((uint32_t)a << 11) | (tblocked ? 0x4000u : 0u) | delta16;
+                    rec[(i0 + k) * EPW] = code | (rv4[k] & 0x7800u) | delta16;
                 }
+                cd[k] = code;
                 // ---------------------------------------------------- observation of agent i on the boards as they are now
                 const int r = (int)(code >> 5), c = (int)(code & 31u);
                 const WB obst = lut[code];
                 const int sa = c > SR ? c - SR : 0, sb2 = (c < SR ? SR - c : 0) + 2;   // window columns start at c - SR
-                const uint2 *brow = &board[(r - SR) * 32];
+                const uint32_t *orow = &occ[(r - SR) * 32], *grow = &goalb[(r - SR) * EPW];
                 uint32_t acc[(4 * (V2 + 3) + 31) / 32 + 1];
 #pragma unroll
                 for (int j = 0; j < (int)(sizeof(acc) / sizeof(acc[0])); ++j) acc[j] = 0;
                 uint32_t blk_up = 0, blk_mid = 0, blk_dn = 0;
 #pragma unroll
                 for (int wr = 0; wr < V; ++wr) {
-                    const uint2 b = brow[wr * 32];  // rows outside the map read neighbouring shared memory: masked by the obstacle plane
+                    // rows outside the map read neighbouring shared memory: masked by the obstacle plane
+                    const uint32_t bx = orow[wr * 32], by = grow[wr * EPW];
                     const uint32_t o4 = (wr * V >= 2 ? (uint32_t)(obst >> (wr * V - 2)) : (uint32_t)(obst << 2)) & M4;
                     const uint32_t MC = (wr == SR) ? (M4 & ~(4u << SR)) : M4;   // my own cell is not "another agent" (ENV:737)
-                    const uint32_t occ4 = ((b.x >> sa) << sb2) & MC;
+                    const uint32_t occ4 = ((bx >> sa) << sb2) & MC;
                     const uint32_t agent4 = occ4 & ~o4;
                     const uint32_t blk4 = occ4 | o4;
-                    const uint32_t g4 = ((b.y >> sa) << sb2) & M4 & ~blk4;
+                    const uint32_t g4 = ((by >> sa) << sb2) & M4 & ~blk4;
                     if (wr == SR - 1) blk_up = blk4;
                     if (wr == SR) blk_mid = blk4;
                     if (wr == SR + 1) blk_dn = blk4;
@@ -790,7 +945,7 @@ __global__ void __launch_bounds__(448, 1) mapf_step_env_kernel(const KParams p, 
                     const int dr = (int)(gcode >> 5) - r + SR, dc = (int)(gcode & 31u) - c + SR;
                     if ((unsigned)dr < (unsigned)V && (unsigned)dc < (unsigned)V) {
                         const int ci = dr * V + dc;
-                        const bool occ_other = (ci != CTR) && ((board[(gcode >> 5) * 32].x >> (gcode & 31u)) & 1u);
+                        const bool occ_other = (ci != CTR) && ((occ[(gcode >> 5) * 32] >> (gcode & 31u)) & 1u);
                         if (!((obst >> ci) & 1) && !occ_other) patch[k] = V2 * k + ci;
                     }
                 }
@@ -823,7 +978,6 @@ __global__ void __launch_bounds__(448, 1) mapf_step_env_kernel(const KParams p, 
             if (stepmode) {
                 stq32<VEC>(p.positions, ab + i0, i0, N, ok,
                            make_uint4(packed_of(cd[0]), packed_of(cd[1]), packed_of(cd[2]), packed_of(cd[3])));
-                if (goal_changed) stq32<VEC>(p.goals, ab + i0, i0, N, ok, gq);
                 if (p.lock_enabled) {
                     stq32<VEC>(p.lock_gp, ab + i0, i0, N, ok, gpq);
                     stq32<VEC>(p.lock_mv, ab + i0, i0, N, ok, mvq);
@@ -862,15 +1016,18 @@ __global__ void __launch_bounds__(448, 1) mapf_step_env_kernel(const KParams p, 
                 if (p.o_blocking_prev) stq8<VEC>(p.o_blocking_prev, ab + i0, i0, N, true, spread4(bprev_m >> i0));
                 if (p.sample_mode) stq8<VEC>(reinterpret_cast<uint8_t *>(p.o_next_actions), ab + i0, i0, N, true, next4);
             }
-            // ------------------------------------------------ coalesced flush of the quad's byte channels
+            // ------------------------------------------------ coalesced flush of the stage rows (one per lane)
+            // row `e` holds quad (e % LPE) + qq * LPE of env env0 + e / LPE: agent index (env0 * N + 4 * qq * LPE) + e * AST
             __syncwarp();
             if (VEC) {
+                const size_t agent0 = env0 * N + (size_t)(4 * qq * LPE);
+                const uint32_t AST = (LPE == 1) ? (uint32_t)N : 4u;   // agents between consecutive stage rows (N == 4 * LPE when LPE > 1)
                 for (int w = lane; w < OBS_W + 5; w += 32) {
                     const bool is_obs = w < OBS_W;
-                    unsigned char *gp = is_obs ? (p.o_local_obs ? p.o_local_obs + (env0 * N + i0) * V2 + 4 * w : nullptr)
+                    unsigned char *gp = is_obs ? (p.o_local_obs ? p.o_local_obs + agent0 * V2 + 4 * w : nullptr)
                                                : (p.o_action_mask ? reinterpret_cast<unsigned char *>(p.o_action_mask) +
-                                                                        (env0 * N + i0) * 5 + 4 * (w - OBS_W) : nullptr);
-                    const uint32_t gstride = (uint32_t)(is_obs ? N * V2 : N * 5);
+                                                                        agent0 * 5 + 4 * (w - OBS_W) : nullptr);
+                    const uint32_t gstride = AST * (uint32_t)(is_obs ? V2 : 5);
                     const uint32_t *src = stage_w + w;
                     if (gp) {
                         if (act_w == full) {
@@ -885,7 +1042,7 @@ __global__ void __launch_bounds__(448, 1) mapf_step_env_kernel(const KParams p, 
                         }
                     }
                 }
-            } else {
+            } else {   // LPE == 1 only
                 const int na = (N - i0) < 4 ? (N - i0) : 4;
                 for (int e = 0; e < 32; ++e) {
                     if (!((act_w >> e) & 1u)) continue;
@@ -902,20 +1059,15 @@ __global__ void __launch_bounds__(448, 1) mapf_step_env_kernel(const KParams p, 
             }
             __syncwarp();
         }
-        if (stepmode) {
-            if (p.lock_enabled) lock_head = slot_next;
-            arrivals = __popc(gstep_m);
-            goals_total += arrivals;  // lifelong: every arrival; else first arrivals (ENV:545,562)
-        }
     }
 
     // ---------------------------------------------------------------- env words write-back
-    if (ok) {
-        int4 *ew = p.env_words + (size_t)env * 4;
-        ew[0] = make_int4(step_count, lock_count, lock_prev, goals_total);
-        ew[1] = make_int4(blocking_total, dl_events, ll_events, dl_steps);
-        ew[2] = make_int4(ll_steps, (int)rng_counter, ep_return_x2, wfg_steps);
-        ew[3] = make_int4(episodes, lock_head, w3.z, w3.w);
+    if (ok && sub == 0) {
+        int4 *ew4 = p.env_words + (size_t)env * 4;
+        ew4[0] = make_int4(step_count, lock_count, lock_prev, goals_total);
+        ew4[1] = make_int4(blocking_total, dl_events, ll_events, dl_steps);
+        ew4[2] = make_int4(ll_steps, (int)rng_counter, ep_return_x2, wfg_steps);
+        ew4[3] = make_int4(episodes, lock_head, w3.z, w3.w);
     }
     __syncwarp();
     }  // tile loop
