@@ -116,3 +116,33 @@ def test_small_maps_and_lock_window_variants():
         cfg = {"env_name": name, "num_agents": n, "sensor_range": 2, "steps_per_episode": 60, "lifelong_mapf": True,
                "deadlock_window_steps": 2, "livelock_window_steps": 4, "lock_nearby_manhattan": 3, "seed": 5}
         run_pair(cfg, 200, 150, masked=False)
+
+
+def test_sliced_host_step_equals_device_step(monkeypatch):
+    """mapf_step_host pipelines big batches in slices over two streams (H2D / kernel / D2H overlap); slicing must not
+    change anything: same outputs as one device-side step of an identical env, for 1, 3 and the default 2 slices."""
+    import ctypes as C
+
+    import torch
+
+    B = 8192 + 64
+    cfg = c3(steps_per_episode=12)
+    for slices in ("1", "3", None):
+        if slices is None:
+            monkeypatch.delenv("MAPF_HOST_SLICES", raising=False)
+        else:
+            monkeypatch.setenv("MAPF_HOST_SLICES", slices)
+        a, b = make(cfg, B, "lane"), make(cfg, B, "lane")
+        a.reset()
+        b.reset()
+        host = {k: torch.empty_like(v, device="cpu").pin_memory() for k, v in b.out.items()}
+        cout = nat.MapfOutputs(**{k: host[k].data_ptr() for k in nat.OUTPUT_FIELDS})
+        gen = torch.Generator().manual_seed(5)
+        for s in range(30):
+            acts = torch.randint(0, 5, (B, a.N), dtype=torch.int8, generator=gen)
+            oa = a.step(acts.cuda(), auto_reset=True)
+            nat.check(nat.lib().mapf_step_host(b._h, C.c_void_p(acts.pin_memory().data_ptr()), None, None, C.byref(cout), 1))
+            for k in OUT_KEYS:
+                assert torch.equal(getattr(oa, k).cpu(), host[k]), f"slices={slices} step {s}: {k}"
+        for k in a.state:
+            assert torch.equal(a.state[k], b.state[k]), f"slices={slices}: state {k}"
