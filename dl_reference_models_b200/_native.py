@@ -16,7 +16,7 @@ PKG = Path(__file__).resolve().parent
 REPO = PKG.parent
 CSRC = PKG / "csrc"
 LIB_PATH = Path(os.environ.get("MAPF_B200_LIB", PKG / "libmapf_b200.so"))
-SOURCES = (CSRC / "mapf_b200.cu", CSRC / "mapf_kernels.cuh", CSRC / "mapf_env_kernel.cuh",
+SOURCES = (CSRC / "mapf_b200.cu", CSRC / "mapf_kernels.cuh", CSRC / "mapf_env_kernel.cuh", CSRC / "mapf_cte_kernel.cuh",
            REPO / "include" / "mapf_b200.h")
 
 MAX_AGENTS = 32
@@ -78,6 +78,18 @@ class MapfState(C.Structure):
 
 class MapfOutputs(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in OUTPUT_FIELDS]
+
+
+class MapfCteArgs(C.Structure):
+    """mapf_cte_args of include/mapf_b200.h (single-agent / CTE view)."""
+
+    _fields_ = [
+        ("num_envs", C.c_int32), ("num_agents", C.c_int32), ("rows", C.c_int32), ("cols", C.c_int32),
+        ("steps_per_episode", C.c_int32), ("reserved", C.c_int32),
+        ("blocking_penalty", C.c_double), ("move_after_goal_penalty", C.c_double),
+    ] + [(k, C.c_void_p) for k in (
+        "grid", "positions", "goals", "reached_once", "step_count", "blocking_total", "actions", "obs_grid",
+        "action_mask", "flat_obs", "reward", "terminated", "truncated", "info", "err_bits", "reset_mask")]
 
 
 class MapfError(RuntimeError):
@@ -159,6 +171,8 @@ def lib():
     L.mapf_launch_count.argtypes = [vp]
     L.mapf_launch_count.restype = i64
     L.mapf_step_kernel_kind.argtypes = [vp]
+    L.mapf_cte_step.argtypes = [C.POINTER(MapfCteArgs), vp]
+    L.mapf_cte_reset.argtypes = [C.POINTER(MapfCteArgs), vp]
     for name in EXPORTS:
         if name not in ("mapf_version", "mapf_last_error", "mapf_launch_count"):
             getattr(L, name).restype = C.c_int
@@ -173,7 +187,7 @@ EXPORTS = (
     "mapf_observe", "mapf_observe_host",
     "mapf_flat_obs_dim", "mapf_pack_flat_obs", "mapf_sample_masked_actions",
     "mapf_sample_random_actions", "mapf_set_fused_sampler", "mapf_metrics_reduce", "mapf_poll_errors", "mapf_launch_count",
-    "mapf_step_kernel_kind",
+    "mapf_step_kernel_kind", "mapf_cte_step", "mapf_cte_reset",
 )
 
 

@@ -3,6 +3,7 @@
 // state/IO buffer management.  There is no CPU implementation of the transition in here: every
 // entry point that computes launches a kernel, and fails with MAPF_ERR_CUDA if it cannot.
 #include "mapf_env_kernel.cuh"
+#include "mapf_cte_kernel.cuh"
 
 #include <cstdarg>
 #include <cstdio>
@@ -860,6 +861,27 @@ int mapf_poll_errors(mapf_handle *h, uint32_t *bits, void *stream) {
     }
     return MAPF_OK;
 }
+
+static int cte_launch(const mapf_cte_args *a, int mode, void *stream) {
+    if (!a) return fail(MAPF_ERR_INVALID_ARG, "null argument");
+    if (a->num_envs < 1 || a->num_agents < 1 || a->num_agents > MAPF_MAX_AGENTS || a->rows < 1 || a->cols < 1 ||
+        a->rows > MAPF_MAX_DIM || a->cols > MAPF_MAX_DIM)
+        return fail(MAPF_ERR_UNSUPPORTED, "cte: num_envs=%d num_agents=%d map %dx%d outside the supported range",
+                    a->num_envs, a->num_agents, a->rows, a->cols);
+    if (!a->grid || !a->positions || !a->goals || !a->reached_once || !a->step_count || !a->blocking_total || !a->err_bits)
+        return fail(MAPF_ERR_INVALID_ARG, "cte: grid / state / err_bits pointers are required");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
+        return fail(MAPF_ERR_CUDA, "no CUDA device (libmapf_b200 has no CPU fallback)");
+    const int threads = 128;
+    const unsigned grid = (unsigned)((a->num_envs + threads - 1) / threads);
+    mapf::mapf_cte_kernel<<<grid, threads, 0, static_cast<cudaStream_t>(stream)>>>(*a, mode);
+    CUDA_TRY(cudaGetLastError());
+    return MAPF_OK;
+}
+
+int mapf_cte_step(const mapf_cte_args *a, void *stream) { return cte_launch(a, 0, stream); }
+int mapf_cte_reset(const mapf_cte_args *a, void *stream) { return cte_launch(a, 1, stream); }
 
 int64_t mapf_launch_count(const mapf_handle *h) { return h ? h->launches : 0; }
 

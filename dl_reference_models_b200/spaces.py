@@ -81,6 +81,29 @@ except Exception:  # gymnasium absent: self-contained descriptors
             return f"MultiBinary({self.n})"
 
 try:  # pragma: no cover - depends on the installation
+    from gymnasium.spaces import MultiDiscrete  # type: ignore
+except Exception:
+    class MultiDiscrete:  # joint action space of the single-agent (CTE) view
+        def __init__(self, nvec):
+            self.nvec = np.asarray(nvec, dtype=np.int64)
+            self.shape = self.nvec.shape
+            self.dtype = np.dtype(np.int64)
+
+        def contains(self, x) -> bool:
+            x = np.asarray(x)
+            return bool(x.shape == self.shape and np.all(x >= 0) and np.all(x < self.nvec))
+
+        def __contains__(self, x):
+            return self.contains(x)
+
+        def sample(self, rng=None):
+            rng = rng or np.random.default_rng()
+            return rng.integers(0, self.nvec).astype(self.dtype)
+
+        def __repr__(self):
+            return f"MultiDiscrete({self.nvec.tolist()})"
+
+try:  # pragma: no cover - depends on the installation
     from ray.rllib.env.multi_agent_env import MultiAgentEnv  # type: ignore
 
     HAVE_RLLIB = True

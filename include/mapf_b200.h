@@ -285,6 +285,42 @@ int64_t mapf_launch_count(const mapf_handle *h);
  * 2 = env-per-thread (one env per thread, bitboards in shared memory).  Same results either way. */
 int mapf_step_kernel_kind(const mapf_handle *h);
 
+/* ------------------------------------------------------------------------------------------------
+ * Single-agent ("CTE") view of the same grid world: src/environments/reference_model_single_agent.py
+ * ("CTE:line") -- one joint action, one full-grid observation, one scalar reward.  Stateless entry points:
+ * every buffer is a caller-owned DEVICE pointer; outputs may be NULL.
+ *   ReferenceModel.step(action)   CTE:237-346 -> mapf_cte_step
+ *   ReferenceModel.reset()        CTE:218-235 -> mapf_cte_reset (the caller installs positions / goals first:
+ *                                                deterministic table CTE:225 or its own draw CTE:155-185)
+ *   get_obs / get_action_mask     CTE:428-441, 466-489 -> obs_grid / action_mask / flat_obs outputs
+ */
+typedef struct mapf_cte_args {
+    int32_t num_envs, num_agents, rows, cols; /* B, N <= 32, map shape */
+    int32_t steps_per_episode;                /* CTE:85 */
+    int32_t reserved;
+    double blocking_penalty;                  /* CTE:92 */
+    double move_after_goal_penalty;           /* CTE:93 */
+    const uint8_t *grid;        /* [R,C] 0 free / 1 obstacle, shared by all envs */
+    int16_t *positions;         /* [B,N,2] state */
+    const int16_t *goals;       /* [B,N,2] */
+    uint8_t *reached_once;      /* [B,N]  goal_reached_once, CTE:91 */
+    int32_t *step_count;        /* [B] */
+    double *blocking_total;     /* [B]    _episode_blocking_count, CTE:94 */
+    const int8_t *actions;      /* [B,N]  step input (NULL = all NO_OP) */
+    uint8_t *obs_grid;          /* [B,R,C] 1 obstacle, 2i+2 agent i, 2i+3 goal of agent i */
+    int8_t *action_mask;        /* [B,5N] */
+    float *flat_obs;            /* [B,R*C+5N] CTE:187-196 */
+    double *reward;             /* [B] the Python float of the reference, bit for bit */
+    uint8_t *terminated;        /* [B] */
+    uint8_t *truncated;         /* [B] */
+    double *info;               /* [B,4] blocking_count_step, goals_reached_step, goals_reached_total, blocking_count_total */
+    uint32_t *err_bits;         /* [1] MAPF_DEV_ERR_INVALID_ACTION (required) */
+    const uint8_t *reset_mask;  /* mapf_cte_reset: [B] or NULL = every env */
+} mapf_cte_args;
+
+int mapf_cte_step(const mapf_cte_args *args, void *stream);
+int mapf_cte_reset(const mapf_cte_args *args, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

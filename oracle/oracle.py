@@ -77,12 +77,11 @@ class _Outputs(C.Structure):
 
 def build(force: bool = False) -> Path:
     """Compile the oracle with gcc (a few hundred ms)."""
-    src = _HERE / "mapf_oracle.c"
-    hdr = _HERE / "mapf_oracle.h"
+    srcs = [_HERE / "mapf_oracle.c", _HERE / "mapf_oracle.h", _HERE / "cte_oracle.c"]
     if (
         force
         or not _SO.exists()
-        or _SO.stat().st_mtime < max(src.stat().st_mtime, hdr.stat().st_mtime)
+        or _SO.stat().st_mtime < max(f.stat().st_mtime for f in srcs)
     ):
         subprocess.run(["make", "-C", str(_HERE), "-s", "-B"], check=True)
     return _SO
