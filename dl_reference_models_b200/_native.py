@@ -171,6 +171,7 @@ def lib():
     L.mapf_launch_count.argtypes = [vp]
     L.mapf_launch_count.restype = i64
     L.mapf_step_kernel_kind.argtypes = [vp]
+    L.mapf_occupancy_accumulate.argtypes = [vp, vp, vp, vp]
     L.mapf_cte_step.argtypes = [C.POINTER(MapfCteArgs), vp]
     L.mapf_cte_reset.argtypes = [C.POINTER(MapfCteArgs), vp]
     for name in EXPORTS:
@@ -187,7 +188,7 @@ EXPORTS = (
     "mapf_observe", "mapf_observe_host",
     "mapf_flat_obs_dim", "mapf_pack_flat_obs", "mapf_sample_masked_actions",
     "mapf_sample_random_actions", "mapf_set_fused_sampler", "mapf_metrics_reduce", "mapf_poll_errors", "mapf_launch_count",
-    "mapf_step_kernel_kind", "mapf_cte_step", "mapf_cte_reset",
+    "mapf_step_kernel_kind", "mapf_cte_step", "mapf_cte_reset", "mapf_occupancy_accumulate",
 )
 
 

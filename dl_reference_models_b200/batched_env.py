@@ -246,6 +246,14 @@ class BatchedMapfEnv:
         nat.check(self._lib.mapf_metrics_reduce(self._h, self._ptr(self._metrics_dev), self._stream()))
         return self._metrics_dev
 
+    def accumulate_occupancy(self, counts: torch.Tensor, active: torch.Tensor | None = None) -> torch.Tensor:
+        """counts[r, c] (int64 [R,C] on this device) += agents standing on (r, c) over the envs with ``active`` != 0
+        (uint8 [B], None = all): the occupancy heat-map of the reference's evaluator (main.py:153-155, 265-267)."""
+        assert counts.dtype == torch.int64 and counts.is_contiguous() and tuple(counts.shape) == tuple(self.grid.shape[-2:])
+        a = None if active is None else active.to(device=self.device, dtype=torch.uint8).contiguous()
+        nat.check(self._lib.mapf_occupancy_accumulate(self._h, self._ptr(a), self._ptr(counts), self._stream()))
+        return counts
+
     def poll_errors(self) -> int:
         bits = C.c_uint32(0)
         nat.check(self._lib.mapf_poll_errors(self._h, C.byref(bits), self._stream()))

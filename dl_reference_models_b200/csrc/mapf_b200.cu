@@ -849,6 +849,26 @@ int mapf_metrics_reduce(mapf_handle *h, double *out_device, void *stream) {
     return MAPF_OK;
 }
 
+int mapf_occupancy_accumulate(mapf_handle *h, const uint8_t *active, uint64_t *counts, void *stream) {
+    int rc = check_ready(h);
+    if (rc) return rc;
+    if (!counts) return fail(MAPF_ERR_INVALID_ARG, "null argument");
+    DeviceGuard guard(h->cfg.device);
+    const long long BN = (long long)h->cfg.num_envs * h->cfg.num_agents;
+    const int cells = h->cfg.rows * h->cfg.cols;
+    const int use_smem = cells * 4 <= 48 * 1024;
+    const int threads = 256;
+    long long blocks = (BN + threads * 8 - 1) / (threads * 8);
+    if (blocks > 1184) blocks = 1184;
+    if (blocks < 1) blocks = 1;
+    mapf::mapf_occupancy_kernel<<<(unsigned)blocks, threads, use_smem ? cells * 4 : 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const uint32_t *>(h->st.positions), active, BN, h->cfg.num_agents, h->cfg.rows, h->cfg.cols,
+        reinterpret_cast<unsigned long long *>(counts), use_smem);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    return MAPF_OK;
+}
+
 int mapf_poll_errors(mapf_handle *h, uint32_t *bits, void *stream) {
     if (!h || !bits) return fail(MAPF_ERR_INVALID_ARG, "null argument");
     DeviceGuard guard(h->cfg.device);

@@ -1119,6 +1119,32 @@ __global__ void mapf_sample_actions_kernel(const int8_t *mask, int8_t *actions, 
     actions[idx] = (int8_t)sample_action(seed, env_id_base + env, a, counter, bits);
 }
 
+// Occupancy heat-map of the reference's evaluator (main.py:153-155, 265-267): counts[r, c] += number of agents of
+// the selected envs standing on (r, c).  Integer counts, so the order of the atomics does not matter; a CTA first
+// accumulates in a shared-memory histogram when the map fits.
+__global__ void mapf_occupancy_kernel(const uint32_t *positions, const uint8_t *active, long long BN, int N, int R, int C,
+                                      unsigned long long *counts, int use_smem) {
+    extern __shared__ unsigned int hist[];
+    const int cells = R * C;
+    if (use_smem) {
+        for (int i = threadIdx.x; i < cells; i += blockDim.x) hist[i] = 0u;
+        __syncthreads();
+    }
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < BN; idx += (long long)gridDim.x * blockDim.x) {
+        if (active && !active[idx / N]) continue;
+        const uint32_t p = positions[idx];
+        const int r = prow(p), c = pcol(p);
+        if (r < 0 || r >= R || c < 0 || c >= C) continue;   // main.py:266
+        if (use_smem) atomicAdd(&hist[r * C + c], 1u);
+        else atomicAdd(&counts[r * C + c], 1ull);
+    }
+    if (use_smem) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < cells; i += blockDim.x)
+            if (hist[i]) atomicAdd(&counts[i], (unsigned long long)hist[i]);
+    }
+}
+
 // Deterministic reduction of env_metrics[B,K]: CTA k reduces metric k in a fixed order
 // (strided partial sums, then a shared-memory tree), so the result does not depend on timing.
 __global__ void mapf_metrics_reduce_kernel(const double *env_metrics, int B, double *out) {

@@ -275,6 +275,10 @@ int mapf_set_fused_sampler(mapf_handle *h, int8_t *next_actions, int32_t mode, u
  * device double out[MAPF_METRIC_COUNT] (off the step path; ranks then all-reduce it). */
 int mapf_metrics_reduce(mapf_handle *h, double *out_device, void *stream);
 
+/* Occupancy heat-map of the reference's evaluator (main.py:153-155, 265-267): counts[r*C+c] (device uint64 [R*C]) +=
+ * the number of agents standing on (r, c), over the envs with active[env] != 0 (device uint8 [B], NULL = all). */
+int mapf_occupancy_accumulate(mapf_handle *h, const uint8_t *active, uint64_t *counts, void *stream);
+
 /* OR of MAPF_DEV_ERR_* bits raised by kernels since the last poll (synchronises `stream`). */
 int mapf_poll_errors(mapf_handle *h, uint32_t *bits, void *stream);
 
