@@ -199,9 +199,12 @@ __device__ __forceinline__ void warp_copy_out(uint8_t *dst, const uint8_t *stage
     uintptr_t d = (uintptr_t)dst;
     int phase = (int)(d & 15);
     if (phase == 0 && (nbytes & 15) == 0) {  // the common case: whole 16-byte chunks, aligned
-        const uint4 *s4 = reinterpret_cast<const uint4 *>(stage);
-        uint4 *d4 = reinterpret_cast<uint4 *>(dst);
-        for (int i = lane; i < (nbytes >> 4); i += 32) d4[i] = s4[i];
+        const uint4 *s4 = reinterpret_cast<const uint4 *>(stage) + lane;
+        uint4 *d4 = reinterpret_cast<uint4 *>(dst) + lane;
+        const int n16 = nbytes >> 4;
+        if (lane < n16) d4[0] = s4[0];            // up to 1 KB without a loop (C3: 800 B of windows per warp)
+        if (lane + 32 < n16) d4[32] = s4[32];
+        for (int i = lane + 64; i < n16; i += 32) d4[i - lane] = s4[i - lane];
         return;
     }
     const uint8_t *src = stage + phase;  // src[i] <-> dst[i]
@@ -776,7 +779,7 @@ __global__ void __launch_bounds__(256, MAPF_STEP_MIN_CTAS) mapf_step_kernel(cons
 
     // ---------------------------------------------------------------- wait-for graph (pointer jumping)
     bool wf_cycle = false;
-    {
+    if (__any_sync(full, po.wf_next >= 0)) {   // no edge in the whole warp (the common case with masked actions): no cycle
         int ptr = po.wf_next;  // -1: no outgoing edge
         unsigned reach = ptr >= 0 ? (1u << ptr) : 0u;
 #pragma unroll
