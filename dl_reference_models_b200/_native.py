@@ -16,7 +16,7 @@ PKG = Path(__file__).resolve().parent
 REPO = PKG.parent
 CSRC = PKG / "csrc"
 LIB_PATH = Path(os.environ.get("MAPF_B200_LIB", PKG / "libmapf_b200.so"))
-SOURCES = (CSRC / "mapf_b200.cu", CSRC / "mapf_kernels.cuh", CSRC / "mapf_env_kernel.cuh", CSRC / "mapf_cte_kernel.cuh",
+SOURCES = (CSRC / "mapf_b200.cu", CSRC / "mapf_kernels.cuh", CSRC / "mapf_env_kernel.cuh", CSRC / "mapf_cte_kernel.cuh", CSRC / "mapf_policy_kernel.cuh",
            REPO / "include" / "mapf_b200.h")
 
 MAX_AGENTS = 32
@@ -90,6 +90,18 @@ class MapfCteArgs(C.Structure):
     ] + [(k, C.c_void_p) for k in (
         "grid", "positions", "goals", "reached_once", "step_count", "blocking_total", "actions", "obs_grid",
         "action_mask", "flat_obs", "reward", "terminated", "truncated", "info", "err_bits", "reset_mask")]
+
+
+class MapfPolicyArgs(C.Structure):
+    """mapf_policy_args of include/mapf_b200.h (fused action-mask MLP + sampler)."""
+
+    _fields_ = [
+        ("num_envs", C.c_int32), ("num_agents", C.c_int32), ("v2", C.c_int32), ("feature_dim", C.c_int32),
+        ("no_masking", C.c_int32), ("reserved", C.c_int32),
+        ("seed", C.c_uint64), ("counter", C.c_uint64), ("env_id_base", C.c_int64),
+    ] + [(k, C.c_void_p) for k in (
+        "local_obs", "goal_delta", "blocking_prev", "action_mask", "weights", "actions", "actions64", "logp", "value",
+        "logits_out", "features_out")]
 
 
 class MapfError(RuntimeError):
@@ -172,10 +184,15 @@ def lib():
     L.mapf_launch_count.restype = i64
     L.mapf_step_kernel_kind.argtypes = [vp]
     L.mapf_occupancy_accumulate.argtypes = [vp, vp, vp, vp]
+    L.mapf_policy_weights_nbytes.argtypes = [i32]
+    L.mapf_policy_weights_nbytes.restype = i64
+    L.mapf_policy_pack_weights.argtypes = [i32] + [vp] * 9
+    L.mapf_policy_act.argtypes = [C.POINTER(MapfPolicyArgs), vp]
+    L.mapf_gae.argtypes = [vp, vp, vp, vp, vp, vp, i32, i64, i32, C.c_float, C.c_float, vp]
     L.mapf_cte_step.argtypes = [C.POINTER(MapfCteArgs), vp]
     L.mapf_cte_reset.argtypes = [C.POINTER(MapfCteArgs), vp]
     for name in EXPORTS:
-        if name not in ("mapf_version", "mapf_last_error", "mapf_launch_count"):
+        if name not in ("mapf_version", "mapf_last_error", "mapf_launch_count", "mapf_policy_weights_nbytes"):
             getattr(L, name).restype = C.c_int
     _lib = L
     return L
@@ -189,6 +206,7 @@ EXPORTS = (
     "mapf_flat_obs_dim", "mapf_pack_flat_obs", "mapf_sample_masked_actions",
     "mapf_sample_random_actions", "mapf_set_fused_sampler", "mapf_metrics_reduce", "mapf_poll_errors", "mapf_launch_count",
     "mapf_step_kernel_kind", "mapf_cte_step", "mapf_cte_reset", "mapf_occupancy_accumulate",
+    "mapf_policy_weights_nbytes", "mapf_policy_pack_weights", "mapf_policy_act", "mapf_gae",
 )
 
 

@@ -4,6 +4,7 @@
 // entry point that computes launches a kernel, and fails with MAPF_ERR_CUDA if it cannot.
 #include "mapf_env_kernel.cuh"
 #include "mapf_cte_kernel.cuh"
+#include "mapf_policy_kernel.cuh"
 
 #include <cstdarg>
 #include <cstdio>
@@ -902,6 +903,78 @@ static int cte_launch(const mapf_cte_args *a, int mode, void *stream) {
 
 int mapf_cte_step(const mapf_cte_args *a, void *stream) { return cte_launch(a, 0, stream); }
 int mapf_cte_reset(const mapf_cte_args *a, void *stream) { return cte_launch(a, 1, stream); }
+
+static int policy_kc1(int F) { return F < 1 ? 0 : F <= 32 ? 2 : F <= 64 ? 4 : 0; }
+
+int64_t mapf_policy_weights_nbytes(int32_t F) {
+    const int kc1 = policy_kc1(F);
+    if (!kc1) return fail(MAPF_ERR_UNSUPPORTED, "policy: feature_dim %d outside 1..64", F);
+    const int s1 = 16 * kc1 + 8;
+    return (int64_t)(mapf::POL_H * s1 + mapf::POL_H * mapf::POL_W2_STRIDE + 8 * mapf::POL_W2_STRIDE) * 2 + (2 * mapf::POL_H + 8) * 4;
+}
+
+int mapf_policy_pack_weights(int32_t F, const float *w1, const float *b1, const float *w2, const float *b2,
+                             const float *wl, const float *bl, const float *wv, const float *bv, void *packed) {
+    const int kc1 = policy_kc1(F);
+    if (!kc1) return fail(MAPF_ERR_UNSUPPORTED, "policy: feature_dim %d outside 1..64", F);
+    if (!w1 || !b1 || !w2 || !b2 || !wl || !bl || !wv || !bv || !packed) return fail(MAPF_ERR_INVALID_ARG, "null argument");
+    const int s1 = 16 * kc1 + 8, H = mapf::POL_H, S2 = mapf::POL_W2_STRIDE;
+    memset(packed, 0, (size_t)mapf_policy_weights_nbytes(F));
+    __nv_bfloat16 *p1 = static_cast<__nv_bfloat16 *>(packed), *p2 = p1 + H * s1, *p3 = p2 + H * S2;
+    float *pb = reinterpret_cast<float *>(p3 + 8 * S2);
+    for (int o = 0; o < H; ++o) {
+        for (int i = 0; i < F; ++i) p1[o * s1 + i] = __float2bfloat16_rn(w1[o * F + i]);
+        for (int i = 0; i < H; ++i) p2[o * S2 + i] = __float2bfloat16_rn(w2[o * H + i]);
+        pb[o] = b1[o];
+        pb[H + o] = b2[o];
+    }
+    for (int o = 0; o < 5; ++o) {
+        for (int i = 0; i < H; ++i) p3[o * S2 + i] = __float2bfloat16_rn(wl[o * H + i]);
+        pb[2 * H + o] = bl[o];
+    }
+    for (int i = 0; i < H; ++i) p3[5 * S2 + i] = __float2bfloat16_rn(wv[i]);
+    pb[2 * H + 5] = bv[0];
+    return MAPF_OK;
+}
+
+int mapf_policy_act(const mapf_policy_args *a, void *stream) {
+    if (!a) return fail(MAPF_ERR_INVALID_ARG, "null argument");
+    const int kc1 = policy_kc1(a->feature_dim);
+    if (!kc1 || a->v2 < 1 || a->feature_dim != a->v2 + 2 + (a->blocking_prev ? 1 : 0))
+        return fail(MAPF_ERR_UNSUPPORTED, "policy: feature_dim %d does not match v2 %d (+2 goal delta, +1 pressure) or exceeds 64",
+                    a->feature_dim, a->v2);
+    if (a->num_envs < 1 || a->num_agents < 1 || !a->local_obs || !a->goal_delta || !a->weights)
+        return fail(MAPF_ERR_INVALID_ARG, "policy: env outputs and weights are required");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
+        return fail(MAPF_ERR_CUDA, "no CUDA device (libmapf_b200 has no CPU fallback)");
+    const int threads = 256, warps = threads / 32, s1 = 16 * kc1 + 8;
+    const size_t smem = (size_t)mapf_policy_weights_nbytes(a->feature_dim) + (size_t)warps * 32 * s1 * 2;
+    const long long tiles = ((long long)a->num_envs * a->num_agents + 31) / 32;
+    long long blocks = (tiles + warps - 1) / warps;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (kc1 == 2) {
+        mapf::mapf_policy_act_kernel<2><<<(unsigned)blocks, threads, smem, st>>>(*a);
+    } else {
+        CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void *>(mapf::mapf_policy_act_kernel<4>),
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        mapf::mapf_policy_act_kernel<4><<<(unsigned)blocks, threads, smem, st>>>(*a);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return MAPF_OK;
+}
+
+int mapf_gae(const float *rewards, const float *values, const uint8_t *dones, const float *last_value, float *adv,
+             float *ret, int32_t T, int64_t B, int32_t N, float gamma, float lam, void *stream) {
+    if (!rewards || !values || !dones || !last_value || !adv || !ret || T < 1 || B < 1 || N < 1)
+        return fail(MAPF_ERR_INVALID_ARG, "gae: null or empty argument");
+    const long long BN = (long long)B * N;
+    mapf::mapf_gae_kernel<<<(unsigned)((BN + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        rewards, values, dones, last_value, adv, ret, T, BN, N, gamma, lam);
+    CUDA_TRY(cudaGetLastError());
+    return MAPF_OK;
+}
 
 int64_t mapf_launch_count(const mapf_handle *h) { return h ? h->launches : 0; }
 

@@ -70,6 +70,35 @@ def sample_categorical(logits: torch.Tensor):
 
 
 @torch.no_grad()
+def collect_fused(env, fused, steps: int, out=None) -> Batch:
+    """Like :func:`collect`, with policy forward + sampling in ONE CUDA launch per step
+    (:class:`policy_kernels.FusedPolicy`: bf16 tensor-core MLP straight from the env's output channels): per step
+    two launches in total -- the policy kernel and the env step."""
+    B, N = env.B, env.N
+    dev = env.device
+    F = env.flat_obs_dim(include_action_mask=False)
+    T = int(steps)
+    feats = torch.empty((T, B, N, F), device=dev)
+    masks = torch.empty((T, B, N, 5), dtype=torch.int8, device=dev)
+    actions = torch.empty((T, B, N), dtype=torch.int64, device=dev)
+    logp = torch.empty((T, B, N), device=dev)
+    values = torch.empty((T, B, N), device=dev)
+    rewards = torch.empty((T, B, N), device=dev)
+    dones = torch.empty((T, B), dtype=torch.bool, device=dev)
+    if out is None:
+        out = env._output()
+    for t in range(T):
+        masks[t].copy_(out.action_mask)
+        a, _, _ = fused.act(out, features_out=feats[t], logp=logp[t], value=values[t], actions64=actions[t])
+        out = env.step(a, auto_reset=True)
+        rewards[t].copy_(out.reward)
+        dones[t] = (out.terminated | out.truncated).bool()
+    last_value = torch.empty((B, N), device=dev)
+    fused.act(out, value=last_value)
+    return Batch(feats, masks, actions, logp, values, rewards, dones, last_value)
+
+
+@torch.no_grad()
 def collect(env, policy: ActionMaskPolicy, steps: int, out=None) -> Batch:
     """Roll the policy for ``steps`` env steps entirely on the env's device."""
     B, N = env.B, env.N
@@ -176,9 +205,19 @@ def benchmark(num_envs: int = 65536, steps: int = 64, device: str = "cuda:0") ->
         env.step(a, auto_reset=True)
     torch.cuda.synchronize(env.device)
     env_s = time.perf_counter() - t0
+    from .policy_kernels import FusedPolicy
+
+    env.fuse_sampler(None)
+    fused = FusedPolicy(policy, env)
+    collect_fused(env, fused, 4)
+    torch.cuda.synchronize(env.device)
+    t0 = time.perf_counter()
+    collect_fused(env, fused, steps)
+    torch.cuda.synchronize(env.device)
+    fused_s = time.perf_counter() - t0
     n = num_envs * env.N * steps
     return {"envs": num_envs, "agents": env.N, "steps": steps, "env_only_agent_steps_per_s": n / env_s,
-            "policy_loop_agent_steps_per_s": n / loop_s}
+            "policy_loop_agent_steps_per_s": n / loop_s, "fused_policy_loop_agent_steps_per_s": n / fused_s}
 
 
 if __name__ == "__main__":

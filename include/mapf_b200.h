@@ -325,6 +325,45 @@ typedef struct mapf_cte_args {
 int mapf_cte_step(const mapf_cte_args *args, void *stream);
 int mapf_cte_reset(const mapf_cte_args *args, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Rollout-loop kernels around the env step (BASELINE config 5): the reference's action-mask MLP
+ * (models/action_mask_model.py:8-67: Linear(F,64)-ReLU-Linear(64,64)-ReLU-{Linear(64,5), Linear(64,1)},
+ * logits + log(mask + 1e-6)) evaluated straight from the env's output channels and sampled, in one launch
+ * (bf16 tensor-core MLP, f32 accumulation), and generalised advantage estimation as a backwards scan.
+ */
+typedef struct mapf_policy_args {
+    int32_t num_envs, num_agents;
+    int32_t v2;           /* window cells, V * V */
+    int32_t feature_dim;  /* F = v2 + 2 + (blocking_prev ? 1 : 0), <= 64: order of ENV:306-328 without the mask */
+    int32_t no_masking;   /* action_mask_model.py:33 */
+    int32_t reserved;
+    uint64_t seed;        /* Philox key (with env_id_base + env), counter = (counter, agent) */
+    uint64_t counter;
+    int64_t env_id_base;
+    const uint8_t *local_obs;     /* [B,N,V,V]   device, the env's outputs */
+    const float *goal_delta;      /* [B,N,2] */
+    const uint8_t *blocking_prev; /* [B,N] or NULL */
+    const int8_t *action_mask;    /* [B,N,5] */
+    const void *weights;          /* device copy of the block written by mapf_policy_pack_weights */
+    int8_t *actions;              /* [B,N] sampled action (feeds mapf_step), may be NULL */
+    int64_t *actions64;           /* [B,N] the same as int64 (torch indexing dtype), may be NULL */
+    float *logp;                  /* [B,N] log-probability of the sampled action */
+    float *value;                 /* [B,N] value head */
+    float *logits_out;            /* [B,N,5] masked logits, may be NULL */
+    float *features_out;          /* [B,N,F] float32 feature block for the learner, may be NULL */
+} mapf_policy_args;
+
+/* Bytes of the packed weight block for feature_dim F (negative = unsupported F). */
+int64_t mapf_policy_weights_nbytes(int32_t feature_dim);
+/* HOST float32 weights in torch's Linear layout ([out, in] row-major) -> HOST packed block (bf16, padded). */
+int mapf_policy_pack_weights(int32_t feature_dim, const float *w1, const float *b1, const float *w2, const float *b2,
+                             const float *w_logits, const float *b_logits, const float *w_value, const float *b_value,
+                             void *packed_host);
+int mapf_policy_act(const mapf_policy_args *args, void *stream);
+/* rewards / values / adv / ret: device float32 [T,B,N]; dones uint8 [T,B]; last_value float32 [B,N]. */
+int mapf_gae(const float *rewards, const float *values, const uint8_t *dones, const float *last_value, float *adv,
+             float *ret, int32_t T, int64_t B, int32_t N, float gamma, float lam, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
