@@ -948,13 +948,15 @@ int mapf_policy_act(const mapf_policy_args *a, void *stream) {
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
         return fail(MAPF_ERR_CUDA, "no CUDA device (libmapf_b200 has no CPU fallback)");
-    const int threads = 256, warps = threads / 32, s1 = 16 * kc1 + 8;
-    const size_t smem = (size_t)mapf_policy_weights_nbytes(a->feature_dim) + (size_t)warps * 32 * s1 * 2;
+    const int threads = 256, warps = threads / 32;
+    const size_t smem = (size_t)mapf_policy_weights_nbytes(a->feature_dim) + (size_t)warps * mapf::pol_warp_bytes(kc1, a->v2);
     const long long tiles = ((long long)a->num_envs * a->num_agents + 31) / 32;
     long long blocks = (tiles + warps - 1) / warps;
     if (blocks > 148 * 8) blocks = 148 * 8;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (kc1 == 2) {
+        CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void *>(mapf::mapf_policy_act_kernel<2>),
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         mapf::mapf_policy_act_kernel<2><<<(unsigned)blocks, threads, smem, st>>>(*a);
     } else {
         CUDA_TRY(cudaFuncSetAttribute(reinterpret_cast<const void *>(mapf::mapf_policy_act_kernel<4>),

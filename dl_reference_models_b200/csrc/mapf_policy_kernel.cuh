@@ -38,6 +38,12 @@ __device__ __forceinline__ uint32_t pack_relu_bf16(float lo, float hi) {
     return *reinterpret_cast<const uint32_t *>(&v);
 }
 
+// per-warp shared memory of mapf_policy_act_kernel (bytes)
+__host__ __device__ constexpr int pol_raw_bytes(int v2) { return (((32 * v2 + 3) / 4 + 2) * 4 + 15) & ~15; }   // raw window bytes + slack, 16-byte multiple
+__host__ __device__ constexpr int pol_warp_bytes(int kc1, int v2) {
+    return 32 * (16 * kc1 + 8) * 2 /* bf16 feature tile */ + pol_raw_bytes(v2) + 160 /* masks */ + 32 * 8 * 4 /* head outputs */;
+}
+
 // KC1 = k16 chunks of the first layer (F <= 16 * KC1), W1 row stride = 16 * KC1 + 8
 template <int KC1>
 __global__ void __launch_bounds__(256) mapf_policy_act_kernel(const mapf_policy_args a) {
@@ -47,32 +53,55 @@ __global__ void __launch_bounds__(256) mapf_policy_act_kernel(const mapf_policy_
     __nv_bfloat16 *w2 = w1 + POL_H * S1;                                        // [64][72]
     __nv_bfloat16 *w3 = w2 + POL_H * POL_W2_STRIDE;                             // [8][72]: 5 logits, value, 2 zero rows
     float *bias = reinterpret_cast<float *>(w3 + 8 * POL_W2_STRIDE);            // b1[64] b2[64] b3[8]
-    __nv_bfloat16 *xs_all = reinterpret_cast<__nv_bfloat16 *>(bias + 2 * POL_H + 8);   // per warp [32][S1]
+    unsigned char *wsm0 = reinterpret_cast<unsigned char *>(bias + 2 * POL_H + 8);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, warps = blockDim.x >> 5;
     {   // weights: already bf16 and padded on the host side (mapf_policy_pack_weights)
         const uint4 *src = reinterpret_cast<const uint4 *>(a.weights);
         uint4 *dst = reinterpret_cast<uint4 *>(psm);
-        const int n16 = (int)((reinterpret_cast<unsigned char *>(xs_all) - psm) >> 4);
+        const int n16 = (int)((wsm0 - psm) >> 4);
         for (int i = tid; i < n16; i += blockDim.x) dst[i] = src[i];
     }
     __syncthreads();
-    __nv_bfloat16 *xs = xs_all + warp * 32 * S1;
-    const int g = lane >> 2, t = lane & 3;
     const int V2 = a.v2, F = a.feature_dim, N = a.num_agents;
+    unsigned char *wsm = wsm0 + warp * pol_warp_bytes(KC1, V2);
+    __nv_bfloat16 *xs = reinterpret_cast<__nv_bfloat16 *>(wsm);                 // [32][S1] bf16 features
+    uint32_t *raw = reinterpret_cast<uint32_t *>(wsm + 32 * S1 * 2);            // the tile's window bytes, as loaded
+    uint32_t *rawm = reinterpret_cast<uint32_t *>(wsm + 32 * S1 * 2 + pol_raw_bytes(V2));   // 32 x 5 mask bytes
+    float *os = reinterpret_cast<float *>(wsm + 32 * S1 * 2 + pol_raw_bytes(V2) + 160);     // [32][8] head outputs
+    const int g = lane >> 2, t = lane & 3;
     const long long BN = (long long)a.num_envs * N;
     const long long ntiles = (BN + 31) >> 5;
+    const int NW = (V2 + 3) >> 2;   // words of one agent's window
     for (long long tile = (long long)blockIdx.x * warps + warp; tile < ntiles; tile += (long long)gridDim.x * warps) {
         const long long ag0 = tile << 5;
-        // ---------------------------------------------------------------- feature tile (ENV:306-328 order: window, goal delta, pressure)
-        for (int i = lane; i < 32 * S1 / 2; i += 32) reinterpret_cast<uint32_t *>(xs)[i] = 0u;
-        __syncwarp();
+        const long long left = BN - ag0;
+        const int na = left < 32 ? (int)left : 32;
+        // ---------------------------------------------------------------- raw channels of the tile, coalesced
         {
-            const long long left = BN - ag0;
-            const int na = left < 32 ? (int)left : 32;
-            const uint8_t *ob = a.local_obs + ag0 * V2;
-            for (int i = lane; i < na * V2; i += 32) {
-                const int r = i / V2, c = i - r * V2;
-                xs[r * S1 + c] = __float2bfloat16((float)ob[i]);
+            const uint32_t *ob32 = reinterpret_cast<const uint32_t *>(a.local_obs + ag0 * V2);   // 32 * V2 bytes: 4-byte aligned
+            const int nwords = (na * V2 + 3) >> 2;
+            for (int i = lane; i < (32 * V2 + 3) / 4 + 2; i += 32) raw[i] = i < nwords ? ob32[i] : 0u;
+            if (a.action_mask) {
+                const uint32_t *mk32 = reinterpret_cast<const uint32_t *>(a.action_mask + ag0 * 5);
+                const int mwords = (na * 5 + 3) >> 2;
+                for (int i = lane; i < 40; i += 32) rawm[i] = i < mwords ? mk32[i] : 0u;
+            }
+        }
+        __syncwarp();
+        // ---------------------------------------------------------------- feature row of agent `lane` (ENV:306-328 order: window, goal delta, pressure)
+        {
+            uint2 *row = reinterpret_cast<uint2 *>(xs + lane * S1);
+            const int off = lane * V2;
+            for (int j = 0; j < 4 * KC1; ++j) {   // 4 cells -> 4 bf16 per trip; columns beyond the window are zero
+                uint32_t w = 0;
+                if (j < NW) {
+                    const int b = off + 4 * j;
+                    w = __funnelshift_r(raw[b >> 2], raw[(b >> 2) + 1], (b & 3) * 8);
+                    if (4 * j + 4 > V2) w &= (1u << (8 * (V2 - 4 * j))) - 1u;
+                }
+                const __nv_bfloat162 lo = __floats2bfloat162_rn((float)(w & 0xFFu), (float)((w >> 8) & 0xFFu));
+                const __nv_bfloat162 hi = __floats2bfloat162_rn((float)((w >> 16) & 0xFFu), (float)(w >> 24));
+                row[j] = make_uint2(*reinterpret_cast<const uint32_t *>(&lo), *reinterpret_cast<const uint32_t *>(&hi));
             }
             if (lane < na) {
                 const float2 gd = reinterpret_cast<const float2 *>(a.goal_delta)[ag0 + lane];
@@ -82,10 +111,11 @@ __global__ void __launch_bounds__(256) mapf_policy_act_kernel(const mapf_policy_
             }
             if (a.features_out) {   // float32 feature block for the learner (optional)
                 float *fo = a.features_out + ag0 * F;
+                const uint8_t *rb = reinterpret_cast<const uint8_t *>(raw);
                 for (int i = lane; i < na * F; i += 32) {
                     const int r = i / F, c = i - r * F;
                     float v;
-                    if (c < V2) v = (float)ob[r * V2 + c];
+                    if (c < V2) v = (float)rb[r * V2 + c];
                     else if (c < V2 + 2) v = a.goal_delta[(ag0 + r) * 2 + (c - V2)];
                     else v = (float)a.blocking_prev[ag0 + r];
                     fo[i] = v;
@@ -107,7 +137,8 @@ __global__ void __launch_bounds__(256) mapf_policy_act_kernel(const mapf_policy_
             uint32_t h1[POL_H / 16][4];   // A fragments of layer 2
 #pragma unroll
             for (int j = 0; j < POL_H / 8; ++j) {
-                float d[4] = {bias[8 * j + 2 * t], bias[8 * j + 2 * t + 1], bias[8 * j + 2 * t], bias[8 * j + 2 * t + 1]};
+                const float2 bb = *reinterpret_cast<const float2 *>(bias + 8 * j + 2 * t);
+                float d[4] = {bb.x, bb.y, bb.x, bb.y};
 #pragma unroll
                 for (int kk = 0; kk < KC1; ++kk) {
                     const uint32_t *wb = reinterpret_cast<const uint32_t *>(w1 + (8 * j + g) * S1 + 16 * kk + 2 * t);
@@ -120,8 +151,8 @@ __global__ void __launch_bounds__(256) mapf_policy_act_kernel(const mapf_policy_
             uint32_t h2[POL_H / 16][4];
 #pragma unroll
             for (int j = 0; j < POL_H / 8; ++j) {
-                const float *b2 = bias + POL_H;
-                float d[4] = {b2[8 * j + 2 * t], b2[8 * j + 2 * t + 1], b2[8 * j + 2 * t], b2[8 * j + 2 * t + 1]};
+                const float2 bb = *reinterpret_cast<const float2 *>(bias + POL_H + 8 * j + 2 * t);
+                float d[4] = {bb.x, bb.y, bb.x, bb.y};
 #pragma unroll
                 for (int kk = 0; kk < POL_H / 16; ++kk) {
                     const uint32_t *wb = reinterpret_cast<const uint32_t *>(w2 + (8 * j + g) * POL_W2_STRIDE + 16 * kk + 2 * t);
@@ -131,56 +162,50 @@ __global__ void __launch_bounds__(256) mapf_policy_act_kernel(const mapf_policy_
                 h2[j >> 1][(j & 1) * 2 + 1] = pack_relu_bf16(d[2], d[3]);
             }
             // ------------------------------------------------------------ heads: columns 0..4 logits, 5 value
-            const float *b3 = bias + 2 * POL_H;
-            float d[4] = {b3[2 * t], b3[2 * t + 1], b3[2 * t], b3[2 * t + 1]};
+            const float2 bb = *reinterpret_cast<const float2 *>(bias + 2 * POL_H + 2 * t);
+            float d[4] = {bb.x, bb.y, bb.x, bb.y};
 #pragma unroll
             for (int kk = 0; kk < POL_H / 16; ++kk) {
                 const uint32_t *wb = reinterpret_cast<const uint32_t *>(w3 + g * POL_W2_STRIDE + 16 * kk + 2 * t);
                 mma_bf16_16816(d, h2[kk], wb[0], wb[4]);
             }
-            // gather the 6 outputs of row g / g+8 in the quad's lane 0 (t = 1 holds cols 2,3; t = 2 holds 4,5)
-            const unsigned full = 0xFFFFFFFFu;
-            float lo[6], hi[6];
-            lo[0] = d[0]; lo[1] = d[1]; hi[0] = d[2]; hi[1] = d[3];
-            lo[2] = __shfl_down_sync(full, d[0], 1); lo[3] = __shfl_down_sync(full, d[1], 1);
-            hi[2] = __shfl_down_sync(full, d[2], 1); hi[3] = __shfl_down_sync(full, d[3], 1);
-            lo[4] = __shfl_down_sync(full, d[0], 2); lo[5] = __shfl_down_sync(full, d[1], 2);
-            hi[4] = __shfl_down_sync(full, d[2], 2); hi[5] = __shfl_down_sync(full, d[3], 2);
-            if (t == 0) {
+            *reinterpret_cast<float2 *>(os + row0 * 8 + 2 * t) = make_float2(d[0], d[1]);
+            *reinterpret_cast<float2 *>(os + (row0 + 8) * 8 + 2 * t) = make_float2(d[2], d[3]);
+        }
+        __syncwarp();
+        // ---------------------------------------------------------------- one agent per lane: mask, softmax, draw
+        if (lane < na) {
+            const long long ag = ag0 + lane;
+            const float4 o03 = *reinterpret_cast<const float4 *>(os + lane * 8);
+            const float2 o45 = *reinterpret_cast<const float2 *>(os + lane * 8 + 4);
+            float l[5] = {o03.x, o03.y, o03.z, o03.w, o45.x};
+            if (!a.no_masking && a.action_mask) {   // logits + clamp(log(mask + 1e-6), FLOAT_MIN), action_mask_model.py:57-61
+                const uint8_t *mk = reinterpret_cast<const uint8_t *>(rawm) + lane * 5;
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    const long long ag = ag0 + row0 + 8 * half;
-                    if (ag >= BN) continue;
-                    const float *o = half ? hi : lo;
-                    float l[5];
-                    const int8_t *mk = a.action_mask + ag * 5;
+                for (int k = 0; k < 5; ++k) l[k] += mk[k] ? 9.99999e-07f : -13.815511f;
+            }
+            float mx = l[0];
 #pragma unroll
-                    for (int k = 0; k < 5; ++k)   // logits + clamp(log(mask + 1e-6), FLOAT_MIN), action_mask_model.py:57-61
-                        l[k] = o[k] + ((a.no_masking || !a.action_mask) ? 0.f : (mk[k] ? 9.99999e-07f : -13.815511f));
-                    float mx = l[0];
+            for (int k = 1; k < 5; ++k) mx = fmaxf(mx, l[k]);
+            float pr[5], sum = 0.f;
 #pragma unroll
-                    for (int k = 1; k < 5; ++k) mx = fmaxf(mx, l[k]);
-                    float pr[5], sum = 0.f;
+            for (int k = 0; k < 5; ++k) { pr[k] = __expf(l[k] - mx); sum += pr[k]; }
+            const unsigned env = (unsigned)((unsigned long long)ag / (unsigned)N);   // B * N < 2^32 in any batch that fits a GPU
+            const int agent = (int)(ag - (long long)env * N);
+            Philox ph(a.seed ^ 0x504F4C49ull /* "POLI" */, a.env_id_base + env);
+            const uint4 x = ph((uint32_t)a.counter, (uint32_t)(a.counter >> 32), (uint32_t)agent, 0x53414D50u /* "SAMP" */);
+            const float u = ((float)(x.x >> 8) + 0.5f) * (1.0f / 16777216.0f) * sum;   // uniform in (0, sum)
+            int act = 0;
+            float cum = pr[0];
 #pragma unroll
-                    for (int k = 0; k < 5; ++k) { pr[k] = __expf(l[k] - mx); sum += pr[k]; }
-                    const long long env = ag / N;
-                    const int agent = (int)(ag - env * N);
-                    Philox ph(a.seed ^ 0x504F4C49ull /* "POLI" */, a.env_id_base + env);
-                    const uint4 x = ph((uint32_t)a.counter, (uint32_t)(a.counter >> 32), (uint32_t)agent, 0x53414D50u /* "SAMP" */);
-                    const float u = ((float)(x.x >> 8) + 0.5f) * (1.0f / 16777216.0f) * sum;   // uniform in (0, sum)
-                    int act = 0;
-                    float cum = pr[0];
+            for (int k = 1; k < 5; ++k) { if (u >= cum) act = k; cum += pr[k]; }
+            if (a.actions) a.actions[ag] = (int8_t)act;
+            if (a.actions64) a.actions64[ag] = (long long)act;
+            if (a.logp) a.logp[ag] = l[act] - mx - __logf(sum);
+            if (a.value) a.value[ag] = o45.y;
+            if (a.logits_out) {
 #pragma unroll
-                    for (int k = 1; k < 5; ++k) { if (u >= cum) act = k; cum += pr[k]; }
-                    if (a.actions) a.actions[ag] = (int8_t)act;
-                    if (a.actions64) a.actions64[ag] = (long long)act;
-                    if (a.logp) a.logp[ag] = l[act] - mx - __logf(sum);
-                    if (a.value) a.value[ag] = o[5];
-                    if (a.logits_out) {
-#pragma unroll
-                        for (int k = 0; k < 5; ++k) a.logits_out[ag * 5 + k] = l[k];
-                    }
-                }
+                for (int k = 0; k < 5; ++k) a.logits_out[ag * 5 + k] = l[k];
             }
         }
         __syncwarp();
