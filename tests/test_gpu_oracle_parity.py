@@ -9,6 +9,12 @@ from gpu_utils import ORACLE_STEP_KEYS, STATE_KEYS, assert_batch_equal, gpu_chan
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=["lane", "env"])
+def kind(request):
+    """Both step kernels face the oracle directly (lane-per-agent / env-per-thread)."""
+    return request.param
+
+
 def _run_parity(cfg, grid, B, steps, seed, policy="random", per_env_grid=False, auto_reset=False):
     import torch
 
@@ -86,28 +92,29 @@ def test_c2_4096_envs_4_agents_reference_map():
     assert eps >= 3 * 4096 - 4096  # early terminations shift the phase of a few envs
 
 
-def test_c2_goal_seeking_policy_terminations():
+def test_c2_goal_seeking_policy_terminations(kind):
     from dl_reference_models_b200 import maps
 
-    cfg = {"num_agents": 4, "sensor_range": 2, "steps_per_episode": 60, "seed": 5}
+    cfg = {"num_agents": 4, "sensor_range": 2, "steps_per_episode": 60, "seed": 5, "step_kernel": kind}
     _run_parity(cfg, maps.get_grid("ReferenceModel-2-1"), 1000, 150, seed=11, policy="greedy")
 
 
-def test_c3_lifelong_32x32_16_agents():
+def test_c3_lifelong_32x32_16_agents(kind):
     """BASELINE config 3 shape at a size the oracle finishes in seconds."""
     from dl_reference_models_b200 import maps
 
     grid = maps.random_obstacle_grid(32, 32, 0.30, 2026, min_free=32)
-    cfg = {"num_agents": 16, "sensor_range": 2, "steps_per_episode": 64, "lifelong_mapf": True, "seed": 1}
+    cfg = {"num_agents": 16, "sensor_range": 2, "steps_per_episode": 64, "lifelong_mapf": True, "seed": 1,
+           "step_kernel": kind}
     _run_parity(cfg, grid, 777, 160, seed=3, policy="greedy")
 
 
-def test_c4_corridor_32_agents_lock_metrics():
+def test_c4_corridor_32_agents_lock_metrics(kind):
     """BASELINE config 4: all eight lock keys on deadlock-heavy corridors, 64 envs x 256 steps."""
     from dl_reference_models_b200 import maps
 
     cfg = {"num_agents": 32, "sensor_range": 2, "steps_per_episode": 256, "seed": 2,
-           "deadlock_window_steps": 8, "livelock_window_steps": 16}
+           "deadlock_window_steps": 8, "livelock_window_steps": 16, "step_kernel": kind}
     _run_parity(cfg, maps.corridor_grid(32, 32), 64, 256, seed=17, policy="greedy")
     _run_parity(cfg, maps.corridor_grid(32, 32), 33, 128, seed=19, policy="masked")
 
@@ -118,26 +125,28 @@ def test_c4_corridor_32_agents_lock_metrics():
     (13, 3, "ReferenceModel-3-1", False), (32, 3, "ReferenceModel-3-1", True),
     (4, 2, "ReferenceModel-1-4", False), (2, 2, "ReferenceModel-1-1", True),
 ])
-def test_shapes_and_agent_counts(n, sr, name, lifelong):
+def test_shapes_and_agent_counts(n, sr, name, lifelong, kind):
     from dl_reference_models_b200 import maps
 
-    cfg = {"num_agents": n, "sensor_range": sr, "steps_per_episode": 40, "lifelong_mapf": lifelong,
+    cfg = {"num_agents": n, "sensor_range": sr, "steps_per_episode": 40, "lifelong_mapf": lifelong, "step_kernel": kind,
            "seed": 7, "deadlock_window_steps": 3, "livelock_window_steps": 5,
            "lock_nearby_manhattan": 3, "lock_min_neighbors": 1 if n < 4 else 2,
            "normalize_goal_delta": n % 2 == 0}
     _run_parity(cfg, maps.get_grid(name), 67, 90, seed=n * 10 + sr, policy="greedy")
 
 
-def test_lock_metrics_disabled_and_windows_32():
+def test_lock_metrics_disabled_and_windows_32(kind):
     from dl_reference_models_b200 import maps
 
     g = maps.get_grid("ReferenceModel-1-4")
-    _run_parity({"num_agents": 4, "sensor_range": 2, "steps_per_episode": 50, "enable_lock_metrics": False},
-                g, 40, 120, seed=1, policy="greedy")
+    _run_parity({"num_agents": 4, "sensor_range": 2, "steps_per_episode": 50, "enable_lock_metrics": False,
+                 "step_kernel": kind}, g, 40, 120, seed=1, policy="greedy")
     _run_parity({"num_agents": 4, "sensor_range": 2, "steps_per_episode": 90, "deadlock_window_steps": 32,
-                 "livelock_window_steps": 32, "lock_progress_epsilon": 2.5}, g, 40, 200, seed=2, policy="greedy")
+                 "livelock_window_steps": 32, "lock_progress_epsilon": 2.5, "step_kernel": kind}, g, 40, 200, seed=2,
+                policy="greedy")
     _run_parity({"num_agents": 4, "sensor_range": 2, "steps_per_episode": 90, "deadlock_window_steps": 1,
-                 "livelock_window_steps": 1, "lock_progress_epsilon": 0}, g, 40, 100, seed=3, policy="greedy")
+                 "livelock_window_steps": 1, "lock_progress_epsilon": 0, "step_kernel": kind}, g, 40, 100, seed=3,
+                policy="greedy")
 
 
 def test_per_env_maps():
