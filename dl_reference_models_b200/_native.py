@@ -184,6 +184,8 @@ def lib():
     L.mapf_launch_count.restype = i64
     L.mapf_step_kernel_kind.argtypes = [vp]
     L.mapf_occupancy_accumulate.argtypes = [vp, vp, vp, vp]
+    L.mapf_distance_table.argtypes = [vp, vp, vp]
+    L.mapf_goal_path_lengths.argtypes = [vp, vp, vp, vp]
     L.mapf_policy_weights_nbytes.argtypes = [i32]
     L.mapf_policy_weights_nbytes.restype = i64
     L.mapf_policy_pack_weights.argtypes = [i32] + [vp] * 9
@@ -205,7 +207,7 @@ EXPORTS = (
     "mapf_observe", "mapf_observe_host",
     "mapf_flat_obs_dim", "mapf_pack_flat_obs", "mapf_sample_masked_actions",
     "mapf_sample_random_actions", "mapf_set_fused_sampler", "mapf_metrics_reduce", "mapf_poll_errors", "mapf_launch_count",
-    "mapf_step_kernel_kind", "mapf_cte_step", "mapf_cte_reset", "mapf_occupancy_accumulate",
+    "mapf_step_kernel_kind", "mapf_cte_step", "mapf_cte_reset", "mapf_occupancy_accumulate", "mapf_distance_table", "mapf_goal_path_lengths",
     "mapf_policy_weights_nbytes", "mapf_policy_pack_weights", "mapf_policy_act", "mapf_gae",
 )
 

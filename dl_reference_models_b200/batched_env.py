@@ -254,6 +254,23 @@ class BatchedMapfEnv:
         nat.check(self._lib.mapf_occupancy_accumulate(self._h, self._ptr(a), self._ptr(counts), self._stream()))
         return counts
 
+    def distance_table(self) -> torch.Tensor:
+        """uint8 [R*C, R*C]: moves between any two cells of the shared map around the obstacles (255 = unreachable),
+        built once by a bit-parallel BFS kernel (one warp per source cell) and cached."""
+        if getattr(self, "_dist_table", None) is None:
+            cells = int(self.grid.shape[-2] * self.grid.shape[-1])
+            t = torch.empty((cells, cells), dtype=torch.uint8, device=self.device)
+            nat.check(self._lib.mapf_distance_table(self._h, self._ptr(t), self._stream()))
+            self._dist_table = t
+        return self._dist_table
+
+    def goal_path_lengths(self) -> torch.Tensor:
+        """int16 [B,N]: shortest obstacle-aware path length from every agent's position to its goal (-1 = unreachable),
+        other agents ignored -- the single-agent lower bound the classical planners start from (scripts/a-star.py)."""
+        out = torch.empty((self.B, self.N), dtype=torch.int16, device=self.device)
+        nat.check(self._lib.mapf_goal_path_lengths(self._h, self._ptr(self.distance_table()), self._ptr(out), self._stream()))
+        return out
+
     def poll_errors(self) -> int:
         bits = C.c_uint32(0)
         nat.check(self._lib.mapf_poll_errors(self._h, C.byref(bits), self._stream()))

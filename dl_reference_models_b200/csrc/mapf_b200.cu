@@ -870,6 +870,36 @@ int mapf_occupancy_accumulate(mapf_handle *h, const uint8_t *active, uint64_t *c
     return MAPF_OK;
 }
 
+int mapf_distance_table(mapf_handle *h, uint8_t *table, void *stream) {
+    int rc = check_ready(h);
+    if (rc) return rc;
+    if (!table) return fail(MAPF_ERR_INVALID_ARG, "null argument");
+    if (h->cfg.per_env_maps || h->cfg.rows > 32 || h->cfg.cols > 32)
+        return fail(MAPF_ERR_UNSUPPORTED, "distance table needs one shared map of at most 32x32 cells (got %dx%d, per_env_maps=%d)",
+                    h->cfg.rows, h->cfg.cols, h->cfg.per_env_maps);
+    DeviceGuard guard(h->cfg.device);
+    const int cells = h->cfg.rows * h->cfg.cols, warps = 8;
+    mapf::mapf_distance_table_kernel<<<(cells + warps - 1) / warps, warps * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+        h->d_free_bits, h->cfg.rows, h->cfg.cols, table);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    return MAPF_OK;
+}
+
+int mapf_goal_path_lengths(mapf_handle *h, const uint8_t *table, int16_t *out, void *stream) {
+    int rc = check_ready(h);
+    if (rc) return rc;
+    if (!table || !out) return fail(MAPF_ERR_INVALID_ARG, "null argument");
+    DeviceGuard guard(h->cfg.device);
+    const long long BN = (long long)h->cfg.num_envs * h->cfg.num_agents;
+    mapf::mapf_goal_path_lengths_kernel<<<(unsigned)((BN + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const uint32_t *>(h->st.positions), reinterpret_cast<const uint32_t *>(h->st.goals), table, BN,
+        h->cfg.rows, h->cfg.cols, out);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    return MAPF_OK;
+}
+
 int mapf_poll_errors(mapf_handle *h, uint32_t *bits, void *stream) {
     if (!h || !bits) return fail(MAPF_ERR_INVALID_ARG, "null argument");
     DeviceGuard guard(h->cfg.device);

@@ -1148,6 +1148,50 @@ __global__ void mapf_occupancy_kernel(const uint32_t *positions, const uint8_t *
     }
 }
 
+// Single-agent shortest paths on the shared map (the obstacle-aware distance field behind the
+// reference's classical planners, scripts/a-star.py:123-126 uses the Manhattan heuristic of the same 4-neighbour
+// moves).  One warp per source cell, one lane per map row (R, C <= 32): the BFS frontier is a bitboard, one wavefront
+// per iteration: next = (left | right | up | down) & free & ~visited, up / down by warp shuffles.
+// table[src * R*C + cell] = number of moves from src to cell, 255 = unreachable (or > 254).
+__global__ void mapf_distance_table_kernel(const uint32_t *free_bits, int R, int C, uint8_t *table) {
+    const unsigned full = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31;
+    const int src = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int cells = R * C;
+    if (src >= cells) return;
+    // free cells of my row as a C-bit word (the free bitmap is cell-linear)
+    uint32_t freerow = 0;
+    if (lane < R) {
+        const int b0 = lane * C;
+        const uint64_t w = (uint64_t)free_bits[b0 >> 5] | ((uint64_t)(((b0 >> 5) + 1) * 32 < cells + 32 ? free_bits[(b0 >> 5) + 1] : 0u) << 32);
+        freerow = (uint32_t)(w >> (b0 & 31)) & (C >= 32 ? full : ((1u << C) - 1u));
+    }
+    uint8_t *out = table + (size_t)src * cells;
+    for (int c = 0; c < C; ++c) if (lane < R) out[lane * C + c] = 255;
+    const int sr = src / C, sc = src % C;
+    uint32_t frontier = (lane == sr) ? ((1u << sc) & freerow) : 0u, visited = frontier;
+    for (int d = 0; d < 255; ++d) {
+        if (!__any_sync(full, frontier != 0)) break;
+        for (uint32_t f = frontier; f; f &= f - 1) out[lane * C + (__ffs(f) - 1)] = (uint8_t)d;
+        const uint32_t up = __shfl_up_sync(full, frontier, 1), dn = __shfl_down_sync(full, frontier, 1);
+        uint32_t nf = (frontier << 1) | (frontier >> 1) | (lane > 0 ? up : 0u) | (lane < 31 ? dn : 0u);
+        nf &= freerow & ~visited;
+        visited |= nf;
+        frontier = nf;
+    }
+}
+
+// out[b, n] = table[goal][position] of every agent (int16; -1 = unreachable)
+__global__ void mapf_goal_path_lengths_kernel(const uint32_t *positions, const uint32_t *goals, const uint8_t *table,
+                                              long long BN, int R, int C, int16_t *out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= BN) return;
+    const uint32_t p = positions[i], g = goals[i];
+    const int pc = prow(p) * C + pcol(p), gc = prow(g) * C + pcol(g);
+    const uint8_t d = table[(size_t)gc * (R * C) + pc];
+    out[i] = d == 255 ? (int16_t)-1 : (int16_t)d;
+}
+
 // Deterministic reduction of env_metrics[B,K]: CTA k reduces metric k in a fixed order
 // (strided partial sums, then a shared-memory tree), so the result does not depend on timing.
 __global__ void mapf_metrics_reduce_kernel(const double *env_metrics, int B, double *out) {

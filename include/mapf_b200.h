@@ -279,6 +279,14 @@ int mapf_metrics_reduce(mapf_handle *h, double *out_device, void *stream);
  * the number of agents standing on (r, c), over the envs with active[env] != 0 (device uint8 [B], NULL = all). */
 int mapf_occupancy_accumulate(mapf_handle *h, const uint8_t *active, uint64_t *counts, void *stream);
 
+/* Single-agent shortest paths on the shared map (4-neighbour moves around obstacles, other agents ignored): the
+ * distance field behind the reference's classical planners (scripts/a-star.py:123-126, scripts/cbs.py).
+ * mapf_distance_table fills table[src * R*C + cell] (device uint8 [R*C, R*C], 255 = unreachable; maps <= 32x32);
+ * mapf_goal_path_lengths writes out[b, n] = moves from agent n's position to its goal (device int16 [B,N], -1 =
+ * unreachable): a lower bound of the agent's arrival time and, as the max over agents, of the makespan. */
+int mapf_distance_table(mapf_handle *h, uint8_t *table, void *stream);
+int mapf_goal_path_lengths(mapf_handle *h, const uint8_t *table, int16_t *out, void *stream);
+
 /* OR of MAPF_DEV_ERR_* bits raised by kernels since the last poll (synchronises `stream`). */
 int mapf_poll_errors(mapf_handle *h, uint32_t *bits, void *stream);
 
