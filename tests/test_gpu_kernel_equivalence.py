@@ -156,3 +156,28 @@ def test_several_lanes_per_env_variant(monkeypatch, n):
     run_pair(c3(num_agents=n, steps_per_episode=30), 1500, 70)
     run_pair({"env_name": "ReferenceModel-3-1", "num_agents": n, "sensor_range": 1, "steps_per_episode": 50, "seed": 9},
              300, 120, masked=False)
+
+
+def test_tall_map_null_actions_and_invalid_actions():
+    """Edge inputs on both kernels: a 48-row map (boards taller than a warp), NULL actions (= all NO_OP, ENV:498-500),
+    out-of-range actions (flagged MAPF_DEV_ERR_INVALID_ACTION and treated as NO_OP), maximum agent count."""
+    import torch
+
+    from dl_reference_models_b200 import maps
+
+    grid = maps.random_obstacle_grid(48, 32, 0.25, 11, min_free=200)
+    cfg = {"num_agents": 32, "sensor_range": 3, "steps_per_episode": 20, "lifelong_mapf": True, "seed": 3, "grid": grid}
+    a, b = make(cfg, 257, "lane"), make(cfg, 257, "env")
+    oa, ob = a.reset(), b.reset()
+    assert_same(a, b, oa, ob, "reset")
+    gen = torch.Generator().manual_seed(0)
+    for s in range(50):
+        if s % 7 == 3:
+            oa, ob = a.step(None, auto_reset=True), b.step(None, auto_reset=True)
+            assert int(oa.agent_step_flags.bitwise_and(nat.ASF_MOVED).sum()) == 0, "NULL actions move nobody"
+        else:
+            acts = torch.randint(-2 if s % 11 == 5 else 0, 7 if s % 11 == 5 else 5, (257, 32), dtype=torch.int8, generator=gen)
+            oa, ob = a.step(acts, auto_reset=True), b.step(acts, auto_reset=True)
+        assert_same(a, b, oa, ob, f"step {s}")
+    ea, eb = a.poll_errors(), b.poll_errors()
+    assert ea == eb and (ea & nat.DEV_ERR_INVALID_ACTION)
