@@ -1012,10 +1012,10 @@ __global__ void __launch_bounds__(LPE == 1 ? 448 : 512, 1) mapf_step_env_kernel(
                 my_stage[OBS_W + 3] = (lo[2] >> 16) | (hi[2] << 16) | (lo[3] << 24);
                 my_stage[OBS_W + 4] = (lo[3] >> 8) | (hi[3] << 24);
                 if (p.o_goal_delta) {
-                    if (VEC) {
-                        float4 *g4p = reinterpret_cast<float4 *>(p.o_goal_delta + ab + i0);
-                        g4p[0] = make_float4(gd[0].x, gd[0].y, gd[1].x, gd[1].y);
-                        g4p[1] = make_float4(gd[2].x, gd[2].y, gd[3].x, gd[3].y);
+                    if (VEC) {   // one 256-bit store per quad (sm_100 STG.256): half the L1 tag look-ups of two 128-bit stores
+                        asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p.o_goal_delta + ab + i0),
+                                     "f"(gd[0].x), "f"(gd[0].y), "f"(gd[1].x), "f"(gd[1].y), "f"(gd[2].x), "f"(gd[2].y),
+                                     "f"(gd[3].x), "f"(gd[3].y) : "memory");
                     } else {
 #pragma unroll
                         for (int k = 0; k < 4; ++k) if (i0 + k < N) p.o_goal_delta[ab + i0 + k] = gd[k];
