@@ -477,6 +477,162 @@ __global__ void __launch_bounds__(LPE == 1 ? 448 : 512, 1) mapf_step_env_kernel(
             uint32_t pend = p.lifelong ? gstep_m : 0u;
             reassigned = pend != 0;
             if (!__any_sync(full, reassigned)) continue;
+            if constexpr (LPE == 1) {
+                // An arrival is rare per env (once in a few hundred steps) but not per warp of 32 envs, and the kernel is
+                // one wave: the slowest warp sets the launch time.  So the WARP serves each of its reassigned envs
+                // together -- lane = agent for the roll-back / re-emission, lane = map row for the candidate scan --
+                // instead of 32 lanes re-walking their own env for the sake of one.
+                unsigned rw = __ballot_sync(full, pend != 0);
+                while (rw) {
+                    const int e = __ffs(rw) - 1;
+                    rw &= rw - 1;
+                    uint32_t pe = __shfl_sync(full, pend, e);
+                    const uint32_t mv_e = __shfl_sync(full, moved_m, e), bp_e = __shfl_sync(full, bprev_m, e);
+                    const uint32_t rc_e = __shfl_sync(full, rng_counter, e);
+                    const int slot_new_e = __shfl_sync(full, slot_new, e), slot_next_e = __shfl_sync(full, slot_next, e);
+                    const bool use_ring_e = __shfl_sync(full, (int)use_ring, e) != 0;
+                    const long long eg = p.env_id_base + (long long)(env0 + e);
+                    const size_t abe = (env0 + e) * (size_t)N, enve = env0 + e;
+                    uint32_t *occ_e = occ_w + e, *goal_e = (goalb - ew) + e, *rec_e = (rec - ew) + e;
+                    uint32_t rng_inc = 0, err_e = 0, ongoal_fix = 0;
+                    while (pe) {   // arrivals in agent order (ENV:284-304)
+                        const int i = __ffs(pe) - 1;
+                        pe &= pe - 1;
+                        // roll the env's occupancy board back to snapshot i: later movers leave their new cell, then re-take the old one
+                        const uint32_t later = mv_e & ~((2u << i) - 1u);
+                        const bool und = lane < N && ((later >> lane) & 1u);
+                        uint32_t nc = 0, oc = 0;
+                        if (und) {
+                            const uint32_t rv = rec_e[lane * 32];
+                            nc = rv & REC_CODE;
+                            oc = nc - (uint32_t)action_delta((rv >> 11) & 7u);
+                            atomicAnd(&occ_e[(nc >> 5) * 32], ~(1u << (nc & 31u)));
+                        }
+                        const uint32_t gold = code_of(p.goals[abe + i]);
+                        if (lane == 0) goal_e[(gold >> 5) * 32] &= ~(1u << (gold & 31u));   // ENV:288
+                        __syncwarp();
+                        if (und) atomicOr(&occ_e[(oc >> 5) * 32], 1u << (oc & 31u));
+                        __syncwarp();
+                        uint32_t ng = 0xFFFFFFFFu;
+                        if (p.goal_override) {
+                            const uint32_t ov = p.goal_override[abe + i];
+                            if (prow(ov) >= 0) ng = code_of(ov);
+                        }
+                        if (ng == 0xFFFFFFFFu) {   // candidates = free, unoccupied, nobody's goal; rows lane and lane + 32
+                            const uint32_t c0 = lane < R ? (freerow[lane] & ~occ_e[lane * 32] & ~goal_e[lane * 32]) : 0u;
+                            const uint32_t c1 = lane + 32 < R ? (freerow[lane + 32] & ~occ_e[(lane + 32) * 32] & ~goal_e[(lane + 32) * 32]) : 0u;
+                            const int n0 = __popc(c0), n1 = __popc(c1);
+                            int pre0 = n0, pre1 = n1;   // inclusive prefix sums over the lanes
+#pragma unroll
+                            for (int sft = 1; sft < 32; sft <<= 1) {
+                                const int v0 = __shfl_up_sync(full, pre0, sft), v1 = __shfl_up_sync(full, pre1, sft);
+                                if (lane >= sft) { pre0 += v0; pre1 += v1; }
+                            }
+                            const int tot0 = __shfl_sync(full, pre0, 31), n = tot0 + __shfl_sync(full, pre1, 31);
+                            int kk = -1;
+                            if (p.goal_rank) kk = p.goal_rank[abe + i];
+                            if (kk < 0 && n > 0) {
+                                const Philox ph(p.seed, eg);
+                                const uint4 x = ph(rc_e + rng_inc, (uint32_t)i, 0x474F414Cu /* "GOAL" */, 0);
+                                kk = (int)__umulhi(x.x, (uint32_t)n);
+                                rng_inc++;
+                            }
+                            if (n > 0 && kk < n) {   // row-major order: rows 0..31, then 32..63
+                                const bool hit0 = kk >= pre0 - n0 && kk < pre0;
+                                const bool hit1 = kk >= tot0 + pre1 - n1 && kk < tot0 + pre1;
+                                uint32_t mine = 0;
+                                if (hit0) mine = (uint32_t)(lane * 32) + __fns(c0, 0, kk - (pre0 - n0) + 1);
+                                if (hit1) mine = (uint32_t)((lane + 32) * 32) + __fns(c1, 0, kk - tot0 - (pre1 - n1) + 1);
+                                const unsigned hb = __ballot_sync(full, hit0 || hit1);
+                                ng = __shfl_sync(full, mine, __ffs(hb) - 1);
+                            } else {
+                                err_e |= MAPF_DEV_ERR_NO_GOAL_CELL;
+                            }
+                        }
+                        if (ng == 0xFFFFFFFFu) { ng = gold; ongoal_fix |= 1u << i; }   // no cell: the old goal stays, the agent is on it
+                        if (lane == 0) {
+                            goal_e[(ng >> 5) * 32] |= 1u << (ng & 31u);
+                            p.goals[abe + i] = packed_of(ng);
+                            if (p.lock_enabled) {   // ENV:591: distance to the NEW goal
+                                const uint32_t rv = rec_e[i * 32], code = rv & REC_CODE;
+                                const int dist = abs((int)(ng >> 5) - (int)(code >> 5)) + abs((int)(ng & 31u) - (int)(code & 31u));
+                                p.lock_dist[((size_t)enve * p.lw + slot_new_e) * N + i] = (int16_t)dist;
+                                if (use_ring_e) {
+                                    const int ring_old = (int)p.lock_dist[((size_t)enve * p.lw + slot_next_e) * N + i];
+                                    rec_e[i * 32] = (rv & 0xFFFFu) | ((uint32_t)(ring_old - dist) << 16);
+                                }
+                            }
+                        }
+                        // roll forward again
+                        if (und) atomicAnd(&occ_e[(oc >> 5) * 32], ~(1u << (oc & 31u)));
+                        __syncwarp();
+                        if (und) atomicOr(&occ_e[(nc >> 5) * 32], 1u << (nc & 31u));
+                        __syncwarp();
+                    }
+                    // ENV:565-575: everybody of this env shows the final state; lane = agent
+                    if (lane < N) {
+                        const uint32_t code = rec_e[lane * 32] & REC_CODE;
+                        const uint32_t gcode = code_of(p.goals[abe + lane]);
+                        const int r = (int)(code >> 5), c = (int)(code & 31u);
+                        const WB obst = lut[code];
+                        const int sa = c > SR ? c - SR : 0, sb2 = (c < SR ? SR - c : 0) + 2;
+                        const uint32_t *orow = occ_e + (r - SR) * 32, *grow = goal_e + (r - SR) * 32;
+                        uint32_t acc[(4 * V2 + 31) / 32 + 1];
+#pragma unroll
+                        for (int j = 0; j < (int)(sizeof(acc) / sizeof(acc[0])); ++j) acc[j] = 0;
+                        uint32_t blk_up = 0, blk_mid = 0, blk_dn = 0;
+#pragma unroll
+                        for (int wr = 0; wr < V; ++wr) {
+                            const uint32_t bx = orow[wr * 32], by = grow[wr * 32];
+                            const uint32_t o4 = (wr * V >= 2 ? (uint32_t)(obst >> (wr * V - 2)) : (uint32_t)(obst << 2)) & M4;
+                            const uint32_t MC = (wr == SR) ? (M4 & ~(4u << SR)) : M4;
+                            const uint32_t occ4 = ((bx >> sa) << sb2) & MC;
+                            const uint32_t agent4 = occ4 & ~o4, blk4 = occ4 | o4;
+                            const uint32_t g4 = ((by >> sa) << sb2) & M4 & ~blk4;
+                            if (wr == SR - 1) blk_up = blk4;
+                            if (wr == SR) blk_mid = blk4;
+                            if (wr == SR + 1) blk_dn = blk4;
+                            const uint32_t t = *reinterpret_cast<const uint32_t *>(t1b + o4) +
+                                               (*reinterpret_cast<const uint32_t *>(t1b + agent4) << 1) +
+                                               (*reinterpret_cast<const uint32_t *>(t1b + g4) << 2);
+                            const int bitpos = 4 * V * wr, wi = bitpos >> 5, sh = bitpos & 31;
+                            acc[wi] |= t << sh;
+                            if (sh + 4 * V > 32) acc[wi + 1] |= t >> (32 - sh);
+                        }
+                        const uint32_t am = 1u | ((~blk_up >> (2 + SR)) & 1u) << 1 | ((~blk_mid >> (2 + SR + 1)) & 1u) << 2 |
+                                            ((~blk_dn >> (2 + SR)) & 1u) << 3 | ((~blk_mid >> (2 + SR - 1)) & 1u) << 4;
+                        if (p.o_local_obs) {
+                            uint8_t *ob = p.o_local_obs + (abe + lane) * V2;
+#pragma unroll
+                            for (int n = 0; n < V2; ++n) ob[n] = (uint8_t)((acc[n >> 3] >> (4 * (n & 7))) & 0xFu);
+                            const int dr = (int)(gcode >> 5) - r + SR, dc = (int)(gcode & 31u) - c + SR;
+                            if ((unsigned)dr < (unsigned)V && (unsigned)dc < (unsigned)V) {   // own goal: code 3
+                                const int ci = dr * V + dc;
+                                const bool occ_other = (ci != CTR) && ((occ_e[(gcode >> 5) * 32] >> (gcode & 31u)) & 1u);
+                                if (!((obst >> ci) & 1) && !occ_other) ob[ci] = 3;
+                            }
+                        }
+                        if (p.o_action_mask) {
+#pragma unroll
+                            for (int k = 0; k < 5; ++k) p.o_action_mask[(abe + lane) * 5 + k] = (int8_t)((am >> k) & 1u);
+                        }
+                        if (p.o_goal_delta) {
+                            const int gi0 = (int)(gcode >> 5) - r + (R - 1), gi1 = (int)(gcode & 31u) - c + (C - 1) + 2 * R - 1;
+                            p.o_goal_delta[abe + lane] = make_float2(gdt[gi0], gdt[gi1]);
+                        }
+                        if (p.o_blocking_prev) p.o_blocking_prev[abe + lane] = (uint8_t)((bp_e >> lane) & 1u);
+                        if (p.sample_mode) {
+                            const uint4 rnd = sample_quad(p.seed, eg, lane >> 2, p.sample_counter);
+                            const uint32_t x = qget(rnd, lane & 3);
+                            const uint32_t na = p.sample_mode == 1 ? kth[am * 8 + __umulhi(x, (uint32_t)__popc(am))] : __umulhi(x, 5u);
+                            p.o_next_actions[abe + lane] = (int8_t)na;
+                        }
+                    }
+                    if (lane == e) { rng_counter += rng_inc; errs |= err_e; ongoal_m |= ongoal_fix; }
+                    __syncwarp();
+                }
+                continue;   // no re-walk
+            } else {
             // Arrivals are served in agent order.  The owner of agent i rolls its occupancy board back to snapshot i
             // (its own later moves undone), draws the new goal against the env's goal board, rolls forward again and
             // re-does the one piece of lock history that depends on the goal: the distance.
@@ -521,13 +677,14 @@ __global__ void __launch_bounds__(LPE == 1 ? 448 : 512, 1) mapf_step_env_kernel(
                 pend &= pend - 1;
                 __syncwarp();
             }
-            if (LPE > 1) {   // everybody shows the final state: take the board of the env's last lane
+            {   // everybody shows the final state: take the board of the env's last lane
                 __syncwarp();
                 const uint32_t *fin = occ_w + g0 + (LPE - 1);
                 if (sub != LPE - 1) for (int r = 0; r < E.board_rows; ++r) occ[r * 32] = fin[r * 32];
                 __syncwarp();
             }
             active = reassigned;
+            }
         }
         if (round == 2) {
             // ------------------------------------------------------------ epilogue: owner masks, locks, blocking, wait-for graph
