@@ -398,6 +398,7 @@ __global__ void __launch_bounds__(LPE == 1 ? 448 : 512, 1) mapf_step_env_kernel(
     const int slot_next = (lock_head + 1 == p.lw) ? 0 : lock_head + 1;
     const bool use_ring = p.lock_enabled && count_after >= p.lw && p.lw > 1;
 
+    uint32_t reached_m = 0, completed_m = 0, bprev_m = 0;   // agent_flags of the previous step (MAPF_AF_*), one bit per agent
     // ---------------------------------------------------------------- pre-pass: agent records and owner boards of the state before the step
     for (int j = lane; j < E.board_rows * EPW; j += 32) (goalb - ew)[j] = 0u;
     if (LPE > 1) { for (int j = lane; j < E.board_rows * EPW; j += 32) stage_w[j] = 0u; }   // shared old-occupancy board (stage is idle)
@@ -408,6 +409,10 @@ __global__ void __launch_bounds__(LPE == 1 ? 448 : 512, 1) mapf_step_env_kernel(
         const uint4 pq = ldq32<VEC>(p.positions, ab + i0, i0, N, ok, 0u);
         const uint4 gq = ldq32<VEC>(p.goals, ab + i0, i0, N, ok, 0u);
         const uint32_t act4 = p.actions ? ldq8<VEC>(reinterpret_cast<const uint8_t *>(p.actions), ab + i0, i0, N, ok) : 0u;
+        const uint32_t fl4 = ldq8<VEC>(p.agent_flags, ab + i0, i0, N, ok);
+        reached_m |= gather4(fl4, 0) << i0;      // MAPF_AF_REACHED
+        completed_m |= gather4(fl4, 1) << i0;    // MAPF_AF_COMPLETED_ONCE
+        bprev_m |= gather4(fl4, 2) << i0;        // MAPF_AF_BLOCKING_PREV
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             if (i0 + k < N) {
@@ -418,7 +423,7 @@ __global__ void __launch_bounds__(LPE == 1 ? 448 : 512, 1) mapf_step_env_kernel(
                 const uint32_t nbi = __byte_perm((uint32_t)CTR | ((uint32_t)(CTR - V) << 8) | ((uint32_t)(CTR + 1) << 16) |
                                                  ((uint32_t)(CTR + V) << 24), (uint32_t)(CTR - 1), (uint32_t)a) & 0xFFu;
                 const uint32_t tblocked = ((uint32_t)lut[code] >> nbi) & 1u;
-                rec[(i0 + k) * EPW] = code | ((uint32_t)a << 11) | (tblocked << 14);
+                rec[(i0 + k) * EPW] = code | ((uint32_t)a << 11) | (tblocked << 14) | (gcode << 16);   // goal rides in the (still unused) delta half
                 if (ok) {
                     if (LPE > 1) {
                         atomicOr(&stage_w[(code >> 5) * EPW + ew], 1u << (code & 31u));
@@ -451,7 +456,6 @@ __global__ void __launch_bounds__(LPE == 1 ? 448 : 512, 1) mapf_step_env_kernel(
     }
 
     uint32_t moved_m = 0, failed_m = 0, gstep_m = 0, ongoal_m = 0;
-    uint32_t reached_m = 0, completed_m = 0, bprev_m = 0;
     uint32_t Gd = 0, Md = 0, Fd = 0, Gl = 0, Ml = 0;
     uint32_t wf_m = 0, blocking_m = 0;
     bool reassigned = false, terminated = false, truncated = false, done = false, do_reset = false;
@@ -987,14 +991,11 @@ __global__ void __launch_bounds__(LPE == 1 ? 448 : 512, 1) mapf_step_env_kernel(
             uint32_t rv4[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) rv4[k] = (i0 + k < N) ? rec[(i0 + k) * EPW] : 0u;
-            uint4 gq = ldq32<VEC>(p.goals, ab + i0, i0, N, active, 0u);
+            uint4 gq = make_uint4(0, 0, 0, 0);
+            if (!stepmode) gq = ldq32<VEC>(p.goals, ab + i0, i0, N, active, 0u);   // round 0 takes the goals from the records
             uint4 gpq = make_uint4(0, 0, 0, 0), mvq = gpq, fmq = gpq;
             uint2 ringq = make_uint2(0u, 0u);
             if (stepmode) {
-                const uint32_t fl4 = ldq8<VEC>(p.agent_flags, ab + i0, i0, N, ok);
-                reached_m |= gather4(fl4, 0) << i0;      // MAPF_AF_REACHED
-                completed_m |= gather4(fl4, 1) << i0;    // MAPF_AF_COMPLETED_ONCE
-                bprev_m |= gather4(fl4, 2) << i0;        // MAPF_AF_BLOCKING_PREV
                 if (p.lock_enabled) {
                     gpq = ldq32<VEC>(p.lock_gp, ab + i0, i0, N, ok, 0u);
                     mvq = ldq32<VEC>(p.lock_mv, ab + i0, i0, N, ok, 0u);
@@ -1016,7 +1017,7 @@ __global__ void __launch_bounds__(LPE == 1 ? 448 : 512, 1) mapf_step_env_kernel(
                 if (i0 + k >= N) continue;
                 const uint32_t bit = 1u << (i0 + k);
                 uint32_t code = rv4[k] & REC_CODE;
-                const uint32_t gcode = code_of(qget(gq, k));
+                const uint32_t gcode = stepmode ? (rv4[k] >> 16) : code_of(qget(gq, k));
                 if (stepmode) {
                     const uint32_t ocode = code;
                     const uint32_t a = (rv4[k] >> 11) & 7u;
