@@ -44,7 +44,7 @@ KERNEL_NAMES = {1: "mapf_step_kernel<16,2> (lane-per-agent)", 2: "mapf_step_env_
 def default_traffic(kind: int):
     """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the step kernel at the default C3 shape, from the
     committed `ncu --set full` captures (profiles/README.md); None for other shapes."""
-    return {1: 54.3e6, 2: 80.2e6}.get(kind)
+    return {1: 54.3e6, 2: 75.3e6}.get(kind)
 
 
 def workload(args) -> tuple[dict, np.ndarray]:
