@@ -699,33 +699,29 @@ __global__ void __launch_bounds__(LPE == 1 ? 448 : 512, 1) mapf_step_env_kernel(
             if (LPE == 1) for (int r = 0; r < E.board_rows; ++r) goalb[r * EPW] = 0u;
             __syncwarp();
             if (ok) {
-                for (int q = sub; q < NQ; q += LPE) {
-                    uint32_t cq[4];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) cq[k] = (4 * q + k < N) ? (rec[(4 * q + k) * EPW] & REC_CODE) : 0u;   // 4 loads in flight
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const int i = 4 * q + k;
-                        if (i >= N) break;
-                        if (LPE > 1) {
-                            atomicOr(&rowm[((cq[k] >> 5) + PADR) * 32], 1u << i);
-                            atomicOr(&colm[((cq[k] & 31u) + PADR) * 32], 1u << i);
-                        } else {
-                            rowm[((cq[k] >> 5) + PADR) * 32] |= 1u << i;
-                            colm[((cq[k] & 31u) + PADR) * 32] |= 1u << i;
-                        }
+#pragma unroll 1
+                for (uint32_t m = own_m; m;) {
+                    const int i = __ffs(m) - 1;
+                    m &= m - 1;
+                    const uint32_t code = rec[i * EPW] & REC_CODE;
+                    if (LPE > 1) {
+                        atomicOr(&rowm[((code >> 5) + PADR) * 32], 1u << i);
+                        atomicOr(&colm[((code & 31u) + PADR) * 32], 1u << i);
+                    } else {
+                        rowm[((code >> 5) + PADR) * 32] |= 1u << i;
+                        colm[((code & 31u) + PADR) * 32] |= 1u << i;
                     }
                 }
             }
             __syncwarp();
             uint32_t coloc_any = 0, wf_alive = 0, flags_any = 0;   // flags_any: bit 0 deadlock, bit 1 livelock participant set found
             const uint32_t intent_m = allN & ~reached_m;  // ENV:619-621: only agents that have not (sticky-)reached press
-            // four agents per trip: their shared-memory lookups are independent, so the chains overlap
-            for (int q = sub; q < (ok ? NQ : 0); q += LPE)
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int i = 4 * q + k;
-                if (i >= N) break;
+            // a rolled loop on purpose: the launch is one pass over the code per warp, the instruction cache is a
+            // contended resource (stall_no_inst was 18 % with this loop unrolled by four)
+#pragma unroll 1
+            for (uint32_t om = ok ? own_m : 0u; om;) {
+                const int i = __ffs(om) - 1;
+                om &= om - 1;
                 const uint32_t bit = 1u << i;
                 const uint32_t rv = rec[i * EPW];
                 const uint32_t code = rv & REC_CODE;
