@@ -288,8 +288,7 @@ def run_b200(args, rank: int, local_rank: int, world: int):
     cout = nat.MapfOutputs(**{k: v.data_ptr() for k, v in host_out.items()})
     gen = torch.Generator().manual_seed(999 + rank)
     host_actions = [torch.randint(0, 5, (B, N), dtype=torch.int8, generator=gen).pin_memory() for _ in range(4)]
-    d2h = sum(v.numel() * v.element_size() for v in host_out.values())
-    h2d = host_actions[0].numel()
+    delivered = sum(v.numel() * v.element_size() for v in host_out.values())
     lib = nat.lib()
     Ke, We = max(3, min(K, 50)), 3
     torch.cuda.synchronize(dev)
@@ -304,6 +303,11 @@ def run_b200(args, rank: int, local_rank: int, world: int):
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t0
     checksum = float(host_out["reward"].sum())  # the step's result is really on the host
+    # bytes that crossed PCIe in one call (the big per-agent channels travel bit-packed and are expanded into the
+    # host arrays by the library's host threads inside the call; `delivered` is the size of the arrays filled)
+    c_h2d, c_d2h = C.c_int64(0), C.c_int64(0)
+    nat.check(lib.mapf_host_transfer_bytes(e2e_env._h, C.byref(c_h2d), C.byref(c_d2h)))
+    h2d, d2h = int(c_h2d.value), int(c_d2h.value)
 
     # ---- reduce over ranks (max time), metric all-reduce off the step path
     t = torch.tensor([ms_total, kernel_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
@@ -335,7 +339,10 @@ def run_b200(args, rank: int, local_rank: int, world: int):
                          "algorithmic_bytes_per_launch": alg_bytes, "bytes_per_agent_step": bytes_per_as,
                          "peak_source": peak_src},
             "e2e": {"value": world * B * N * Ke / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "steps": Ke, "api": "mapf_step_host (C ABI, pinned host buffers)",
+                    "d2h_bytes_per_step": d2h, "delivered_bytes_per_step": delivered, "steps": Ke,
+                    "api": "mapf_step_host (C ABI, pinned host buffers)",
+                    "transfer": ("bit-packed agent records over PCIe, expanded into the host arrays inside the call"
+                                 if d2h < delivered else "plain copies"),
                     "actions": "uniform random from pinned host buffers", "checksum": checksum},
             "gpu_launches": int(launches), "clocks": clocks, "step_kernel": {1: "lane", 2: "env"}.get(kind),
             "episode_metrics": {k: metrics[k] for k in ("episodes", "goals_reached_mean", "deadlock_steps_mean",

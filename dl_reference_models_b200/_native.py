@@ -17,6 +17,7 @@ REPO = PKG.parent
 CSRC = PKG / "csrc"
 LIB_PATH = Path(os.environ.get("MAPF_B200_LIB", PKG / "libmapf_b200.so"))
 SOURCES = (CSRC / "mapf_b200.cu", CSRC / "mapf_kernels.cuh", CSRC / "mapf_env_kernel.cuh", CSRC / "mapf_cte_kernel.cuh", CSRC / "mapf_policy_kernel.cuh",
+           CSRC / "mapf_pack_kernel.cuh", CSRC / "mapf_host_unpack.h", CSRC / "mapf_host_unpack.cpp",
            REPO / "include" / "mapf_b200.h")
 
 MAX_AGENTS = 32
@@ -116,7 +117,8 @@ def nvcc_command(out: Path = LIB_PATH) -> list[str]:
     return [
         nvcc, "-std=c++17", "-O3", "-shared", "-Xcompiler", "-fPIC",
         "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-        "-o", str(out), str(CSRC / "mapf_b200.cu"),
+        "-Xcompiler", "-pthread",
+        "-o", str(out), str(CSRC / "mapf_b200.cu"), str(CSRC / "mapf_host_unpack.cpp"),
     ]
 
 
@@ -173,6 +175,9 @@ def lib():
     L.mapf_observe_host.argtypes = [vp, C.POINTER(MapfOutputs)]
     L.mapf_reset_host.argtypes = [vp, vp, vp, vp, C.POINTER(MapfOutputs)]
     L.mapf_step_host.argtypes = [vp, vp, vp, vp, C.POINTER(MapfOutputs), i32]
+    L.mapf_host_transfer_bytes.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    L.mapf_packed_record_bytes.argtypes = [i32]
+    L.mapf_unpack_records.argtypes = [vp, C.c_int64, i32, i32, vp, vp, vp, vp, vp, vp, vp]
     L.mapf_flat_obs_dim.argtypes = [vp, i32, i32, i32]
     L.mapf_pack_flat_obs.argtypes = [vp, C.POINTER(MapfOutputs), i32, i32, i32, vp, vp]
     L.mapf_sample_masked_actions.argtypes = [vp, vp, vp, u64, vp]
@@ -204,6 +209,7 @@ EXPORTS = (
     "mapf_version", "mapf_last_error", "mapf_create", "mapf_destroy", "mapf_set_map",
     "mapf_state_nbytes", "mapf_bind_state", "mapf_alloc_state", "mapf_get_state_host",
     "mapf_set_state_host", "mapf_reset", "mapf_step", "mapf_reset_host", "mapf_step_host",
+    "mapf_host_transfer_bytes", "mapf_packed_record_bytes", "mapf_unpack_records",
     "mapf_observe", "mapf_observe_host",
     "mapf_flat_obs_dim", "mapf_pack_flat_obs", "mapf_sample_masked_actions",
     "mapf_sample_random_actions", "mapf_set_fused_sampler", "mapf_metrics_reduce", "mapf_poll_errors", "mapf_launch_count",

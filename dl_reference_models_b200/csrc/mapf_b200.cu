@@ -5,11 +5,14 @@
 #include "mapf_env_kernel.cuh"
 #include "mapf_cte_kernel.cuh"
 #include "mapf_policy_kernel.cuh"
+#include "mapf_pack_kernel.cuh"
+#include "mapf_host_unpack.h"
 
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <sched.h>
 #include <new>
 #include <string>
 #include <vector>
@@ -96,6 +99,8 @@ EnvKernelFn pick_env_step(int sr, bool vec, int lpe) {
 
 }  // namespace
 
+constexpr int kMaxHostSlices = 16;
+
 struct mapf_handle {
     mapf_config cfg;
     int G, SR, V2, LW;
@@ -129,6 +134,13 @@ struct mapf_handle {
     int32_t *io_goal_rank;
     uint8_t *io_reset_mask;
     mapf_outputs io_out;
+    // packed device->host transfer of mapf_step_host (mapf_pack_kernel.cuh / mapf_host_unpack.cpp)
+    bool pack_alloc;
+    uint8_t *d_packed, *h_packed;
+    mapf::HostPool *pool;
+    cudaEvent_t slice_ev[kMaxHostSlices];
+    float gdt_row[256], gdt_col[256];
+    int64_t last_h2d_bytes, last_d2h_bytes;
 };
 
 namespace {
@@ -339,6 +351,45 @@ int copy_outputs_back(mapf_handle *h, const mapf_outputs *host) {
     return MAPF_OK;
 }
 
+int host_threads_default() {
+    if (const char *ov = getenv("MAPF_HOST_THREADS")) {
+        const int v = atoi(ov);
+        if (v >= 1) return v > 64 ? 64 : v;
+    }
+    int n = 0;
+    cpu_set_t set;
+    if (sched_getaffinity(0, sizeof(set), &set) == 0) n = CPU_COUNT(&set);
+    if (n < 1) n = 1;
+    return n > 16 ? 16 : n;
+}
+
+// The bit-packed transfer applies when the four big per-agent channels are all requested, the integer goal
+// differences fit an int8 and the batch is big enough for the PCIe time to matter; MAPF_HOST_PACK=0 turns it off.
+bool host_pack_applies(const mapf_handle *h, const mapf_outputs *host) {
+    if (!host || !host->local_obs || !host->action_mask || !host->goal_delta || !host->reward) return false;
+    if (h->cfg.rows > 128 || h->cfg.cols > 128 || h->cfg.num_envs < 8192) return false;
+    if (const char *ov = getenv("MAPF_HOST_PACK")) return atoi(ov) != 0;
+    return true;
+}
+
+int ensure_pack(mapf_handle *h) {
+    if (h->pack_alloc) return MAPF_OK;
+    const size_t BN = (size_t)h->cfg.num_envs * h->cfg.num_agents;
+    const size_t bytes = BN * mapf::pack_record_bytes(h->V2) + 16;
+    CUDA_TRY(cudaMalloc(&h->d_packed, bytes));
+    CUDA_TRY(cudaMallocHost(&h->h_packed, bytes));
+    for (int i = 0; i < kMaxHostSlices; ++i) CUDA_TRY(cudaEventCreateWithFlags(&h->slice_ev[i], cudaEventDisableTiming));
+    const float den0 = (float)(h->cfg.rows - 1 > 1 ? h->cfg.rows - 1 : 1);
+    const float den1 = (float)(h->cfg.cols - 1 > 1 ? h->cfg.cols - 1 : 1);
+    for (int d = -128; d < 128; ++d) {  // the kernels' goal-delta table (mapf_kernels.cuh fill_goal_delta_table)
+        h->gdt_row[d + 128] = h->cfg.normalize_goal_delta ? (float)d / den0 : (float)d;
+        h->gdt_col[d + 128] = h->cfg.normalize_goal_delta ? (float)d / den1 : (float)d;
+    }
+    h->pool = mapf::host_pool_create(host_threads_default());
+    h->pack_alloc = true;
+    return MAPF_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -489,6 +540,11 @@ int mapf_destroy(mapf_handle *h) {
         cudaFree(h->io_actions); cudaFree(h->io_goal_override); cudaFree(h->io_starts_override);
         cudaFree(h->io_goals_override); cudaFree(h->io_goal_rank); cudaFree(h->io_reset_mask);
         for (int i = 0; i < 10; ++i) cudaFree(*output_member(&h->io_out, i));
+    }
+    if (h->pack_alloc) {
+        mapf::host_pool_destroy(h->pool);
+        cudaFree(h->d_packed); cudaFreeHost(h->h_packed);
+        for (int i = 0; i < kMaxHostSlices; ++i) cudaEventDestroy(h->slice_ev[i]);
     }
     if (h->hstream) cudaStreamDestroy(h->hstream);
     if (h->hstream2) cudaStreamDestroy(h->hstream2);
@@ -733,47 +789,123 @@ int mapf_step_host(mapf_handle *h, const int8_t *actions, const int16_t *goal_ov
     p.goal_override = goal_override ? h->io_goal_override : nullptr;
     p.goal_rank = goal_rank ? h->io_goal_rank : nullptr;
     p.auto_reset = auto_reset != 0;
-    // Big batches go through in slices on two streams: the device-to-host copies of slice c (the PCIe-bound part,
-    // ~43 B per agent) overlap the host-to-device copy and the kernel of slice c + 1.  Envs are independent and
-    // Philox is keyed by the global env id, so slicing does not change any result.  Measured on B200 / PCIe Gen5
-    // at 65 536 x 16: 1 / 2 / 4 / 8 slices -> 1.12 / 1.13 / 1.11 / 1.01 e9 agent-steps/s (the D2H copy is the floor).
-    int64_t slice = B;
-    if (B >= 8192) slice = ((B + 1) / 2 + 31) / 32 * 32;
+    // Big batches go through in slices on two streams: the device-to-host copies of slice c (the PCIe-bound part)
+    // overlap the host-to-device copy and the kernel of slice c + 1.  Envs are independent and Philox is keyed by
+    // the global env id, so slicing does not change any result.  When the four big per-agent channels are all
+    // requested they cross PCIe bit-packed (43 -> 14 B per agent at sensor range 2) and host threads expand slice c
+    // into the caller's arrays while slice c + 1 is in flight.
+    const bool packed = host_pack_applies(h, out_host);
+    if (packed) {
+        rc = ensure_pack(h);
+        if (rc) return rc;
+    }
+    int nslices = B >= 8192 ? 2 : 1;
+    if (packed) nslices = B >= 32768 ? 4 : 2;
     if (const char *ov = getenv("MAPF_HOST_SLICES")) {
         const int v = atoi(ov);
-        if (v >= 1) slice = ((B + v - 1) / v + 31) / 32 * 32;
+        if (v >= 1) nslices = v;
     }
+    if (nslices > kMaxHostSlices) nslices = kMaxHostSlices;
+    const int64_t slice = ((B + nslices - 1) / nslices + 31) / 32 * 32;
     int64_t n_out[10];
     output_sizes(h, n_out);
     mapf_outputs host_tmp;
     memset(&host_tmp, 0, sizeof(host_tmp));
     if (out_host) host_tmp = *out_host;
+    const int RS = mapf::pack_record_bytes(h->V2);
+    const float inv0 = h->cfg.normalize_goal_delta ? (float)(h->cfg.rows - 1 > 1 ? h->cfg.rows - 1 : 1) : 1.f;
+    const float inv1 = h->cfg.normalize_goal_delta ? (float)(h->cfg.cols - 1 > 1 ? h->cfg.cols - 1 : 1) : 1.f;
+    int64_t h2d = 0, d2h = 0;
     int c = 0;
     for (int64_t e0 = 0; e0 < B; e0 += slice, ++c) {
         const int64_t n = (B - e0 < slice) ? (B - e0) : slice;
         cudaStream_t st = (c & 1) ? h->hstream2 : h->hstream;
-        if (actions) CUDA_TRY(cudaMemcpyAsync(h->io_actions + e0 * N, actions + e0 * N, (size_t)(n * N), cudaMemcpyHostToDevice, st));
-        if (goal_override)
+        if (actions) {
+            CUDA_TRY(cudaMemcpyAsync(h->io_actions + e0 * N, actions + e0 * N, (size_t)(n * N), cudaMemcpyHostToDevice, st));
+            h2d += n * N;
+        }
+        if (goal_override) {
             CUDA_TRY(cudaMemcpyAsync(h->io_goal_override + e0 * N, goal_override + e0 * N * 2, (size_t)(n * N * 4),
                                      cudaMemcpyHostToDevice, st));
-        if (goal_rank)
+            h2d += n * N * 4;
+        }
+        if (goal_rank) {
             CUDA_TRY(cudaMemcpyAsync(h->io_goal_rank + e0 * N, goal_rank + e0 * N, (size_t)(n * N * 4), cudaMemcpyHostToDevice, st));
+            h2d += n * N * 4;
+        }
         if (slice >= B) {
             rc = launch(h, h->step_fn, p, st);
         } else {
             rc = launch_step_range(h, p, e0, (int)n, st);
         }
         if (rc) return rc;
+        if (packed) {
+            const int64_t a0 = e0 * N, na = n * N;
+            const int threads = 256;
+            mapf::mapf_pack_host_kernel<<<(unsigned)((na + threads - 1) / threads), threads, threads * RS + 4, st>>>(
+                h->io_out.local_obs + a0 * h->V2, h->io_out.action_mask + a0 * 5,
+                reinterpret_cast<const float2 *>(h->io_out.goal_delta) + a0, h->io_out.reward + a0,
+                host_tmp.blocking_prev ? h->io_out.blocking_prev + a0 : nullptr, h->d_packed + a0 * RS, na, h->V2, RS,
+                inv0, inv1);
+            CUDA_TRY(cudaGetLastError());
+            h->launches++;
+            CUDA_TRY(cudaMemcpyAsync(h->h_packed + a0 * RS, h->d_packed + a0 * RS, (size_t)(na * RS), cudaMemcpyDeviceToHost, st));
+            d2h += na * RS;
+        }
         for (int i = 0; i < 10; ++i) {
             char *dst = static_cast<char *>(*output_member(&host_tmp, i));
-            if (!dst) continue;
+            if (!dst || (packed && i < 5)) continue;
             const int64_t per_env = n_out[i] / B;
             CUDA_TRY(cudaMemcpyAsync(dst + e0 * per_env, static_cast<char *>(*output_member(&h->io_out, i)) + e0 * per_env,
                                      (size_t)(n * per_env), cudaMemcpyDeviceToHost, st));
+            d2h += n * per_env;
+        }
+        if (packed) CUDA_TRY(cudaEventRecord(h->slice_ev[c], st));
+    }
+    if (packed) {
+        c = 0;
+        for (int64_t e0 = 0; e0 < B; e0 += slice, ++c) {
+            const int64_t n = (B - e0 < slice) ? (B - e0) : slice;
+            CUDA_TRY(cudaEventSynchronize(h->slice_ev[c]));
+            mapf::UnpackJob job;
+            job.packed = h->h_packed + e0 * N * RS;
+            job.a0 = e0 * N; job.a1 = (e0 + n) * N;
+            job.V2 = h->V2; job.RS = RS;
+            job.obs = host_tmp.local_obs; job.mask = host_tmp.action_mask; job.goal_delta = host_tmp.goal_delta;
+            job.reward = host_tmp.reward; job.blocking_prev = host_tmp.blocking_prev;
+            job.gdt_row = h->gdt_row; job.gdt_col = h->gdt_col;
+            mapf::host_pool_unpack(h->pool, job);
         }
     }
     CUDA_TRY(cudaStreamSynchronize(h->hstream));
     if (c > 1) CUDA_TRY(cudaStreamSynchronize(h->hstream2));
+    h->last_h2d_bytes = h2d;
+    h->last_d2h_bytes = d2h;
+    return MAPF_OK;
+}
+
+int mapf_host_transfer_bytes(const mapf_handle *h, int64_t *h2d_bytes, int64_t *d2h_bytes) {
+    if (!h) return fail(MAPF_ERR_INVALID_ARG, "null handle");
+    if (h2d_bytes) *h2d_bytes = h->last_h2d_bytes;
+    if (d2h_bytes) *d2h_bytes = h->last_d2h_bytes;
+    return MAPF_OK;
+}
+
+int mapf_packed_record_bytes(int32_t v2) { return v2 >= 1 ? mapf::pack_record_bytes(v2) : 0; }
+
+int mapf_unpack_records(const uint8_t *packed, int64_t n_agents, int32_t v2, int32_t threads, uint8_t *local_obs,
+                        int8_t *action_mask, float *goal_delta, float *reward, uint8_t *blocking_prev,
+                        const float *gdt_row, const float *gdt_col) {
+    if (!packed || !local_obs || !action_mask || !goal_delta || !reward || !gdt_row || !gdt_col)
+        return fail(MAPF_ERR_INVALID_ARG, "null argument");
+    if (n_agents < 0 || v2 < 1 || threads < 1) return fail(MAPF_ERR_INVALID_ARG, "bad size");
+    mapf::HostPool *pool = mapf::host_pool_create(threads);
+    mapf::UnpackJob job;
+    job.packed = packed; job.a0 = 0; job.a1 = n_agents; job.V2 = v2; job.RS = mapf::pack_record_bytes(v2);
+    job.obs = local_obs; job.mask = action_mask; job.goal_delta = goal_delta; job.reward = reward;
+    job.blocking_prev = blocking_prev; job.gdt_row = gdt_row; job.gdt_col = gdt_col;
+    mapf::host_pool_unpack(pool, job);
+    mapf::host_pool_destroy(pool);
     return MAPF_OK;
 }
 

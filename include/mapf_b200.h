@@ -248,6 +248,20 @@ int mapf_reset_host(mapf_handle *h, const uint8_t *reset_mask, const int16_t *st
 int mapf_step_host(mapf_handle *h, const int8_t *actions, const int16_t *goal_override,
                    const int32_t *goal_rank, const mapf_outputs *out_host, int32_t auto_reset);
 
+/* mapf_step_host is PCIe-bound on big batches.  When local_obs, action_mask, goal_delta and reward are all
+ * requested (and num_envs >= 8192, rows/cols <= 128) those channels cross PCIe as one bit-packed record per
+ * agent (3 bits per window cell, 1 bit per mask entry, the integer goal difference, 2*reward) and host threads
+ * inside the call expand them into the caller's arrays -- the delivered arrays are bit for bit the same.
+ * MAPF_HOST_PACK=0 disables it, MAPF_HOST_THREADS / MAPF_HOST_SLICES tune it.
+ * mapf_host_transfer_bytes: bytes that actually crossed PCIe in the last mapf_step_host call. */
+int mapf_host_transfer_bytes(const mapf_handle *h, int64_t *h2d_bytes, int64_t *d2h_bytes);
+/* Record size, and the host-side expansion on its own (no GPU needed; used by the CPU test-suite):
+ * packed holds n_agents records; gdt_row / gdt_col are 256-entry tables indexed by (int8 difference + 128). */
+int mapf_packed_record_bytes(int32_t v2);
+int mapf_unpack_records(const uint8_t *packed, int64_t n_agents, int32_t v2, int32_t threads, uint8_t *local_obs,
+                        int8_t *action_mask, float *goal_delta, float *reward, uint8_t *blocking_prev,
+                        const float *gdt_row, const float *gdt_col);
+
 /* ENV:306-328: pack channels into float32 flat[B,N,D] (device pointers),
  * D = V*V + 2 + gdist + bp + 5*mask, component order of ENV:214-236. */
 int mapf_flat_obs_dim(const mapf_handle *h, int32_t include_goal_distance,

@@ -1,0 +1,100 @@
+"""mapf_step_host's bit-packed device->host transfer (csrc/mapf_pack_kernel.cuh + mapf_host_unpack.cpp):
+the arrays delivered to the host buffers are bit for bit those of an unpacked device-side step, for every sensor
+range, with and without goal-delta normalisation, with optional channels left out, for several thread / slice
+counts; and fewer bytes cross PCIe."""
+import ctypes as C
+
+import pytest
+
+from dl_reference_models_b200 import _native as nat
+
+pytestmark = pytest.mark.gpu
+
+OUT_KEYS = ("local_obs", "action_mask", "goal_delta", "blocking_prev", "reward", "terminated", "truncated",
+            "step_flags", "agent_step_flags", "info")
+
+
+def make(cfg, B):
+    from dl_reference_models_b200.batched_env import BatchedMapfEnv
+
+    return BatchedMapfEnv(cfg, B, "cuda:0")
+
+
+def transfer_bytes(env):
+    h2d, d2h = C.c_int64(0), C.c_int64(0)
+    nat.check(nat.lib().mapf_host_transfer_bytes(env._h, C.byref(h2d), C.byref(d2h)))
+    return h2d.value, d2h.value
+
+
+def run_host_vs_device(cfg, B, steps, want=OUT_KEYS):
+    import torch
+
+    a, b = make(cfg, B), make(cfg, B)
+    a.reset()
+    b.reset()
+    host = {k: torch.full_like(v, 111, device="cpu").pin_memory() for k, v in b.out.items()}
+    cout = nat.MapfOutputs(**{k: (host[k].data_ptr() if k in want else None) for k in nat.OUTPUT_FIELDS})
+    gen = torch.Generator().manual_seed(5)
+    for s in range(steps):
+        acts = torch.randint(0, 5, (B, a.N), dtype=torch.int8, generator=gen)
+        oa = a.step(acts.cuda(), auto_reset=True)
+        nat.check(nat.lib().mapf_step_host(b._h, C.c_void_p(acts.pin_memory().data_ptr()), None, None, C.byref(cout), 1))
+        for k in want:
+            assert torch.equal(getattr(oa, k).cpu(), host[k]), f"step {s}: {k}"
+    for k in a.state:
+        assert torch.equal(a.state[k], b.state[k]), f"state {k}"
+    return a, b
+
+
+def c3(**kw):
+    from dl_reference_models_b200 import maps
+
+    cfg = {"num_agents": 16, "sensor_range": 2, "steps_per_episode": 12, "lifelong_mapf": True, "seed": 4242,
+           "grid": maps.random_obstacle_grid(32, 32, 0.30, 2026, min_free=32)}
+    cfg.update(kw)
+    return cfg
+
+
+@pytest.mark.parametrize("sr", [1, 2, 3])
+@pytest.mark.parametrize("normalize", [True, False])
+def test_packed_transfer_is_exact(monkeypatch, sr, normalize):
+    monkeypatch.delenv("MAPF_HOST_PACK", raising=False)
+    B = 8192 + 96
+    cfg = c3(sensor_range=sr, normalize_goal_delta=normalize)
+    a, b = run_host_vs_device(cfg, B, 20)
+    v2 = (2 * sr + 1) ** 2
+    rs = nat.lib().mapf_packed_record_bytes(v2)
+    h2d, d2h = transfer_bytes(b)
+    assert h2d == B * 16
+    assert d2h == B * 16 * (rs + 1) + B * (3 + 64), "records + agent_step_flags + per-env channels"
+    assert rs < v2 + 5 + 8 + 4 + 1
+
+
+def test_packed_transfer_with_channels_left_out_and_odd_shapes(monkeypatch):
+    monkeypatch.delenv("MAPF_HOST_PACK", raising=False)
+    want = ("local_obs", "action_mask", "goal_delta", "reward", "terminated")
+    for slices, threads in (("1", "1"), ("5", "3"), ("16", "7")):
+        monkeypatch.setenv("MAPF_HOST_SLICES", slices)
+        monkeypatch.setenv("MAPF_HOST_THREADS", threads)
+        run_host_vs_device(c3(num_agents=7, lifelong_mapf=False), 8192 + 33, 14, want=want)
+    # a map wider than the env-per-thread kernel takes (the packed path does not depend on the step kernel)
+    from dl_reference_models_b200 import maps
+
+    monkeypatch.delenv("MAPF_HOST_SLICES", raising=False)
+    monkeypatch.delenv("MAPF_HOST_THREADS", raising=False)
+    grid = maps.random_obstacle_grid(40, 100, 0.2, 3, min_free=300)
+    run_host_vs_device({"num_agents": 12, "sensor_range": 2, "steps_per_episode": 9, "seed": 1, "grid": grid}, 8192, 12)
+
+
+def test_unpacked_path_still_there(monkeypatch):
+    """MAPF_HOST_PACK=0, a missing big channel, or a small batch: plain copies, same results."""
+    B = 8192 + 64
+    monkeypatch.setenv("MAPF_HOST_PACK", "0")
+    _, b = run_host_vs_device(c3(), B, 6)
+    assert transfer_bytes(b)[1] == B * 16 * 44 + B * 67
+    monkeypatch.delenv("MAPF_HOST_PACK")
+    want = ("local_obs", "action_mask", "reward", "blocking_prev")
+    _, b = run_host_vs_device(c3(), B, 6, want=want)
+    assert transfer_bytes(b)[1] == B * 16 * (25 + 5 + 4 + 1)
+    _, b = run_host_vs_device(c3(), 512, 6)
+    assert transfer_bytes(b)[1] == 512 * 16 * 44 + 512 * 67
