@@ -177,7 +177,7 @@ def lib():
     L.mapf_step_host.argtypes = [vp, vp, vp, vp, C.POINTER(MapfOutputs), i32]
     L.mapf_host_transfer_bytes.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.mapf_packed_record_bytes.argtypes = [i32]
-    L.mapf_unpack_records.argtypes = [vp, C.c_int64, i32, i32, vp, vp, vp, vp, vp, vp, vp]
+    L.mapf_unpack_records.argtypes = [vp, C.c_int64, i32, i32, vp, vp, vp, vp, C.c_float, C.c_float]
     L.mapf_flat_obs_dim.argtypes = [vp, i32, i32, i32]
     L.mapf_pack_flat_obs.argtypes = [vp, C.POINTER(MapfOutputs), i32, i32, i32, vp, vp]
     L.mapf_sample_masked_actions.argtypes = [vp, vp, vp, u64, vp]

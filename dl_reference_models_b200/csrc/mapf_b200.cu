@@ -8,6 +8,7 @@
 #include "mapf_pack_kernel.cuh"
 #include "mapf_host_unpack.h"
 
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -138,7 +139,8 @@ struct mapf_handle {
     bool pack_alloc;
     uint8_t *d_packed, *h_packed;
     mapf::HostPool *pool;
-    cudaEvent_t slice_ev[kMaxHostSlices];
+    uint32_t *h_tickets;   // pinned: slot c = number of the last step whose slice c has arrived on the host
+    uint32_t ticket_seq;
     float gdt_row[256], gdt_col[256];
     int64_t last_h2d_bytes, last_d2h_bytes;
 };
@@ -375,14 +377,15 @@ bool host_pack_applies(const mapf_handle *h, const mapf_outputs *host) {
 int ensure_pack(mapf_handle *h) {
     if (h->pack_alloc) return MAPF_OK;
     const size_t BN = (size_t)h->cfg.num_envs * h->cfg.num_agents;
-    const size_t bytes = BN * mapf::pack_record_bytes(h->V2) + 16;
+    const size_t bytes = BN * (mapf::pack_record_bytes(h->V2) + 1) + (size_t)h->cfg.num_envs * 3 + 64;
     CUDA_TRY(cudaMalloc(&h->d_packed, bytes));
     CUDA_TRY(cudaMallocHost(&h->h_packed, bytes));
-    for (int i = 0; i < kMaxHostSlices; ++i) CUDA_TRY(cudaEventCreateWithFlags(&h->slice_ev[i], cudaEventDisableTiming));
+    CUDA_TRY(cudaMallocHost(&h->h_tickets, (kMaxHostSlices + 1) * sizeof(uint32_t)));
+    memset(h->h_tickets, 0, (kMaxHostSlices + 1) * sizeof(uint32_t));
     const float den0 = (float)(h->cfg.rows - 1 > 1 ? h->cfg.rows - 1 : 1);
     const float den1 = (float)(h->cfg.cols - 1 > 1 ? h->cfg.cols - 1 : 1);
     for (int d = -128; d < 128; ++d) {  // the kernels' goal-delta table (mapf_kernels.cuh fill_goal_delta_table)
-        h->gdt_row[d + 128] = h->cfg.normalize_goal_delta ? (float)d / den0 : (float)d;
+        h->gdt_row[d + 128] = h->cfg.normalize_goal_delta ? (float)d / den0 : (float)d;  // d / 1 == d
         h->gdt_col[d + 128] = h->cfg.normalize_goal_delta ? (float)d / den1 : (float)d;
     }
     h->pool = mapf::host_pool_create(host_threads_default());
@@ -544,7 +547,7 @@ int mapf_destroy(mapf_handle *h) {
     if (h->pack_alloc) {
         mapf::host_pool_destroy(h->pool);
         cudaFree(h->d_packed); cudaFreeHost(h->h_packed);
-        for (int i = 0; i < kMaxHostSlices; ++i) cudaEventDestroy(h->slice_ev[i]);
+        cudaFreeHost(h->h_tickets);
     }
     if (h->hstream) cudaStreamDestroy(h->hstream);
     if (h->hstream2) cudaStreamDestroy(h->hstream2);
@@ -792,21 +795,67 @@ int mapf_step_host(mapf_handle *h, const int8_t *actions, const int16_t *goal_ov
     // Big batches go through in slices on two streams: the device-to-host copies of slice c (the PCIe-bound part)
     // overlap the host-to-device copy and the kernel of slice c + 1.  Envs are independent and Philox is keyed by
     // the global env id, so slicing does not change any result.  When the four big per-agent channels are all
-    // requested they cross PCIe bit-packed (43 -> 14 B per agent at sensor range 2) and host threads expand slice c
-    // into the caller's arrays while slice c + 1 is in flight.
+    // requested they cross PCIe bit-packed (42 -> 13 B per agent at sensor range 2) and host threads expand slice c
+    // into the caller's arrays while slice c + 1 is in flight (and while this thread is still enqueueing).
+    // MAPF_HOST_RAW_32NDS=k sends the last k/32 of the batch as plain copies behind the packed slices (for hosts
+    // with too few cores to keep up with PCIe; measured no gain on the 16-core B200 hosts, so 0 by default).
     const bool packed = host_pack_applies(h, out_host);
     if (packed) {
         rc = ensure_pack(h);
         if (rc) return rc;
     }
+    // slice sizes as weights: uniform by default; the packed path tapers them (small first slice: its records are
+    // on the wire early; small last slice: the expansion nobody overlaps is short).  MAPF_HOST_SLICES=n -> n
+    // uniform slices, MAPF_HOST_PLAN=w0,w1,... -> explicit weights.
+    int weights[kMaxHostSlices];
     int nslices = B >= 8192 ? 2 : 1;
-    if (packed) nslices = B >= 32768 ? 4 : 2;
+    for (int i = 0; i < kMaxHostSlices; ++i) weights[i] = 1;
+    if (packed && B >= 32768) {
+        // measured on B200 / PCIe Gen5 / 16 host cores at 65 536 x 16 (e9 agent-steps/s): 1,1 1.88 | 1,1,1,1 2.19 |
+        // 1,3,4,4,3,1 2.26 | 2,4,4,4,2 2.36 | 1,2,3,4,3,2,1 2.16
+        static const int taper[5] = {2, 4, 4, 4, 2};
+        nslices = 5;
+        for (int i = 0; i < 5; ++i) weights[i] = taper[i];
+    }
     if (const char *ov = getenv("MAPF_HOST_SLICES")) {
         const int v = atoi(ov);
-        if (v >= 1) nslices = v;
+        if (v >= 1) {
+            nslices = v > kMaxHostSlices ? kMaxHostSlices : v;
+            for (int i = 0; i < kMaxHostSlices; ++i) weights[i] = 1;
+        }
     }
-    if (nslices > kMaxHostSlices) nslices = kMaxHostSlices;
-    const int64_t slice = ((B + nslices - 1) / nslices + 31) / 32 * 32;
+    if (const char *ov = getenv("MAPF_HOST_PLAN")) {
+        int k = 0;
+        for (const char *q = ov; *q && k < kMaxHostSlices;) {
+            const int v = atoi(q);
+            if (v >= 1) weights[k++] = v;
+            while (*q && *q != ',') ++q;
+            if (*q == ',') ++q;
+        }
+        if (k >= 1) nslices = k;
+    }
+    int raw32 = 0;
+    if (const char *ov = getenv("MAPF_HOST_RAW_32NDS")) {
+        const int v = atoi(ov);
+        if (packed && v >= 0 && v <= 16) raw32 = v;
+    }
+    struct HostSlice { int64_t e0, n; bool packed; };
+    HostSlice plan[kMaxHostSlices + 1];
+    int S = 0;
+    const int64_t Bp = B - (B * raw32 / 32) / 32 * 32;  // envs [0, Bp): sliced (packed if applicable); [Bp, B): plain tail
+    {
+        int wsum = 0, wacc = 0;
+        for (int i = 0; i < nslices; ++i) wsum += weights[i];
+        int64_t e0 = 0;
+        for (int i = 0; i < nslices && e0 < Bp; ++i) {
+            wacc += weights[i];
+            int64_t e1 = (i == nslices - 1) ? Bp : (Bp * wacc / wsum + 31) / 32 * 32;
+            if (e1 > Bp) e1 = Bp;
+            if (e1 > e0) plan[S++] = HostSlice{e0, e1 - e0, packed};
+            e0 = e1;
+        }
+    }
+    if (Bp < B) plan[S++] = HostSlice{Bp, B - Bp, false};
     int64_t n_out[10];
     output_sizes(h, n_out);
     mapf_outputs host_tmp;
@@ -816,9 +865,12 @@ int mapf_step_host(mapf_handle *h, const int8_t *actions, const int16_t *goal_ov
     const float inv0 = h->cfg.normalize_goal_delta ? (float)(h->cfg.rows - 1 > 1 ? h->cfg.rows - 1 : 1) : 1.f;
     const float inv1 = h->cfg.normalize_goal_delta ? (float)(h->cfg.cols - 1 > 1 ? h->cfg.cols - 1 : 1) : 1.f;
     int64_t h2d = 0, d2h = 0;
-    int c = 0;
-    for (int64_t e0 = 0; e0 < B; e0 += slice, ++c) {
-        const int64_t n = (B - e0 < slice) ? (B - e0) : slice;
+    const uint32_t ticket = ++h->ticket_seq;
+    const bool trace = packed && getenv("MAPF_HOST_TRACE") != nullptr;
+    const int64_t t_begin = std::chrono::steady_clock::now().time_since_epoch().count();
+    if (packed) mapf::host_pool_begin(h->pool);
+    for (int c = 0; c < S; ++c) {
+        const int64_t e0 = plan[c].e0, n = plan[c].n;
         cudaStream_t st = (c & 1) ? h->hstream2 : h->hstream;
         if (actions) {
             CUDA_TRY(cudaMemcpyAsync(h->io_actions + e0 * N, actions + e0 * N, (size_t)(n * N), cudaMemcpyHostToDevice, st));
@@ -833,52 +885,96 @@ int mapf_step_host(mapf_handle *h, const int8_t *actions, const int16_t *goal_ov
             CUDA_TRY(cudaMemcpyAsync(h->io_goal_rank + e0 * N, goal_rank + e0 * N, (size_t)(n * N * 4), cudaMemcpyHostToDevice, st));
             h2d += n * N * 4;
         }
-        if (slice >= B) {
+        if (S == 1) {
             rc = launch(h, h->step_fn, p, st);
         } else {
             rc = launch_step_range(h, p, e0, (int)n, st);
         }
         if (rc) return rc;
-        if (packed) {
+        if (plan[c].packed) {
+            // one block, one DMA per slice: the three packed streams, then the requested byte channels as they are
             const int64_t a0 = e0 * N, na = n * N;
+            uint8_t *blk = h->d_packed + a0 * (RS + 1) + e0 * 3;
+            int64_t off = na * RS;
+            uint8_t *b_bp = nullptr, *b_env[3] = {nullptr, nullptr, nullptr};
+            if (host_tmp.blocking_prev) { b_bp = blk + off; off += na; }
+            for (int i = 5; i <= 7; ++i)
+                if (*output_member(&host_tmp, i)) { b_env[i - 5] = blk + off; off += n; }
             const int threads = 256;
             mapf::mapf_pack_host_kernel<<<(unsigned)((na + threads - 1) / threads), threads, threads * RS + 4, st>>>(
                 h->io_out.local_obs + a0 * h->V2, h->io_out.action_mask + a0 * 5,
-                reinterpret_cast<const float2 *>(h->io_out.goal_delta) + a0, h->io_out.reward + a0,
-                host_tmp.blocking_prev ? h->io_out.blocking_prev + a0 : nullptr, h->d_packed + a0 * RS, na, h->V2, RS,
-                inv0, inv1);
+                reinterpret_cast<const float2 *>(h->io_out.goal_delta) + a0, h->io_out.reward + a0, blk, na, h->V2,
+                inv0, inv1, h->io_out.blocking_prev + a0, b_bp, h->io_out.terminated + e0, b_env[0],
+                h->io_out.truncated + e0, b_env[1], h->io_out.step_flags + e0, b_env[2], n);
             CUDA_TRY(cudaGetLastError());
             h->launches++;
-            CUDA_TRY(cudaMemcpyAsync(h->h_packed + a0 * RS, h->d_packed + a0 * RS, (size_t)(na * RS), cudaMemcpyDeviceToHost, st));
-            d2h += na * RS;
+            CUDA_TRY(cudaMemcpyAsync(h->h_packed + (blk - h->d_packed), blk, (size_t)off, cudaMemcpyDeviceToHost, st));
+            d2h += off;
         }
         for (int i = 0; i < 10; ++i) {
             char *dst = static_cast<char *>(*output_member(&host_tmp, i));
-            if (!dst || (packed && i < 5)) continue;
+            if (!dst || (plan[c].packed && i <= 7)) continue;  // everything but agent_step_flags / info rides in the block
             const int64_t per_env = n_out[i] / B;
             CUDA_TRY(cudaMemcpyAsync(dst + e0 * per_env, static_cast<char *>(*output_member(&h->io_out, i)) + e0 * per_env,
                                      (size_t)(n * per_env), cudaMemcpyDeviceToHost, st));
             d2h += n * per_env;
         }
-        if (packed) CUDA_TRY(cudaEventRecord(h->slice_ev[c], st));
-    }
-    if (packed) {
-        c = 0;
-        for (int64_t e0 = 0; e0 < B; e0 += slice, ++c) {
-            const int64_t n = (B - e0 < slice) ? (B - e0) : slice;
-            CUDA_TRY(cudaEventSynchronize(h->slice_ev[c]));
+        if (plan[c].packed) {
+            // the slice's ticket: written into pinned host memory behind the block's copy; the host threads start on
+            // the job when they see it (no CUDA call, no event wait on their side)
+            mapf::mapf_ticket_kernel<<<1, 1, 0, st>>>(h->h_tickets + c, ticket);
+            CUDA_TRY(cudaGetLastError());
+            h->launches++;
+            const int64_t a0 = e0 * N, na = n * N;
+            const uint8_t *blk = h->h_packed + a0 * (RS + 1) + e0 * 3;
             mapf::UnpackJob job;
-            job.packed = h->h_packed + e0 * N * RS;
-            job.a0 = e0 * N; job.a1 = (e0 + n) * N;
-            job.V2 = h->V2; job.RS = RS;
+            job.packed = blk;
+            job.a0 = a0; job.a1 = a0 + na;
+            job.V2 = h->V2;
             job.obs = host_tmp.local_obs; job.mask = host_tmp.action_mask; job.goal_delta = host_tmp.goal_delta;
-            job.reward = host_tmp.reward; job.blocking_prev = host_tmp.blocking_prev;
+            job.reward = host_tmp.reward;
             job.gdt_row = h->gdt_row; job.gdt_col = h->gdt_col;
-            mapf::host_pool_unpack(h->pool, job);
+            job.den_row = inv0; job.den_col = inv1;
+            job.bytes_src = host_tmp.blocking_prev ? blk + na * RS : nullptr;
+            job.bytes_dst = host_tmp.blocking_prev;
+            if (!mapf::host_pool_submit(h->pool, job, h->h_tickets + c, ticket)) {
+                mapf::host_pool_finish(h->pool);
+                return fail(MAPF_ERR_STATE, "host expansion queue overflow");
+            }
+        }
+    }
+    const int64_t t_enq = std::chrono::steady_clock::now().time_since_epoch().count();
+    if (packed) {
+        if (!mapf::host_pool_finish(h->pool)) {  // this thread joins in; returns when every slice is expanded
+            const cudaError_t e = cudaDeviceSynchronize();
+            return fail(MAPF_ERR_CUDA, "mapf_step_host: a slice never arrived on the host (%s)", cudaGetErrorString(e));
+        }
+        for (int c = 0; c < S; ++c) {     // per-env byte channels: a few KB, copied here
+            if (!plan[c].packed) continue;
+            const int64_t e0 = plan[c].e0, n = plan[c].n, na = n * N;
+            const uint8_t *blk = h->h_packed + e0 * N * (RS + 1) + e0 * 3;
+            int64_t off = na * RS + (host_tmp.blocking_prev ? na : 0);
+            for (int i = 5; i <= 7; ++i)
+                if (void *dst = *output_member(&host_tmp, i)) {
+                    memcpy(static_cast<char *>(dst) + e0, blk + off, (size_t)n);
+                    off += n;
+                }
         }
     }
     CUDA_TRY(cudaStreamSynchronize(h->hstream));
-    if (c > 1) CUDA_TRY(cudaStreamSynchronize(h->hstream2));
+    if (S > 1) CUDA_TRY(cudaStreamSynchronize(h->hstream2));
+    if (trace) {  // where the time of one call went (microseconds since entry)
+        const int64_t t_end = std::chrono::steady_clock::now().time_since_epoch().count();
+        fprintf(stderr, "mapf_step_host: enqueued %.0f", (t_enq - t_begin) * 1e-3);
+        int q = 0;
+        for (int c = 0; c < S; ++c) {
+            if (!plan[c].packed) continue;
+            int64_t f = 0, l = 0;
+            mapf::host_pool_job_times(h->pool, q++, &f, &l);
+            fprintf(stderr, " | slice %d (%lld envs) %.0f-%.0f", c, (long long)plan[c].n, (f - t_begin) * 1e-3, (l - t_begin) * 1e-3);
+        }
+        fprintf(stderr, " | done %.0f us\n", (t_end - t_begin) * 1e-3);
+    }
     h->last_h2d_bytes = h2d;
     h->last_d2h_bytes = d2h;
     return MAPF_OK;
@@ -894,16 +990,21 @@ int mapf_host_transfer_bytes(const mapf_handle *h, int64_t *h2d_bytes, int64_t *
 int mapf_packed_record_bytes(int32_t v2) { return v2 >= 1 ? mapf::pack_record_bytes(v2) : 0; }
 
 int mapf_unpack_records(const uint8_t *packed, int64_t n_agents, int32_t v2, int32_t threads, uint8_t *local_obs,
-                        int8_t *action_mask, float *goal_delta, float *reward, uint8_t *blocking_prev,
-                        const float *gdt_row, const float *gdt_col) {
-    if (!packed || !local_obs || !action_mask || !goal_delta || !reward || !gdt_row || !gdt_col)
-        return fail(MAPF_ERR_INVALID_ARG, "null argument");
-    if (n_agents < 0 || v2 < 1 || threads < 1) return fail(MAPF_ERR_INVALID_ARG, "bad size");
+                        int8_t *action_mask, float *goal_delta, float *reward, float den_row, float den_col) {
+    if (!packed || !local_obs || !action_mask || !goal_delta || !reward) return fail(MAPF_ERR_INVALID_ARG, "null argument");
+    if (n_agents < 0 || (v2 != 9 && v2 != 25 && v2 != 49) || threads < 1 || !(den_row > 0.f) || !(den_col > 0.f))
+        return fail(MAPF_ERR_INVALID_ARG, "bad argument (v2 must be 9, 25 or 49; denominators > 0)");
+    float gdt_row[256], gdt_col[256];
+    for (int d = -128; d < 128; ++d) {
+        gdt_row[d + 128] = (float)d / den_row;
+        gdt_col[d + 128] = (float)d / den_col;
+    }
     mapf::HostPool *pool = mapf::host_pool_create(threads);
     mapf::UnpackJob job;
-    job.packed = packed; job.a0 = 0; job.a1 = n_agents; job.V2 = v2; job.RS = mapf::pack_record_bytes(v2);
+    job.packed = packed; job.a0 = 0; job.a1 = n_agents; job.V2 = v2;
     job.obs = local_obs; job.mask = action_mask; job.goal_delta = goal_delta; job.reward = reward;
-    job.blocking_prev = blocking_prev; job.gdt_row = gdt_row; job.gdt_col = gdt_col;
+    job.gdt_row = gdt_row; job.gdt_col = gdt_col; job.den_row = den_row; job.den_col = den_col;
+    job.bytes_src = nullptr; job.bytes_dst = nullptr;
     mapf::host_pool_unpack(pool, job);
     mapf::host_pool_destroy(pool);
     return MAPF_OK;

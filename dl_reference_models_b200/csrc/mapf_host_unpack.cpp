@@ -7,6 +7,7 @@
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <thread>
@@ -43,92 +44,266 @@ inline uint64_t spread1_generic(uint32_t m) {  // 5 bits -> 5 bytes of 0/1
     return x;
 }
 
-// One body, two instantiations: the BMI2 one (pdep does an 8-cell expansion in one instruction) is compiled with
-// the target attribute and only called when the CPU reports the extension.
-#define MAPF_UNPACK_BODY(SPREAD3, SPREAD1)                                                        \
-    const int V2 = j.V2, RS = j.RS, nfull = V2 >> 3, rem = V2 & 7;                                \
-    const int tail_bytes = (rem * 3 + 5 + 7) / 8;                                                 \
-    for (int64_t a = b0; a < b1; ++a) {                                                           \
-        const uint8_t *r = j.packed + (a - j.a0) * RS;                                            \
-        uint8_t *o = j.obs + a * V2;                                                              \
-        for (int c = 0; c < nfull; ++c) {                                                         \
-            uint32_t w;                                                                           \
-            memcpy(&w, r, 4); /* 3 payload bytes; the 4th belongs to the record's tail */         \
-            const uint64_t x = SPREAD3(w & 0xFFFFFFu);                                            \
-            memcpy(o + 8 * c, &x, 8);                                                             \
-            r += 3;                                                                               \
+// the three streams of a slice's packed block (layout: mapf_host_unpack.h) and the output arrays, all at agent b0
+struct Cursor {
+    const uint8_t *bits;  // window + mask bits, pack_obs_bytes(V2) per agent
+    const int8_t *diff;   // (d_row, d_col) per agent
+    const int8_t *rew2;   // 2 * reward per agent
+    uint8_t *obs;
+    int8_t *mask;
+    float *gd, *rw;
+};
+
+// Scalar expansion of n agents.  One body, two instantiations: the BMI2 one (pdep expands 8 cells in one
+// instruction) carries the target attribute and is only called when the CPU reports the extension.  Window sizes
+// are 9 / 25 / 49 (sensor range 1..3): always whole 8-cell chunks plus one cell that shares a byte with the mask.
+#define MAPF_UNPACK_SCALAR(NAME, ATTR, SPREAD3, SPREAD1)                                          \
+    ATTR void NAME(int V2, Cursor c, int64_t n, const float *gr, const float *gc) {               \
+        const int nfull = V2 >> 3, PB = nfull * 3 + 1;                                            \
+        for (int64_t a = 0; a < n; ++a) {                                                         \
+            for (int k = 0; k < nfull; ++k) {                                                     \
+                uint32_t w = (uint32_t)c.bits[3 * k] | ((uint32_t)c.bits[3 * k + 1] << 8) |       \
+                             ((uint32_t)c.bits[3 * k + 2] << 16);                                 \
+                const uint64_t x = SPREAD3(w);                                                    \
+                memcpy(c.obs + 8 * k, &x, 8);                                                     \
+            }                                                                                     \
+            const uint32_t t = c.bits[3 * nfull];                                                 \
+            c.obs[8 * nfull] = (uint8_t)(t & 7u);                                                 \
+            const uint64_t mx = SPREAD1(t >> 3);                                                  \
+            memcpy(c.mask, &mx, 5);                                                               \
+            c.gd[0] = gr[c.diff[0]];                                                              \
+            c.gd[1] = gc[c.diff[1]];                                                              \
+            c.rw[0] = 0.5f * (float)c.rew2[0];                                                    \
+            c.bits += PB; c.diff += 2; c.rew2 += 1; c.obs += V2; c.mask += 5; c.gd += 2; c.rw += 1; \
         }                                                                                         \
-        uint32_t w;                                                                               \
-        memcpy(&w, r, 4);                                                                         \
-        for (int i = 0; i < rem; ++i) o[nfull * 8 + i] = (uint8_t)((w >> (3 * i)) & 7u);          \
-        const uint64_t mx = SPREAD1((w >> (3 * rem)) & 31u);                                      \
-        memcpy(j.mask + a * 5, &mx, 5);                                                           \
-        r += tail_bytes;                                                                          \
-        j.goal_delta[2 * a] = j.gdt_row[(int)(int8_t)r[0] + 128];                                 \
-        j.goal_delta[2 * a + 1] = j.gdt_col[(int)(int8_t)r[1] + 128];                             \
-        j.reward[a] = 0.5f * (float)(int8_t)r[2];                                                 \
-        if (j.blocking_prev) j.blocking_prev[a] = r[3];                                           \
     }
 
-void unpack_range_generic(const UnpackJob &j, int64_t b0, int64_t b1) {
-    MAPF_UNPACK_BODY(spread3_generic, spread1_generic)
-}
+MAPF_UNPACK_SCALAR(unpack_scalar_generic, , spread3_generic, spread1_generic)
 
 #if MAPF_X86
 #define MAPF_PDEP3(w) _pdep_u64((w), 0x0707070707070707ULL)
 #define MAPF_PDEP1(m) _pdep_u64((m), 0x0101010101ULL)
-__attribute__((target("bmi2"))) void unpack_range_bmi2(const UnpackJob &j, int64_t b0, int64_t b1) {
-    MAPF_UNPACK_BODY(MAPF_PDEP3, MAPF_PDEP1)
+MAPF_UNPACK_SCALAR(unpack_scalar_bmi2, __attribute__((target("bmi2"))), MAPF_PDEP3, MAPF_PDEP1)
+
+// AVX-512 VBMI expansion.  An agent's bits are laid out as nfull + 1 quadwords (one per 3-byte chunk, one for the
+// tail byte) by a byte permute, vpmultishiftqb pulls the 3-bit / 1-bit fields to byte positions, and a second
+// permute compacts windows and masks of 8 / (nfull + 1) agents for two masked stores -- 7 instructions per group
+// instead of ~25 per agent.  Goal differences and rewards go 16 agents at a time (convert, IEEE divide / multiply:
+// the same float values as the kernels' table).
+struct VbmiPlan {
+    alignas(64) uint8_t gather[64], shift[64], keep[64], obs_idx[64], mask_idx[64];
+    int agents;            // agents per 64-byte group
+    uint64_t load_mask, obs_mask, mask_mask;
+};
+
+VbmiPlan make_vbmi_plan(int V2) {
+    VbmiPlan p;
+    memset(&p, 0, sizeof(p));
+    const int nfull = V2 >> 3, QA = nfull + 1, PB = nfull * 3 + 1;
+    p.agents = 8 / QA;
+    for (int k = 0; k < p.agents; ++k) {
+        for (int q = 0; q < QA; ++q)
+            for (int j = 0; j < 8; ++j) {
+                const int at = (k * QA + q) * 8 + j;
+                if (q < nfull) {
+                    p.gather[at] = (uint8_t)(k * PB + q * 3 + (j < 3 ? j : 2));
+                    p.shift[at] = (uint8_t)(3 * j);
+                    p.keep[at] = 7;
+                } else {  // tail byte: cell V2-1 in bits 0..2, mask entries in bits 3..7
+                    p.gather[at] = (uint8_t)(k * PB + 3 * nfull);
+                    p.shift[at] = (uint8_t)(j == 0 ? 0 : (j <= 5 ? 2 + j : 0));
+                    p.keep[at] = (uint8_t)(j == 0 ? 7 : (j <= 5 ? 1 : 0));
+                }
+            }
+        for (int i = 0; i < V2; ++i) p.obs_idx[k * V2 + i] = (uint8_t)(k * QA * 8 + i);
+        for (int m = 0; m < 5; ++m) p.mask_idx[k * 5 + m] = (uint8_t)(k * QA * 8 + nfull * 8 + 1 + m);
+    }
+    auto low = [](int n) { return n >= 64 ? ~0ULL : ((1ULL << n) - 1); };
+    p.load_mask = low(p.agents * PB);
+    p.obs_mask = low(p.agents * V2);
+    p.mask_mask = low(p.agents * 5);
+    return p;
+}
+
+__attribute__((target("avx512f,avx512bw,avx512vl,avx512vbmi,bmi2")))
+void unpack_vbmi(int V2, Cursor c, int64_t n, const float *gr, const float *gc, float den_row, float den_col) {
+    const VbmiPlan p = make_vbmi_plan(V2);
+    const int PB = (V2 >> 3) * 3 + 1, G = p.agents;
+    const __m512i gather = _mm512_load_si512(p.gather), shift = _mm512_load_si512(p.shift),
+                  keep = _mm512_load_si512(p.keep), obs_idx = _mm512_load_si512(p.obs_idx),
+                  mask_idx = _mm512_load_si512(p.mask_idx);
+    const int64_t groups = n / G;
+    for (int64_t g = 0; g < groups; ++g) {
+        const __m512i raw = _mm512_maskz_loadu_epi8(p.load_mask, c.bits + g * G * PB);
+        const __m512i quads = _mm512_permutexvar_epi8(gather, raw);
+        const __m512i cells = _mm512_and_si512(_mm512_multishift_epi64_epi8(shift, quads), keep);
+        _mm512_mask_storeu_epi8(c.obs + g * G * V2, p.obs_mask, _mm512_permutexvar_epi8(obs_idx, cells));
+        _mm512_mask_storeu_epi8(c.mask + g * G * 5, p.mask_mask, _mm512_permutexvar_epi8(mask_idx, cells));
+    }
+    // den_row > 0: normalised goal delta = difference / denominator (IEEE division, the kernels' table values)
+    alignas(64) float dv[16];
+    for (int i = 0; i < 16; ++i) dv[i] = (i & 1) ? den_col : den_row;
+    const __m512 denv = _mm512_load_ps(dv);
+    const __m512 half = _mm512_set1_ps(0.5f);
+    const int64_t n16 = n / 16;
+    for (int64_t b = 0; b < n16; ++b) {
+        const __m256i d = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(c.diff + b * 32));
+        const __m512 lo = _mm512_cvtepi32_ps(_mm512_cvtepi8_epi32(_mm256_castsi256_si128(d)));
+        const __m512 hi = _mm512_cvtepi32_ps(_mm512_cvtepi8_epi32(_mm256_extracti128_si256(d, 1)));
+        _mm512_storeu_ps(c.gd + b * 32, _mm512_div_ps(lo, denv));
+        _mm512_storeu_ps(c.gd + b * 32 + 16, _mm512_div_ps(hi, denv));
+        const __m128i r = _mm_loadu_si128(reinterpret_cast<const __m128i *>(c.rew2 + b * 16));
+        _mm512_storeu_ps(c.rw + b * 16, _mm512_mul_ps(_mm512_cvtepi32_ps(_mm512_cvtepi8_epi32(r)), half));
+    }
+    // left-overs: windows / masks of the last n % G agents, goal deltas / rewards of the last n % 16
+    {
+        Cursor t = c;
+        const int64_t done = groups * G;
+        t.bits += done * PB; t.obs += done * V2; t.mask += done * 5;
+        alignas(8) float sink_gd[2 * 8], sink_rw[8];
+        alignas(8) int8_t zero[2 * 8] = {0};
+        for (int64_t a = done; a < n; ++a) {
+            Cursor one = t;
+            one.diff = zero; one.rew2 = zero; one.gd = sink_gd; one.rw = sink_rw;
+            unpack_scalar_bmi2(V2, one, 1, gr, gc);
+            t.bits += PB; t.obs += V2; t.mask += 5;
+        }
+        for (int64_t a = n16 * 16; a < n; ++a) {
+            c.gd[2 * a] = gr[c.diff[2 * a]];
+            c.gd[2 * a + 1] = gc[c.diff[2 * a + 1]];
+            c.rw[a] = 0.5f * (float)c.rew2[a];
+        }
+    }
 }
 #endif
 
+constexpr int kBlock = 64;  // chunk boundaries fall on whole 64-agent blocks
+
+enum { ISA_GENERIC = 0, ISA_BMI2 = 1, ISA_VBMI = 2 };
+
+// Agents [b0, b1) of the job.  (Expanding into an L1-resident block and streaming it out with non-temporal
+// stores was measured too: slower than plain stores on the B200 hosts, 1.77e9 vs 2.08e9 agent-steps/s end to end.)
+void unpack_agents(const UnpackJob &j, int64_t b0, int64_t b1, int isa) {
+    const int V2 = j.V2, PB = pack_obs_bytes(V2);
+    const int64_t na = j.a1 - j.a0, off = b0 - j.a0;
+    Cursor c;
+    c.bits = j.packed + off * PB;
+    c.diff = reinterpret_cast<const int8_t *>(j.packed + na * PB) + off * 2;
+    c.rew2 = reinterpret_cast<const int8_t *>(j.packed + na * (PB + 2)) + off;
+    c.obs = j.obs + b0 * V2; c.mask = j.mask + b0 * 5; c.gd = j.goal_delta + b0 * 2; c.rw = j.reward + b0;
+    const float *gr = j.gdt_row + 128, *gc = j.gdt_col + 128;
+    if (j.bytes_src) memcpy(j.bytes_dst + b0, j.bytes_src + off, (size_t)(b1 - b0));
+#if MAPF_X86
+    if (isa == ISA_VBMI) return unpack_vbmi(V2, c, b1 - b0, gr, gc, j.den_row, j.den_col);
+    if (isa == ISA_BMI2) return unpack_scalar_bmi2(V2, c, b1 - b0, gr, gc);
+#endif
+    unpack_scalar_generic(V2, c, b1 - b0, gr, gc);
+}
+
 }  // namespace
+
+// A step is a short queue of jobs (one per slice).  The caller's thread submits job c right after it has enqueued
+// slice c's GPU work and goes on enqueueing; the workers take the jobs in order, each job only once its slice has
+// arrived -- signalled by a 32-bit ticket the GPU writes into pinned host memory behind the slice's copy (no CUDA
+// call on a worker thread).  Workers spin for a while after a step (the slices of one step, and back-to-back steps,
+// arrive within ~100 us), then sleep on a condition variable.
+constexpr int kMaxJobs = 32;
+
+struct QueuedJob {
+    UnpackJob job{};
+    std::atomic<const volatile uint32_t *> ticket{nullptr};
+    std::atomic<uint32_t> ticket_value{0};
+    // chunk claims carry the step number in the upper half: a worker that is late by a whole step can never claim
+    // a chunk of a job whose ticket it has not waited for
+    std::atomic<uint64_t> next{0};
+    std::atomic<int> done{0};
+    std::atomic<int64_t> t_first{0}, t_last{0};  // trace: first chunk claimed / last chunk done (steady_clock ns)
+};
 
 struct HostPool {
     int nthreads = 1, nchunks = 1;
-    bool bmi2 = false;
+    int isa = ISA_GENERIC;
     std::vector<std::thread> workers;
     std::mutex mu;
     std::condition_variable cv;
-    std::atomic<uint64_t> generation{0};
-    std::atomic<int> next{0}, done{0};
-    std::atomic<bool> stop{false};
-    UnpackJob job{};
+    std::atomic<uint64_t> epoch{0};       // one per step
+    std::atomic<int> published{0};        // jobs of this step submitted so far
+    std::atomic<bool> closed{true};       // no more jobs will be submitted this step
+    std::atomic<int> sleepers{0};
+    std::atomic<bool> stop{false}, failed{false};
+    QueuedJob jobs[kMaxJobs];
 
-    void run_chunks() {
+    void run_job(QueuedJob &q) {
+        const uint64_t tag = q.next.load(std::memory_order_acquire) >> 32;
+        const volatile uint32_t *ticket = q.ticket.load(std::memory_order_relaxed);
+        const uint32_t want = q.ticket_value.load(std::memory_order_relaxed);
+        if (ticket) {
+            const auto t0 = std::chrono::steady_clock::now();
+            uint32_t polls = 0;
+            while (*ticket != want) {
+                if (stop.load(std::memory_order_relaxed) || failed.load(std::memory_order_relaxed) ||
+                    (q.next.load(std::memory_order_relaxed) >> 32) != tag)
+                    return;
+                // a ticket that never comes means the GPU work in front of it failed: give up instead of hanging
+                if ((++polls & 0xFFFFu) == 0 && std::chrono::steady_clock::now() - t0 > std::chrono::seconds(20)) {
+                    failed.store(true, std::memory_order_release);
+                    return;
+                }
+                cpu_relax();
+            }
+            std::atomic_thread_fence(std::memory_order_acquire);
+        }
         for (;;) {
-            const int c = next.fetch_add(1, std::memory_order_acq_rel);
-            if (c >= nchunks) return;
-            const int64_t n = job.a1 - job.a0;
-            const int64_t b0 = job.a0 + n * c / nchunks, b1 = job.a0 + n * (c + 1) / nchunks;
-#if MAPF_X86
-            if (bmi2) unpack_range_bmi2(job, b0, b1); else
-#endif
-            unpack_range_generic(job, b0, b1);
-            done.fetch_add(1, std::memory_order_acq_rel);
+            uint64_t v = q.next.load(std::memory_order_acquire);
+            int c = -1;
+            while ((v >> 32) == tag && (int)(v & 0xFFFFFFFFu) < nchunks) {
+                if (q.next.compare_exchange_weak(v, v + 1, std::memory_order_acq_rel)) { c = (int)(v & 0xFFFFFFFFu); break; }
+            }
+            if (c < 0) return;
+            if (c == 0) q.t_first.store(std::chrono::steady_clock::now().time_since_epoch().count(), std::memory_order_relaxed);
+            const UnpackJob &job = q.job;
+            const int64_t n = job.a1 - job.a0, nblk = (n + kBlock - 1) / kBlock;
+            int64_t b0 = job.a0 + kBlock * (nblk * c / nchunks), b1 = job.a0 + kBlock * (nblk * (c + 1) / nchunks);
+            if (b1 > job.a1) b1 = job.a1;
+            if (b0 < b1) unpack_agents(job, b0, b1, isa);
+            if (q.done.fetch_add(1, std::memory_order_acq_rel) + 1 == nchunks)
+                q.t_last.store(std::chrono::steady_clock::now().time_since_epoch().count(), std::memory_order_relaxed);
+        }
+    }
+
+    // take this step's jobs in order until the step is closed and every published job has been visited
+    void run_step() {
+        for (int q = 0; q < kMaxJobs; ++q) {
+            while (published.load(std::memory_order_acquire) <= q) {
+                if (closed.load(std::memory_order_acquire) && published.load(std::memory_order_acquire) <= q) return;
+                if (stop.load(std::memory_order_relaxed)) return;
+                cpu_relax();
+            }
+            run_job(jobs[q]);
         }
     }
 
     void worker() {
         uint64_t seen = 0;
         for (;;) {
-            // spin for a while (the slices of one step, and back-to-back steps, arrive within ~100 us), then sleep
             const auto t0 = std::chrono::steady_clock::now();
             int polls = 0;
-            while (generation.load(std::memory_order_acquire) == seen && !stop.load(std::memory_order_acquire)) {
+            while (epoch.load(std::memory_order_acquire) == seen && !stop.load(std::memory_order_acquire)) {
                 cpu_relax();
                 if ((++polls & 255) == 0 &&
                     std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(400)) {
                     std::unique_lock<std::mutex> lk(mu);
+                    sleepers.fetch_add(1, std::memory_order_acq_rel);
                     cv.wait(lk, [&] {
-                        return generation.load(std::memory_order_acquire) != seen || stop.load(std::memory_order_acquire);
+                        return epoch.load(std::memory_order_acquire) != seen || stop.load(std::memory_order_acquire);
                     });
+                    sleepers.fetch_sub(1, std::memory_order_acq_rel);
                     break;
                 }
             }
             if (stop.load(std::memory_order_acquire)) return;
-            seen = generation.load(std::memory_order_acquire);
-            run_chunks();
+            seen = epoch.load(std::memory_order_acquire);
+            run_step();
         }
     }
 };
@@ -136,11 +311,17 @@ struct HostPool {
 HostPool *host_pool_create(int threads) {
     HostPool *p = new HostPool();
     p->nthreads = threads < 1 ? 1 : threads;
-    p->nchunks = p->nthreads * 4;  // fixed for the pool's lifetime (late wakers can never claim a stale chunk)
+    p->nchunks = p->nthreads * 4;  // fixed for the pool's lifetime
 #if MAPF_X86
-    p->bmi2 = __builtin_cpu_supports("bmi2");
+    if (__builtin_cpu_supports("bmi2")) p->isa = ISA_BMI2;
+    if (p->isa == ISA_BMI2 && __builtin_cpu_supports("avx512vbmi") && __builtin_cpu_supports("avx512bw") &&
+        __builtin_cpu_supports("avx512vl"))
+        p->isa = ISA_VBMI;
+    if (const char *ov = getenv("MAPF_HOST_ISA")) {  // generic | bmi2 | vbmi: cap the instruction set (tests)
+        const int cap = ov[0] == 'g' ? ISA_GENERIC : ov[0] == 'b' ? ISA_BMI2 : ISA_VBMI;
+        if (cap < p->isa) p->isa = cap;
+    }
 #endif
-    p->next.store(p->nchunks);
     for (int i = 1; i < p->nthreads; ++i) p->workers.emplace_back([p] { p->worker(); });
     return p;
 }
@@ -158,18 +339,52 @@ void host_pool_destroy(HostPool *p) {
 
 int host_pool_threads(const HostPool *p) { return p ? p->nthreads : 0; }
 
-void host_pool_unpack(HostPool *p, const UnpackJob &job) {
-    if (job.a1 <= job.a0) return;
-    p->job = job;
-    p->done.store(0, std::memory_order_relaxed);
-    p->next.store(0, std::memory_order_release);
-    {
-        std::lock_guard<std::mutex> lk(p->mu);
-        p->generation.fetch_add(1, std::memory_order_acq_rel);
+void host_pool_begin(HostPool *p) {
+    p->failed.store(false, std::memory_order_relaxed);
+    p->published.store(0, std::memory_order_relaxed);
+    p->closed.store(false, std::memory_order_release);
+    p->epoch.fetch_add(1, std::memory_order_acq_rel);
+    if (p->sleepers.load(std::memory_order_acquire) > 0) {
+        { std::lock_guard<std::mutex> lk(p->mu); }
+        p->cv.notify_all();
     }
-    p->cv.notify_all();
-    p->run_chunks();
-    while (p->done.load(std::memory_order_acquire) < p->nchunks) cpu_relax();
+}
+
+bool host_pool_submit(HostPool *p, const UnpackJob &job, const volatile uint32_t *ticket, uint32_t ticket_value) {
+    const int q = p->published.load(std::memory_order_relaxed);
+    if (q >= kMaxJobs) return false;
+    if (job.a1 <= job.a0) return true;
+    QueuedJob &slot = p->jobs[q];
+    slot.job = job;
+    slot.ticket.store(ticket, std::memory_order_relaxed);
+    slot.ticket_value.store(ticket_value, std::memory_order_relaxed);
+    slot.done.store(0, std::memory_order_relaxed);
+    slot.next.store((p->epoch.load(std::memory_order_relaxed) & 0xFFFFFFFFu) << 32, std::memory_order_release);
+    p->published.store(q + 1, std::memory_order_release);
+    return true;
+}
+
+bool host_pool_finish(HostPool *p) {
+    p->closed.store(true, std::memory_order_release);
+    p->run_step();
+    const int n = p->published.load(std::memory_order_acquire);
+    for (int q = 0; q < n; ++q)
+        while (p->jobs[q].done.load(std::memory_order_acquire) < p->nchunks) {
+            if (p->failed.load(std::memory_order_acquire)) return false;
+            cpu_relax();
+        }
+    return !p->failed.load(std::memory_order_acquire);
+}
+
+void host_pool_job_times(const HostPool *p, int q, int64_t *first_ns, int64_t *last_ns) {
+    *first_ns = p->jobs[q].t_first.load(std::memory_order_relaxed);
+    *last_ns = p->jobs[q].t_last.load(std::memory_order_relaxed);
+}
+
+void host_pool_unpack(HostPool *p, const UnpackJob &job) {
+    host_pool_begin(p);
+    host_pool_submit(p, job, nullptr, 0);
+    host_pool_finish(p);
 }
 
 }  // namespace mapf

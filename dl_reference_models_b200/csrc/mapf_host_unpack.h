@@ -11,26 +11,36 @@ inline int pack_obs_bytes(int V2) {
     const int rem = V2 & 7;
     return (V2 >> 3) * 3 + (rem * 3 + 5 + 7) / 8;
 }
-// record: [obs+mask bits][int8 d_row][int8 d_col][int8 2*reward][u8 blocking_prev]
-inline int pack_record_bytes(int V2) { return pack_obs_bytes(V2) + 4; }
+// A packed block of n agents is three streams, one after the other:
+//   [n x pack_obs_bytes: window + mask bits][n x (int8 d_row, int8 d_col)][n x int8 2*reward]
+inline int pack_record_bytes(int V2) { return pack_obs_bytes(V2) + 3; }
 
 struct UnpackJob {
-    const uint8_t *packed;  // records of agents [a0, a1), record of agent a at packed + (a - a0) * RS
+    const uint8_t *packed;  // packed block of agents [a0, a1)
     int64_t a0, a1;         // global agent indices (env * N + agent)
-    int V2, RS;
+    int V2;                 // 9, 25 or 49 (sensor range 1..3)
     uint8_t *obs;           // [BN, V2]   full host arrays (global indexing); may be null
     int8_t *mask;           // [BN, 5]
     float *goal_delta;      // [BN, 2]
     float *reward;          // [BN]
-    uint8_t *blocking_prev; // [BN]
     const float *gdt_row, *gdt_col;  // 256-entry tables indexed by (int8 delta + 128)
+    float den_row, den_col;          // the tables' rule: value = delta / den (1 when not normalised)
+    const uint8_t *bytes_src;        // optional per-agent byte channel carried as is (blocking_prev): agent a0's byte
+    uint8_t *bytes_dst;              // ... and its full host array (global indexing)
 };
 
 struct HostPool;
 HostPool *host_pool_create(int threads);  // threads >= 1 (the caller's thread counts as one)
 void host_pool_destroy(HostPool *p);
 int host_pool_threads(const HostPool *p);
-// blocking: the agents of the job are split over the pool's threads and the calling thread
+// One step = begin, submit (non-blocking, at most 32 jobs; a job starts once *ticket == ticket_value, or at once
+// if ticket is null), finish (the caller's thread joins in and returns when every job is done).  Single caller.
+void host_pool_begin(HostPool *p);
+bool host_pool_submit(HostPool *p, const UnpackJob &job, const volatile uint32_t *ticket, uint32_t ticket_value);
+bool host_pool_finish(HostPool *p);  // false: a ticket did not arrive within 20 s (the GPU work before it failed)
+// trace: steady_clock nanoseconds at which job q of the last step was started / completed
+void host_pool_job_times(const HostPool *p, int q, int64_t *first_ns, int64_t *last_ns);
+// begin + submit + finish of one job
 void host_pool_unpack(HostPool *p, const UnpackJob &job);
 
 }  // namespace mapf

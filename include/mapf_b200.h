@@ -255,12 +255,12 @@ int mapf_step_host(mapf_handle *h, const int8_t *actions, const int16_t *goal_ov
  * MAPF_HOST_PACK=0 disables it, MAPF_HOST_THREADS / MAPF_HOST_SLICES tune it.
  * mapf_host_transfer_bytes: bytes that actually crossed PCIe in the last mapf_step_host call. */
 int mapf_host_transfer_bytes(const mapf_handle *h, int64_t *h2d_bytes, int64_t *d2h_bytes);
-/* Record size, and the host-side expansion on its own (no GPU needed; used by the CPU test-suite):
- * packed holds n_agents records; gdt_row / gdt_col are 256-entry tables indexed by (int8 difference + 128). */
+/* Packed bytes per agent, and the host-side expansion on its own (no GPU needed; used by the CPU test-suite):
+ * packed holds the block of n_agents agents -- [n x window+mask bits][n x (int8 d_row, int8 d_col)][n x int8
+ * 2*reward] (csrc/mapf_pack_kernel.cuh); goal_delta = difference / denominator. */
 int mapf_packed_record_bytes(int32_t v2);
 int mapf_unpack_records(const uint8_t *packed, int64_t n_agents, int32_t v2, int32_t threads, uint8_t *local_obs,
-                        int8_t *action_mask, float *goal_delta, float *reward, uint8_t *blocking_prev,
-                        const float *gdt_row, const float *gdt_col);
+                        int8_t *action_mask, float *goal_delta, float *reward, float den_row, float den_col);
 
 /* ENV:306-328: pack channels into float32 flat[B,N,D] (device pointers),
  * D = V*V + 2 + gdist + bp + 5*mask, component order of ENV:214-236. */

@@ -162,67 +162,53 @@ def test_metric_means():
     assert not any(k.startswith("reserved") for k in m)
 
 
-def _pack_records_numpy(obs, mask, drow, dcol, reward2, bp):
-    """The record format of csrc/mapf_pack_kernel.cuh restated in numpy (the spec the host expansion is
-    checked against): 3 bits per window cell (8 cells -> 3 bytes), the (V2 & 7) left-over cells and the 5 mask
-    bits share the tail bytes, then int8 d_row, int8 d_col, int8 2*reward, u8 blocking_prev."""
+def _pack_block_numpy(obs, mask, drow, dcol, reward2):
+    """The packed block of csrc/mapf_pack_kernel.cuh restated in numpy (the spec the host expansion is checked
+    against): [n x bits][n x (int8 d_row, int8 d_col)][n x int8 2*reward]; bits = 3 per window cell, 8 cells ->
+    3 bytes, the last cell shares its byte with the 5 mask bits."""
     n, v2 = obs.shape
-    nfull, rem = v2 // 8, v2 % 8
-    tail_bytes = (rem * 3 + 5 + 7) // 8
-    rs = nfull * 3 + tail_bytes + 4
-    out = np.zeros((n, rs), dtype=np.uint8)
-    k = 0
+    nfull = v2 // 8
+    assert v2 % 8 == 1
+    bits = np.zeros((n, nfull * 3 + 1), dtype=np.uint8)
     for c in range(nfull):
         w = np.zeros(n, dtype=np.uint32)
         for i in range(8):
             w |= (obs[:, c * 8 + i].astype(np.uint32) & 7) << (3 * i)
         for b in range(3):
-            out[:, k] = (w >> (8 * b)) & 0xFF
-            k += 1
-    w = np.zeros(n, dtype=np.uint32)
-    for i in range(rem):
-        w |= (obs[:, nfull * 8 + i].astype(np.uint32) & 7) << (3 * i)
+            bits[:, 3 * c + b] = (w >> (8 * b)) & 0xFF
+    w = obs[:, v2 - 1].astype(np.uint32) & 7
     for i in range(5):
-        w |= (mask[:, i] != 0).astype(np.uint32) << (3 * rem + i)
-    for b in range(tail_bytes):
-        out[:, k] = (w >> (8 * b)) & 0xFF
-        k += 1
-    out[:, k] = drow.astype(np.int8).view(np.uint8)
-    out[:, k + 1] = dcol.astype(np.int8).view(np.uint8)
-    out[:, k + 2] = reward2.astype(np.int8).view(np.uint8)
-    out[:, k + 3] = bp
-    return out
+        w |= (mask[:, i] != 0).astype(np.uint32) << (3 + i)
+    bits[:, 3 * nfull] = w
+    diff = np.stack([drow.astype(np.int8), dcol.astype(np.int8)], axis=1).view(np.uint8)
+    return np.concatenate([bits.reshape(-1), diff.reshape(-1), reward2.astype(np.int8).view(np.uint8)])
 
 
-@pytest.mark.parametrize("v2,threads", [(9, 1), (25, 1), (25, 5), (49, 3)])
-def test_host_expansion_of_packed_records(v2, threads):
+@pytest.mark.parametrize("isa", ["generic", "bmi2", "vbmi"])
+@pytest.mark.parametrize("v2,threads,n", [(9, 1, 10007), (25, 1, 10007), (25, 5, 70001), (49, 3, 10007), (25, 2, 3), (9, 4, 64)])
+def test_host_expansion_of_packed_block(monkeypatch, isa, v2, threads, n):
+    """Every instruction-set variant of the expansion (capped by MAPF_HOST_ISA; a CPU without the extension falls
+    back to the next one) reproduces the arrays exactly."""
+    monkeypatch.setenv("MAPF_HOST_ISA", isa)
     L = nat.lib()
     rng = np.random.default_rng(v2 * 10 + threads)
-    n = 10007
     obs = rng.integers(0, 5, (n, v2), dtype=np.uint8)
     mask = rng.integers(0, 2, (n, 5), dtype=np.int8)
     drow = rng.integers(-128, 128, n)
     dcol = rng.integers(-128, 128, n)
     reward2 = rng.integers(-64, 4, n)
-    bp = rng.integers(0, 2, n, dtype=np.uint8)
-    packed = _pack_records_numpy(obs, mask, drow, dcol, reward2, bp)
-    assert packed.shape[1] == L.mapf_packed_record_bytes(v2)
-    packed = np.concatenate([packed.reshape(-1), np.zeros(8, np.uint8)])
-    gdt_row = (np.arange(-128, 128, dtype=np.float32) / np.float32(31.0)).astype(np.float32)
-    gdt_col = (np.arange(-128, 128, dtype=np.float32) / np.float32(17.0)).astype(np.float32)
-    o = np.full((n, v2), 255, np.uint8)
-    m = np.full((n, 5), 77, np.int8)
-    gd = np.zeros((n, 2), np.float32)
-    rw = np.zeros(n, np.float32)
-    b = np.full(n, 9, np.uint8)
-    ptr = lambda a: a.ctypes.data_as(C.c_void_p)
-    rc = L.mapf_unpack_records(ptr(packed), n, v2, threads, ptr(o), ptr(m), ptr(gd), ptr(rw), ptr(b), ptr(gdt_row),
-                               ptr(gdt_col))
-    assert rc == 0
-    assert np.array_equal(o, obs) and np.array_equal(m, mask) and np.array_equal(b, bp)
-    assert np.array_equal(gd[:, 0], gdt_row[drow + 128]) and np.array_equal(gd[:, 1], gdt_col[dcol + 128])
-    assert np.array_equal(rw, 0.5 * reward2.astype(np.float32))
-    # blocking_prev is optional
-    rc = L.mapf_unpack_records(ptr(packed), n, v2, threads, ptr(o), ptr(m), ptr(gd), ptr(rw), None, ptr(gdt_row),
-                               ptr(gdt_col))
-    assert rc == 0
+    packed = _pack_block_numpy(obs, mask, drow, dcol, reward2)
+    assert packed.size == n * L.mapf_packed_record_bytes(v2)
+    for den_row, den_col in ((31.0, 17.0), (1.0, 1.0)):
+        o = np.full((n + 1, v2), 255, np.uint8)   # one guard row behind every array: nothing may spill
+        m = np.full((n + 1, 5), 77, np.int8)
+        gd = np.full((n + 1, 2), -7.0, np.float32)
+        rw = np.full(n + 1, -7.0, np.float32)
+        ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+        rc = L.mapf_unpack_records(ptr(packed), n, v2, threads, ptr(o), ptr(m), ptr(gd), ptr(rw), den_row, den_col)
+        assert rc == 0
+        assert np.array_equal(o[:n], obs) and np.array_equal(m[:n], mask)
+        assert np.array_equal(gd[:n, 0], drow.astype(np.float32) / np.float32(den_row))
+        assert np.array_equal(gd[:n, 1], dcol.astype(np.float32) / np.float32(den_col))
+        assert np.array_equal(rw[:n], 0.5 * reward2.astype(np.float32))
+        assert (o[n] == 255).all() and (m[n] == 77).all() and (gd[n] == -7.0).all() and rw[n] == -7.0

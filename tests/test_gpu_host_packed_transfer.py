@@ -59,6 +59,7 @@ def c3(**kw):
 @pytest.mark.parametrize("normalize", [True, False])
 def test_packed_transfer_is_exact(monkeypatch, sr, normalize):
     monkeypatch.delenv("MAPF_HOST_PACK", raising=False)
+    monkeypatch.setenv("MAPF_HOST_RAW_32NDS", "0")  # every env packed (the share is self-tuning otherwise)
     B = 8192 + 96
     cfg = c3(sensor_range=sr, normalize_goal_delta=normalize)
     a, b = run_host_vs_device(cfg, B, 20)
@@ -66,8 +67,8 @@ def test_packed_transfer_is_exact(monkeypatch, sr, normalize):
     rs = nat.lib().mapf_packed_record_bytes(v2)
     h2d, d2h = transfer_bytes(b)
     assert h2d == B * 16
-    assert d2h == B * 16 * (rs + 1) + B * (3 + 64), "records + agent_step_flags + per-env channels"
-    assert rs < v2 + 5 + 8 + 4 + 1
+    assert d2h == B * 16 * (rs + 2) + B * (3 + 64), "records + blocking_prev + agent_step_flags + per-env channels"
+    assert rs < v2 + 5 + 8 + 4
 
 
 def test_packed_transfer_with_channels_left_out_and_odd_shapes(monkeypatch):
@@ -84,6 +85,25 @@ def test_packed_transfer_with_channels_left_out_and_odd_shapes(monkeypatch):
     monkeypatch.delenv("MAPF_HOST_THREADS", raising=False)
     grid = maps.random_obstacle_grid(40, 100, 0.2, 3, min_free=300)
     run_host_vs_device({"num_agents": 12, "sensor_range": 2, "steps_per_episode": 9, "seed": 1, "grid": grid}, 8192, 12)
+
+
+def test_plain_tail_share(monkeypatch):
+    """Part of the batch may go as plain copies behind the records (balances PCIe against the host threads):
+    any share delivers the same arrays."""
+    B = 8192 + 160
+    for share in ("5", "16", None):
+        if share is None:
+            monkeypatch.delenv("MAPF_HOST_RAW_32NDS", raising=False)
+        else:
+            monkeypatch.setenv("MAPF_HOST_RAW_32NDS", share)
+        _, b = run_host_vs_device(c3(), B, 40 if share is None else 10)
+        rs = nat.lib().mapf_packed_record_bytes(25)
+        d2h = transfer_bytes(b)[1]
+        packed_all, plain_all = B * 16 * (rs + 2) + B * 67, B * 16 * 44 + B * 67
+        if share == "16":
+            tail = (B * 16 // 32) // 32 * 32
+            assert d2h == packed_all + tail * 16 * (42 - rs)
+        assert packed_all <= d2h <= plain_all
 
 
 def test_unpacked_path_still_there(monkeypatch):
