@@ -361,6 +361,11 @@ int host_threads_default() {
     int n = 0;
     cpu_set_t set;
     if (sched_getaffinity(0, sizeof(set), &set) == 0) n = CPU_COUNT(&set);
+    // one process per GPU: the ranks of a node share its cores (torchrun exports LOCAL_WORLD_SIZE)
+    if (const char *lw = getenv("LOCAL_WORLD_SIZE")) {
+        const int w = atoi(lw);
+        if (w > 1) n /= w;
+    }
     if (n < 1) n = 1;
     return n > 16 ? 16 : n;
 }
