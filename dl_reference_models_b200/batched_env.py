@@ -192,6 +192,61 @@ class BatchedMapfEnv:
             self._sample_counter += 1
         return self._output()
 
+    # ------------------------------------------------------------------ host-buffer transition
+    HOST_CHANNELS = ("local_obs", "action_mask", "goal_delta", "blocking_prev", "reward", "terminated", "truncated")
+
+    def host_buffers(self, channels=None) -> dict:
+        """Pinned host arrays (numpy views of pinned torch tensors) for :meth:`step_host` / :meth:`reset_host`,
+        one per requested output channel (default: what an RL worker consumes, ``HOST_CHANNELS``)."""
+        channels = self.HOST_CHANNELS if channels is None else tuple(channels)
+        unknown = set(channels) - set(nat.OUTPUT_FIELDS)
+        if unknown:
+            raise KeyError(f"unknown output channels {sorted(unknown)}")
+        self._host_t = {k: torch.empty_like(self.out[k], device="cpu").pin_memory() for k in channels}
+        self._host_actions = torch.zeros((self.B, self.N), dtype=torch.int8).pin_memory()
+        self._host_np = {k: v.numpy() for k, v in self._host_t.items()}
+        self._chost = nat.MapfOutputs(**{k: (self._host_t[k].data_ptr() if k in self._host_t else None)
+                                         for k in nat.OUTPUT_FIELDS})
+        return self._host_np
+
+    def reset_host(self, mask=None, starts=None, goals=None) -> dict:
+        """:meth:`reset` with host arrays in and out (``mapf_reset_host``): returns the dict of :meth:`host_buffers`."""
+        if getattr(self, "_chost", None) is None:
+            self.host_buffers()
+        B, N = self.B, self.N
+        m = None if mask is None else np.ascontiguousarray(np.asarray(mask, dtype=np.uint8).reshape(B))
+        s = g = None
+        if starts is not None or goals is not None:
+            s = np.ascontiguousarray(np.broadcast_to(np.asarray(starts, dtype=np.int16), (B, N, 2)))
+            g = np.ascontiguousarray(np.broadcast_to(np.asarray(goals, dtype=np.int16), (B, N, 2)))
+        vp = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)  # noqa: E731
+        nat.check(self._lib.mapf_reset_host(self._h, vp(m), vp(s), vp(g), C.byref(self._chost)))
+        return self._host_np
+
+    def step_host(self, actions=None, auto_reset: bool = True) -> dict:
+        """One env step with HOST arrays in and out -- the vector-env call of a CPU-side RL worker
+        (``mapf_step_host``: H2D of the actions, the step kernel, and the device-to-host delivery of the requested
+        channels all happen inside the call; big batches cross PCIe bit-packed and are expanded into the returned
+        arrays by the library's host threads).  ``actions``: integer array [B,N] in 0..4 (None = all
+        NO_OP).  Returns the dict of :meth:`host_buffers` (the same arrays every call, overwritten in place)."""
+        if getattr(self, "_chost", None) is None:
+            self.host_buffers()
+        a = None
+        if actions is not None:
+            src = actions.numpy() if isinstance(actions, torch.Tensor) else np.asarray(actions)
+            if src.shape != (self.B, self.N):
+                raise ValueError(f"expected actions of shape {(self.B, self.N)}, got {src.shape}")
+            np.copyto(self._host_actions.numpy(), src, casting="unsafe")
+            a = C.c_void_p(self._host_actions.data_ptr())
+        nat.check(self._lib.mapf_step_host(self._h, a, None, None, C.byref(self._chost), int(bool(auto_reset))))
+        return self._host_np
+
+    def host_transfer_bytes(self) -> tuple:
+        """(host-to-device, device-to-host) bytes that crossed PCIe in the last :meth:`step_host`."""
+        h2d, d2h = C.c_int64(0), C.c_int64(0)
+        nat.check(self._lib.mapf_host_transfer_bytes(self._h, C.byref(h2d), C.byref(d2h)))
+        return int(h2d.value), int(d2h.value)
+
     def sample_actions(self, masked: bool = True) -> torch.Tensor:
         """Uniform (masked) random actions on device, the samplers of the reference's benchmark
         script (scripts/benchmark_multi_agent_env.py:38-57)."""

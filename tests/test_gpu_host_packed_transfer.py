@@ -118,3 +118,54 @@ def test_unpacked_path_still_there(monkeypatch):
     assert transfer_bytes(b)[1] == B * 16 * (25 + 5 + 4 + 1)
     _, b = run_host_vs_device(c3(), 512, 6)
     assert transfer_bytes(b)[1] == 512 * 16 * 44 + 512 * 67
+
+
+def test_python_step_host_api_matches_device_api_and_oracle():
+    """BatchedMapfEnv.step_host / reset_host (numpy in, numpy out): same results as the device-tensor API on a big
+    batch (packed transfer), and as the CPU oracle on a small one (plain copies), from the same layout and actions."""
+    import numpy as np
+    import torch
+
+    from oracle.oracle import OracleBatch
+
+    B = 8192 + 32
+    cfg = c3(steps_per_episode=9)
+    a, b = make(cfg, B), make(cfg, B)
+    oa = a.reset()
+    hb = b.reset_host()
+    assert set(hb) == set(b.HOST_CHANNELS)
+    for k in ("local_obs", "action_mask", "goal_delta", "blocking_prev"):
+        assert np.array_equal(getattr(oa, k).cpu().numpy(), hb[k]), k
+    rng = np.random.default_rng(0)
+    for s in range(25):
+        acts = rng.integers(0, 5, (B, a.N))
+        oa = a.step(torch.as_tensor(acts, dtype=torch.int8), auto_reset=True)
+        hb = b.step_host(acts)
+        for k in b.HOST_CHANNELS:
+            assert np.array_equal(getattr(oa, k).cpu().numpy(), hb[k]), f"step {s}: {k}"
+    h2d, d2h = b.host_transfer_bytes()
+    assert h2d == B * a.N and d2h < sum(v.nbytes for v in hb.values()) // 2
+
+    # small batch against the CPU oracle (plain copies; the oracle draws the layout, no lifelong goal draws)
+    from dl_reference_models_b200 import maps
+
+    grid = maps.get_grid("ReferenceModel-2-1")
+    cfg = {"num_agents": 4, "sensor_range": 2, "steps_per_episode": 40, "seed": 7, "grid": grid}
+    Bs = 64
+    ob = OracleBatch(cfg, grid, Bs, seed=5)
+    env = make(cfg, Bs)
+    ob.reset(2)
+    st = ob.state()
+    hb = env.reset_host(starts=st["starts"], goals=st["goals"])
+    for k in ("local_obs", "action_mask", "goal_delta"):
+        assert np.array_equal(ob.buf[k].reshape(hb[k].shape), hb[k]), f"reset: {k}"
+    for s in range(40):
+        acts = rng.integers(0, 5, (Bs, 4)).astype(np.int8)
+        ob.step(acts)
+        hb = env.step_host(acts, auto_reset=False)
+        assert np.array_equal(ob.state()["positions"], env.state["positions"].cpu().numpy()), f"step {s}"
+        for k in ("local_obs", "action_mask", "goal_delta", "terminated", "truncated"):
+            assert np.array_equal(ob.buf[k].reshape(hb[k].shape), hb[k]), f"step {s}: {k}"
+        assert np.allclose(ob.buf["reward"], hb["reward"], atol=1e-6), f"step {s}: reward"
+        if (ob.buf["terminated"] | ob.buf["truncated"]).any():
+            break
