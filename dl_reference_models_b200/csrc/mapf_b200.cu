@@ -371,12 +371,16 @@ int host_threads_default() {
 }
 
 // The bit-packed transfer applies when the four big per-agent channels are all requested, the integer goal
-// differences fit an int8 and the batch is big enough for the PCIe time to matter; MAPF_HOST_PACK=0 turns it off.
+// differences fit an int8, the batch is big enough for the PCIe time to matter, and this process has at least 12
+// host cores to itself: the expansion trades PCIe bytes for host memory traffic, and on a node whose cores and
+// DRAM are shared by many ranks plain copies win (measured on an 8-GPU / 32-core host: plain 2.24e9, packed
+// 1.76e9 agent-steps/s aggregate; on 1 GPU / 16 cores: plain 1.13e9, packed 2.36e9; 2 GPUs / 24 cores: packed
+// 2.72e9).  MAPF_HOST_PACK=0 / 1 forces it off / on.
 bool host_pack_applies(const mapf_handle *h, const mapf_outputs *host) {
     if (!host || !host->local_obs || !host->action_mask || !host->goal_delta || !host->reward) return false;
     if (h->cfg.rows > 128 || h->cfg.cols > 128 || h->cfg.num_envs < 8192) return false;
     if (const char *ov = getenv("MAPF_HOST_PACK")) return atoi(ov) != 0;
-    return true;
+    return host_threads_default() >= 12;
 }
 
 int ensure_pack(mapf_handle *h) {

@@ -252,7 +252,8 @@ int mapf_step_host(mapf_handle *h, const int8_t *actions, const int16_t *goal_ov
  * requested (and num_envs >= 8192, rows/cols <= 128) those channels cross PCIe as one bit-packed record per
  * agent (3 bits per window cell, 1 bit per mask entry, the integer goal difference, 2*reward) and host threads
  * inside the call expand them into the caller's arrays -- the delivered arrays are bit for bit the same.
- * MAPF_HOST_PACK=0 disables it, MAPF_HOST_THREADS / MAPF_HOST_SLICES tune it.
+ * It is used when this process has >= 12 host cores to itself (cores / LOCAL_WORLD_SIZE); MAPF_HOST_PACK=0 / 1
+ * forces it off / on, MAPF_HOST_THREADS / MAPF_HOST_SLICES tune it.
  * mapf_host_transfer_bytes: bytes that actually crossed PCIe in the last mapf_step_host call. */
 int mapf_host_transfer_bytes(const mapf_handle *h, int64_t *h2d_bytes, int64_t *d2h_bytes);
 /* Packed bytes per agent, and the host-side expansion on its own (no GPU needed; used by the CPU test-suite):

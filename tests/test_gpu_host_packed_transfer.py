@@ -58,7 +58,7 @@ def c3(**kw):
 @pytest.mark.parametrize("sr", [1, 2, 3])
 @pytest.mark.parametrize("normalize", [True, False])
 def test_packed_transfer_is_exact(monkeypatch, sr, normalize):
-    monkeypatch.delenv("MAPF_HOST_PACK", raising=False)
+    monkeypatch.setenv("MAPF_HOST_PACK", "1")  # auto would also pick it on a host with >= 12 cores per rank
     monkeypatch.setenv("MAPF_HOST_RAW_32NDS", "0")  # every env packed (the share is self-tuning otherwise)
     B = 8192 + 96
     cfg = c3(sensor_range=sr, normalize_goal_delta=normalize)
@@ -72,7 +72,7 @@ def test_packed_transfer_is_exact(monkeypatch, sr, normalize):
 
 
 def test_packed_transfer_with_channels_left_out_and_odd_shapes(monkeypatch):
-    monkeypatch.delenv("MAPF_HOST_PACK", raising=False)
+    monkeypatch.setenv("MAPF_HOST_PACK", "1")  # auto would also pick it on a host with >= 12 cores per rank
     want = ("local_obs", "action_mask", "goal_delta", "reward", "terminated")
     for slices, threads in (("1", "1"), ("5", "3"), ("16", "7")):
         monkeypatch.setenv("MAPF_HOST_SLICES", slices)
@@ -91,6 +91,7 @@ def test_plain_tail_share(monkeypatch):
     """Part of the batch may go as plain copies behind the records (balances PCIe against the host threads):
     any share delivers the same arrays."""
     B = 8192 + 160
+    monkeypatch.setenv("MAPF_HOST_PACK", "1")
     for share in ("5", "16", None):
         if share is None:
             monkeypatch.delenv("MAPF_HOST_RAW_32NDS", raising=False)
@@ -112,7 +113,7 @@ def test_unpacked_path_still_there(monkeypatch):
     monkeypatch.setenv("MAPF_HOST_PACK", "0")
     _, b = run_host_vs_device(c3(), B, 6)
     assert transfer_bytes(b)[1] == B * 16 * 44 + B * 67
-    monkeypatch.delenv("MAPF_HOST_PACK")
+    monkeypatch.setenv("MAPF_HOST_PACK", "1")
     want = ("local_obs", "action_mask", "reward", "blocking_prev")
     _, b = run_host_vs_device(c3(), B, 6, want=want)
     assert transfer_bytes(b)[1] == B * 16 * (25 + 5 + 4 + 1)
@@ -120,7 +121,7 @@ def test_unpacked_path_still_there(monkeypatch):
     assert transfer_bytes(b)[1] == 512 * 16 * 44 + 512 * 67
 
 
-def test_python_step_host_api_matches_device_api_and_oracle():
+def test_python_step_host_api_matches_device_api_and_oracle(monkeypatch):
     """BatchedMapfEnv.step_host / reset_host (numpy in, numpy out): same results as the device-tensor API on a big
     batch (packed transfer), and as the CPU oracle on a small one (plain copies), from the same layout and actions."""
     import numpy as np
@@ -128,6 +129,7 @@ def test_python_step_host_api_matches_device_api_and_oracle():
 
     from oracle.oracle import OracleBatch
 
+    monkeypatch.setenv("MAPF_HOST_PACK", "1")
     B = 8192 + 32
     cfg = c3(steps_per_episode=9)
     a, b = make(cfg, B), make(cfg, B)
