@@ -92,7 +92,14 @@ EnvKernelFn env_step_for_sr(int sr) {
     }
     return nullptr;
 }
-EnvKernelFn pick_env_step(int sr, bool vec, int lpe) {
+EnvKernelFn pick_env_step(int sr, bool vec, int lpe, bool fast) {
+    if (fast && vec && lpe == 1) {   // lifelong + lock metrics as compile-time constants
+        switch (sr) {
+            case 1: return mapf::mapf_step_env_kernel<1, true, 1, true>;
+            case 2: return mapf::mapf_step_env_kernel<2, true, 1, true>;
+            case 3: return mapf::mapf_step_env_kernel<3, true, 1, true>;
+        }
+    }
     if (lpe == 4) return env_step_for_sr<true, 4>(sr);
     if (lpe == 2) return env_step_for_sr<true, 2>(sr);
     return vec ? env_step_for_sr<true, 1>(sr) : env_step_for_sr<false, 1>(sr);
@@ -503,7 +510,9 @@ int mapf_create(const mapf_config *cfg, mapf_handle **out) {
             }
         }
         if (h->env_threads) {
-            h->env_fn = pick_env_step(h->SR, c.num_agents % 4 == 0, lpe);
+            bool fast = c.lifelong_mapf != 0 && c.enable_lock_metrics != 0;
+            if (const char *ov = getenv("MAPF_ENV_FAST")) fast = fast && atoi(ov) != 0;
+            h->env_fn = pick_env_step(h->SR, c.num_agents % 4 == 0, lpe, fast);
             e1 = cudaFuncSetAttribute(reinterpret_cast<const void *>(h->env_fn),
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmemEnv);
             const int w = h->env_threads / 32;

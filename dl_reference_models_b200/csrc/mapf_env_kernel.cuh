@@ -319,8 +319,12 @@ constexpr uint32_t REC_CODE = 0x7FFu;
 // One env per LPE lanes.  LPE = 1: the thread walks all quads of its env.  LPE = 2 / 4 (N = 8 / 16): lane `sub`
 // owns quad `sub`; it first replays the moves of quads < sub on its private occupancy board (moves only: a move
 // needs nothing but the board, ENV:516-526), then all lanes walk their own quad at the same time.
-template <int SR, bool VEC, int LPE>
+// FAST: the benchmark's configuration (lifelong goals, lock metrics on) as compile-time constants -- the other
+// branches and their uniform tests drop out of the hot loops (smaller instruction footprint); same results.
+template <int SR, bool VEC, int LPE, bool FAST = false>
 __global__ void __launch_bounds__(LPE == 1 ? 448 : 512, 1) mapf_step_env_kernel(const KParams p, const EnvLayout E) {
+    const bool kLifelong = FAST ? true : p.lifelong;
+    const bool kLock = FAST ? true : p.lock_enabled;
     constexpr int V = 2 * SR + 1, V2 = V * V;
     constexpr uint32_t VM = (1u << V) - 1u;
     constexpr uint32_t M4 = VM << 2;          // a window row, pre-scaled by 4 (byte offset into t1)
@@ -396,7 +400,7 @@ __global__ void __launch_bounds__(LPE == 1 ? 448 : 512, 1) mapf_step_env_kernel(
     if (lock_head < 0 || lock_head >= p.lw) lock_head = 0;
     const int slot_new = lock_head;
     const int slot_next = (lock_head + 1 == p.lw) ? 0 : lock_head + 1;
-    const bool use_ring = p.lock_enabled && count_after >= p.lw && p.lw > 1;
+    const bool use_ring = kLock && count_after >= p.lw && p.lw > 1;
 
     uint32_t reached_m = 0, completed_m = 0, bprev_m = 0;   // agent_flags of the previous step (MAPF_AF_*), one bit per agent
     // ---------------------------------------------------------------- pre-pass: agent records and owner boards of the state before the step
@@ -475,10 +479,10 @@ __global__ void __launch_bounds__(LPE == 1 ? 448 : 512, 1) mapf_step_env_kernel(
                 ongoal_m = group_or<LPE>(ongoal_m); reached_m = group_or<LPE>(reached_m); completed_m = group_or<LPE>(completed_m);
                 Gd = group_or<LPE>(Gd); Md = group_or<LPE>(Md); Fd = group_or<LPE>(Fd); Gl = group_or<LPE>(Gl); Ml = group_or<LPE>(Ml);
             }
-            if (p.lock_enabled) lock_head = slot_next;
+            if (kLock) lock_head = slot_next;
             arrivals = __popc(gstep_m);
             goals_total += arrivals;  // lifelong: every arrival; else first arrivals (ENV:545,562)
-            uint32_t pend = p.lifelong ? gstep_m : 0u;
+            uint32_t pend = kLifelong ? gstep_m : 0u;
             reassigned = pend != 0;
             if (!__any_sync(full, reassigned)) continue;
             if constexpr (LPE == 1) {
@@ -557,7 +561,7 @@ __global__ void __launch_bounds__(LPE == 1 ? 448 : 512, 1) mapf_step_env_kernel(
                         if (lane == 0) {
                             goal_e[(ng >> 5) * 32] |= 1u << (ng & 31u);
                             p.goals[abe + i] = packed_of(ng);
-                            if (p.lock_enabled) {   // ENV:591: distance to the NEW goal
+                            if (kLock) {   // ENV:591: distance to the NEW goal
                                 const uint32_t rv = rec_e[i * 32], code = rv & REC_CODE;
                                 const int dist = abs((int)(ng >> 5) - (int)(code >> 5)) + abs((int)(ng & 31u) - (int)(code & 31u));
                                 p.lock_dist[((size_t)enve * p.lw + slot_new_e) * N + i] = (int16_t)dist;
@@ -665,7 +669,7 @@ __global__ void __launch_bounds__(LPE == 1 ? 448 : 512, 1) mapf_step_env_kernel(
                         occ[(nc >> 5) * 32] |= 1u << (nc & 31u);
                     }
                     p.goals[ab + i] = packed_of(ng.x);
-                    if (p.lock_enabled) {   // ENV:591: distance to the NEW goal
+                    if (kLock) {   // ENV:591: distance to the NEW goal
                         const uint32_t rv = rec[i * EPW], code = rv & REC_CODE;
                         const int dist = abs((int)(ng.x >> 5) - (int)(code >> 5)) + abs((int)(ng.x & 31u) - (int)(code & 31u));
                         p.lock_dist[((size_t)env * p.lw + slot_new) * N + i] = (int16_t)dist;
@@ -730,7 +734,7 @@ __global__ void __launch_bounds__(LPE == 1 ? 448 : 512, 1) mapf_step_env_kernel(
                 const uint32_t here = *prow_ & *pcol_;   // agents on my cell (me included)
                 if (here & ~bit) coloc_any |= bit;
                 // ENV:389-438 neighbours within Manhattan distance `nearby`, via the row / column masks
-                if (p.lock_enabled && !(ongoal_m & bit)) {
+                if (kLock && !(ongoal_m & bit)) {
                     uint32_t nb = 0;
                     if (p.nearby == 2) {
                         const uint32_t c0 = *pcol_;
@@ -812,7 +816,7 @@ __global__ void __launch_bounds__(LPE == 1 ? 448 : 512, 1) mapf_step_env_kernel(
             blocking_total += blocking_step;
 
             // ------------------------------------------------------------ lock detection result, ENV:595-606
-            if (p.lock_enabled) {
+            if (kLock) {
                 dl_step = count_after >= p.dw && dl_any;
                 ll_step = !dl_step && count_after >= p.lw && ll_any;
                 dl_event = dl_step && !(lock_prev & 1);
@@ -823,12 +827,12 @@ __global__ void __launch_bounds__(LPE == 1 ? 448 : 512, 1) mapf_step_env_kernel(
             }
 
             // ------------------------------------------------------------ rewards & termination, ENV:658-690
-            const uint32_t scratch_on = p.lifelong ? 0u : ongoal_m;   // reached_goal scratch (ENV:555)
+            const uint32_t scratch_on = kLifelong ? 0u : ongoal_m;   // reached_goal scratch (ENV:555)
             uint32_t bonus_m = 0, penalty_m = 0;
-            if (!p.lifelong && __popc(scratch_on) == N) { terminated = true; bonus_m = allN; }
+            if (!kLifelong && __popc(scratch_on) == N) { terminated = true; bonus_m = allN; }
             else if (step_count >= p.steps_per_episode) {
                 terminated = true; truncated = true;  // F6
-                if (!p.lifelong) penalty_m = allN & ~scratch_on;
+                if (!kLifelong) penalty_m = allN & ~scratch_on;
             }
             done = ok && (terminated || truncated);
             int rsum = __popc(gstep_m) + 2 * __popc(bonus_m) - 2 * __popc(penalty_m);
@@ -879,7 +883,7 @@ __global__ void __launch_bounds__(LPE == 1 ? 448 : 512, 1) mapf_step_env_kernel(
             if (ok && sub == 0) {
                 if (p.o_info) {  // integer sources of info["__all__"], ENV:639-656
                     int4 *io = p.o_info + (size_t)env * 4;
-                    io[0] = make_int4(arrivals, p.lifelong ? goals_total : n_reach, blocking_step, blocking_total);
+                    io[0] = make_int4(arrivals, kLifelong ? goals_total : n_reach, blocking_step, blocking_total);
                     io[1] = make_int4(dl_step, ll_step, dl_event, ll_event);
                     io[2] = make_int4(dl_events, ll_events, dl_steps, ll_steps);
                     io[3] = make_int4(n_comp, step_count, n_reach, wfg_steps);
@@ -896,7 +900,7 @@ __global__ void __launch_bounds__(LPE == 1 ? 448 : 512, 1) mapf_step_env_kernel(
             // ------------------------------------------------------------ episode end: metrics, auto-reset
             if (done && sub == 0) {   // episode-end metric sums, src/trainers/callbacks.py:152,173,335-345
                 double *m = p.env_metrics + (size_t)env * MAPF_METRIC_COUNT;
-                const double gt = p.lifelong ? (double)goals_total : (double)n_reach;  // ENV:630-633
+                const double gt = kLifelong ? (double)goals_total : (double)n_reach;  // ENV:630-633
                 m[MAPF_M_EPISODES] += 1.0;
                 m[MAPF_M_RETURN_SUM] += 0.5 * (double)ep_return_x2;
                 m[MAPF_M_LENGTH_SUM] += (double)step_count;
@@ -948,7 +952,7 @@ __global__ void __launch_bounds__(LPE == 1 ? 448 : 512, 1) mapf_step_env_kernel(
                     stq32<VEC>(p.positions, ab + i0, i0, N, true, stq);
                     if (sample) { stq32<VEC>(p.starts, ab + i0, i0, N, true, stq); stq32<VEC>(p.goals, ab + i0, i0, N, true, ggq); }
                     stq8<VEC>(p.agent_flags, ab + i0, i0, N, true, 0u);
-                    if (p.lock_enabled) {
+                    if (kLock) {
                         const uint4 z = make_uint4(0, 0, 0, 0);
                         stq32<VEC>(p.lock_gp, ab + i0, i0, N, true, z);
                         stq32<VEC>(p.lock_mv, ab + i0, i0, N, true, z);
@@ -992,7 +996,7 @@ __global__ void __launch_bounds__(LPE == 1 ? 448 : 512, 1) mapf_step_env_kernel(
             uint4 gpq = make_uint4(0, 0, 0, 0), mvq = gpq, fmq = gpq;
             uint2 ringq = make_uint2(0u, 0u);
             if (stepmode) {
-                if (p.lock_enabled) {
+                if (kLock) {
                     gpq = ldq32<VEC>(p.lock_gp, ab + i0, i0, N, ok, 0u);
                     mvq = ldq32<VEC>(p.lock_mv, ab + i0, i0, N, ok, 0u);
                     fmq = ldq32<VEC>(p.lock_fm, ab + i0, i0, N, ok, 0u);
@@ -1036,7 +1040,7 @@ __global__ void __launch_bounds__(LPE == 1 ? 448 : 512, 1) mapf_step_env_kernel(
                     // ENV:538-563.  A lifelong arrival gets its new goal after the walk (round 1), in agent order.
                     const bool on_goal = ok && code == gcode;
                     bool gstep = false, cur_on_goal = on_goal;
-                    if (!p.lifelong) {
+                    if (!kLifelong) {
                         if (on_goal && !(reached_m & bit)) { reached_m |= bit; completed_m |= bit; gstep = true; }
                     } else if (on_goal) {
                         gstep = true;
@@ -1047,9 +1051,9 @@ __global__ void __launch_bounds__(LPE == 1 ? 448 : 512, 1) mapf_step_env_kernel(
                     if (cur_on_goal) ongoal_m |= bit;
                     // ENV:581-594 lock history
                     uint32_t delta16 = 0;
-                    if (p.lock_enabled) {
-                        const bool prev_on_goal = p.lifelong ? false : (ocode == gcode);
-                        const bool gp = p.lifelong ? gstep : (!prev_on_goal && cur_on_goal);
+                    if (kLock) {
+                        const bool prev_on_goal = kLifelong ? false : (ocode == gcode);
+                        const bool gp = kLifelong ? gstep : (!prev_on_goal && cur_on_goal);
                         const uint32_t g2 = (qget(gpq, k) << 1) | (gp ? 1u : 0u);
                         const uint32_t m2 = (qget(mvq, k) << 1) | (moves ? 1u : 0u);
                         const uint32_t f2 = (qget(fmq, k) << 1) | (failed ? 1u : 0u);
@@ -1140,7 +1144,7 @@ __global__ void __launch_bounds__(LPE == 1 ? 448 : 512, 1) mapf_step_env_kernel(
             if (stepmode) {
                 stq32<VEC>(p.positions, ab + i0, i0, N, ok,
                            make_uint4(packed_of(cd[0]), packed_of(cd[1]), packed_of(cd[2]), packed_of(cd[3])));
-                if (p.lock_enabled) {
+                if (kLock) {
                     stq32<VEC>(p.lock_gp, ab + i0, i0, N, ok, gpq);
                     stq32<VEC>(p.lock_mv, ab + i0, i0, N, ok, mvq);
                     stq32<VEC>(p.lock_fm, ab + i0, i0, N, ok, fmq);
