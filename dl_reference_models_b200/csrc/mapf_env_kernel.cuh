@@ -419,7 +419,7 @@ __global__ void __launch_bounds__(LPE == 1 ? 448 : 512, 1) mapf_step_env_kernel(
         bprev_m |= gather4(fl4, 2) << i0;        // MAPF_AF_BLOCKING_PREV
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            if (i0 + k < N) {
+            if (VEC || i0 + k < N) {   // VEC: N is a multiple of 4, every quad is full
                 const uint32_t code = code_of(qget(pq, k)), gcode = code_of(qget(gq, k));
                 int a = (int)(int8_t)(act4 >> (8 * k));
                 if (a < 0 || a > 4) { errs |= MAPF_DEV_ERR_INVALID_ACTION; a = 0; }
@@ -939,7 +939,7 @@ __global__ void __launch_bounds__(LPE == 1 ? 448 : 512, 1) mapf_step_env_kernel(
                     if (p.deterministic) detst = ldq32<VEC>(p.starts, ab + i0, i0, N, true, 0u);
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        if (i0 + k >= N) continue;
+                        if (!VEC && i0 + k >= N) continue;
                         uint32_t st, gg;
                         if (p.deterministic) { st = qget(detst, k); gg = qget(curg, k); }  // F7
                         else if (sample) {
@@ -960,7 +960,7 @@ __global__ void __launch_bounds__(LPE == 1 ? 448 : 512, 1) mapf_step_env_kernel(
                     }
                     // records of the new episode: position only
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) if (i0 + k < N) rec[(i0 + k) * EPW] = code_of(qget(stq, k)) | (code_of(qget(ggq, k)) << 16);
+                    for (int k = 0; k < 4; ++k) if (VEC || i0 + k < N) rec[(i0 + k) * EPW] = code_of(qget(stq, k)) | (code_of(qget(ggq, k)) << 16);
                 }
                 step_count = 0; lock_count = 0; lock_head = 0; lock_prev = 0; goals_total = 0; blocking_total = 0;
                 dl_events = ll_events = dl_steps = ll_steps = 0; ep_return_x2 = 0; wfg_steps = 0;
@@ -990,7 +990,7 @@ __global__ void __launch_bounds__(LPE == 1 ? 448 : 512, 1) mapf_step_env_kernel(
             const int i0 = 4 * q;
             uint32_t rv4[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) rv4[k] = (i0 + k < N) ? rec[(i0 + k) * EPW] : 0u;
+            for (int k = 0; k < 4; ++k) rv4[k] = (VEC || i0 + k < N) ? rec[(i0 + k) * EPW] : 0u;
             uint4 gq = make_uint4(0, 0, 0, 0);
             if (!stepmode) gq = ldq32<VEC>(p.goals, ab + i0, i0, N, active, 0u);   // round 0 takes the goals from the records
             uint4 gpq = make_uint4(0, 0, 0, 0), mvq = gpq, fmq = gpq;
@@ -1014,7 +1014,7 @@ __global__ void __launch_bounds__(LPE == 1 ? 448 : 512, 1) mapf_step_env_kernel(
             for (int k = 0; k < 4; ++k) {
                 gd[k] = make_float2(0.f, 0.f);
                 patch[k] = -1;
-                if (i0 + k >= N) continue;
+                if (!VEC && i0 + k >= N) continue;
                 const uint32_t bit = 1u << (i0 + k);
                 uint32_t code = rv4[k] & REC_CODE;
                 const uint32_t gcode = stepmode ? (rv4[k] >> 16) : code_of(qget(gq, k));
