@@ -181,3 +181,10 @@ def test_tall_map_null_actions_and_invalid_actions():
         assert_same(a, b, oa, ob, f"step {s}")
     ea, eb = a.poll_errors(), b.poll_errors()
     assert ea == eb and (ea & nat.DEV_ERR_INVALID_ACTION)
+
+
+def test_generic_instantiation_on_the_fast_configuration(monkeypatch):
+    """Lifelong + lock metrics normally run the FAST instantiation of the env-per-thread kernel (those two switches
+    compile-time); MAPF_ENV_FAST=0 keeps the generic one on the same configuration -- still the same function."""
+    monkeypatch.setenv("MAPF_ENV_FAST", "0")
+    run_pair(c3(steps_per_episode=25), 2048 + 5, 60)
