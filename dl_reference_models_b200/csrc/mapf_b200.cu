@@ -886,7 +886,15 @@ int mapf_step_host(mapf_handle *h, const int8_t *actions, const int16_t *goal_ov
     const uint32_t ticket = ++h->ticket_seq;
     const bool trace = packed && getenv("MAPF_HOST_TRACE") != nullptr;
     const int64_t t_begin = std::chrono::steady_clock::now().time_since_epoch().count();
-    if (packed) mapf::host_pool_begin(h->pool);
+    // closes the step for the host threads on every exit path (an early error return must not leave them polling)
+    struct PoolStep {
+        mapf::HostPool *pool = nullptr;
+        ~PoolStep() { if (pool) mapf::host_pool_finish(pool); }
+    } pool_step;
+    if (packed) {
+        mapf::host_pool_begin(h->pool);
+        pool_step.pool = h->pool;
+    }
     for (int c = 0; c < S; ++c) {
         const int64_t e0 = plan[c].e0, n = plan[c].n;
         cudaStream_t st = (c & 1) ? h->hstream2 : h->hstream;
@@ -955,14 +963,13 @@ int mapf_step_host(mapf_handle *h, const int8_t *actions, const int16_t *goal_ov
             job.den_row = inv0; job.den_col = inv1;
             job.bytes_src = host_tmp.blocking_prev ? blk + na * RS : nullptr;
             job.bytes_dst = host_tmp.blocking_prev;
-            if (!mapf::host_pool_submit(h->pool, job, h->h_tickets + c, ticket)) {
-                mapf::host_pool_finish(h->pool);
+            if (!mapf::host_pool_submit(h->pool, job, h->h_tickets + c, ticket))
                 return fail(MAPF_ERR_STATE, "host expansion queue overflow");
-            }
         }
     }
     const int64_t t_enq = std::chrono::steady_clock::now().time_since_epoch().count();
     if (packed) {
+        pool_step.pool = nullptr;
         if (!mapf::host_pool_finish(h->pool)) {  // this thread joins in; returns when every slice is expanded
             const cudaError_t e = cudaDeviceSynchronize();
             return fail(MAPF_ERR_CUDA, "mapf_step_host: a slice never arrived on the host (%s)", cudaGetErrorString(e));
