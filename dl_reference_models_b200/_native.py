@@ -102,7 +102,7 @@ class MapfPolicyArgs(C.Structure):
         ("seed", C.c_uint64), ("counter", C.c_uint64), ("env_id_base", C.c_int64),
     ] + [(k, C.c_void_p) for k in (
         "local_obs", "goal_delta", "blocking_prev", "action_mask", "weights", "actions", "actions64", "logp", "value",
-        "logits_out", "features_out")]
+        "logits_out", "features_out", "action_mask_out")]
 
 
 class MapfError(RuntimeError):

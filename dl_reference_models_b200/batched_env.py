@@ -174,22 +174,41 @@ class BatchedMapfEnv:
                                        C.byref(self._cout), self._stream()))
         return self._output()
 
-    def step(self, actions=None, goal_override=None, goal_rank=None, auto_reset: bool = False) -> StepOutput:
+    def step(self, actions=None, goal_override=None, goal_rank=None, auto_reset: bool = False, *, reward_out=None,
+             terminated_out=None, truncated_out=None) -> StepOutput:
         """ENV:474-695 for every env.  ``actions``: int8 [B,N] in 0..4 (None = all NO_OP).
 
         ``goal_rank`` (int32 [B,N], >= 0 replaces ``rng.integers(n)`` of ENV:300) and
         ``goal_override`` (int16 [B,N,2], row >= 0 replaces the drawn cell) are the replay hooks
-        that make lifelong runs bit-reproducible against a recorded reference trace."""
+        that make lifelong runs bit-reproducible against a recorded reference trace.
+
+        ``reward_out`` (float32 [B,N]), ``terminated_out`` / ``truncated_out`` (uint8 [B]): contiguous device tensors
+        the kernel writes those channels to instead of the env's own buffers -- a rollout loop hands in the rows of
+        its [T,...] buffers and needs no copy launches."""
         B, N = self.B, self.N
         a = self._dev_tensor(actions, torch.int8, (B, N))
         go = self._dev_tensor(goal_override, torch.int16, (B, N, 2))
         gr = self._dev_tensor(goal_rank, torch.int32, (B, N))
         # with the fused sampler the kernel may read this step's actions from the very buffer it refills
         # for the next step: every lane reads its own element before it writes it, so in-place is safe
+        cout, over = self._cout, {}
+        for key, t, dt, shape in (("reward", reward_out, torch.float32, (B, N)), ("terminated", terminated_out, torch.uint8, (B,)),
+                                  ("truncated", truncated_out, torch.uint8, (B,))):
+            if t is None:
+                continue
+            if t.dtype != dt or tuple(t.shape) != shape or not t.is_contiguous() or t.device != self.device:
+                raise ValueError(f"{key}_out must be a contiguous {dt} tensor of shape {shape} on {self.device}")
+            over[key] = t
+        if over:
+            cout = nat.MapfOutputs(**{k: (over[k] if k in over else self.out[k]).data_ptr() for k in nat.OUTPUT_FIELDS})
         nat.check(self._lib.mapf_step(self._h, self._ptr(a), self._ptr(go), self._ptr(gr),
-                                      C.byref(self._cout), int(bool(auto_reset)), self._stream()))
+                                      C.byref(cout), int(bool(auto_reset)), self._stream()))
         if getattr(self, "_fused", 0):
             self._sample_counter += 1
+        if over:
+            o = dict(self.out, **over)
+            return StepOutput(o["local_obs"], o["goal_delta"], o["blocking_prev"], o["action_mask"], o["reward"],
+                              o["terminated"], o["truncated"], o["step_flags"], o["agent_step_flags"], o["info"])
         return self._output()
 
     # ------------------------------------------------------------------ host-buffer transition

@@ -85,6 +85,13 @@ __global__ void __launch_bounds__(256) mapf_policy_act_kernel(const mapf_policy_
                 const uint32_t *mk32 = reinterpret_cast<const uint32_t *>(a.action_mask + ag0 * 5);
                 const int mwords = (na * 5 + 3) >> 2;
                 for (int i = lane; i < 40; i += 32) rawm[i] = i < mwords ? mk32[i] : 0u;
+                if (a.action_mask_out) {   // the rollout buffer's copy of the masks (saves a separate copy launch per step)
+                    uint32_t *mo32 = reinterpret_cast<uint32_t *>(a.action_mask_out + ag0 * 5);
+                    // word copies when the destination row is 4-byte aligned (a [T,B,N,5] row may start anywhere)
+                    const int full_words = (reinterpret_cast<uintptr_t>(a.action_mask_out) & 3) == 0 ? (na * 5) >> 2 : 0;
+                    for (int i = lane; i < full_words; i += 32) mo32[i] = mk32[i];
+                    for (int i = full_words * 4 + lane; i < na * 5; i += 32) a.action_mask_out[ag0 * 5 + i] = a.action_mask[ag0 * 5 + i];
+                }
             }
         }
         __syncwarp();

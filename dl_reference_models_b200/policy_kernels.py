@@ -51,9 +51,11 @@ class FusedPolicy:
         self._dev.copy_(torch.from_numpy(self._host))
 
     def act(self, out, logits_out: torch.Tensor | None = None, features_out: torch.Tensor | None = None,
-            logp: torch.Tensor | None = None, value: torch.Tensor | None = None, actions64: torch.Tensor | None = None):
+            logp: torch.Tensor | None = None, value: torch.Tensor | None = None, actions64: torch.Tensor | None = None,
+            mask_out: torch.Tensor | None = None):
         """One launch: features from ``out`` (the env's StepOutput) -> MLP -> masked categorical draw.
-        Returns (actions int8 [B,N], logp, value); optional tensors receive the masked logits / the float feature block."""
+        Returns (actions int8 [B,N], logp, value); optional tensors receive the masked logits / the float feature
+        block / a copy of the action masks (the rollout buffer's rows, so the loop needs no copy launches)."""
         env = self.env
         p = lambda t: None if t is None else C.c_void_p(t.data_ptr())  # noqa: E731
         logp = self.logp if logp is None else logp
@@ -66,7 +68,7 @@ class FusedPolicy:
             env_id_base=int(env.cfg.env_id_base), local_obs=p(out.local_obs), goal_delta=p(out.goal_delta),
             blocking_prev=p(out.blocking_prev) if self.with_bp else None, action_mask=p(out.action_mask),
             weights=p(self._dev), actions=p(self.actions), actions64=p(actions64), logp=p(logp), value=p(value),
-            logits_out=p(logits_out), features_out=p(features_out))
+            logits_out=p(logits_out), features_out=p(features_out), action_mask_out=p(mask_out))
         nat.check(self._lib.mapf_policy_act(C.byref(args), env._stream()))
         return self.actions, logp, value
 

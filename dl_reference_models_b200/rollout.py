@@ -69,33 +69,80 @@ def sample_categorical(logits: torch.Tensor):
     return a, torch.gather(logp_all, -1, a.unsqueeze(-1)).squeeze(-1)
 
 
+class FusedCollector:
+    """T-step rollouts with two kernel launches per env step and nothing else: the policy kernel
+    (:class:`policy_kernels.FusedPolicy`: bf16 tensor-core MLP straight from the env's output channels + masked draw)
+    and the env step write every per-step row of the [T,...] batch themselves (features, masks, actions, logp, values /
+    rewards, terminated, truncated), and the argument blocks of both launches are built once here, so the Python side
+    of a step is two ctypes calls.  The buffers are reused: the :class:`Batch` of one :meth:`collect` is overwritten
+    by the next."""
+
+    def __init__(self, env, fused, steps: int):
+        import ctypes as C
+
+        from . import _native as nat
+
+        self.env, self.fused, self.T = env, fused, int(steps)
+        B, N, T, dev = env.B, env.N, self.T, env.device
+        F = env.flat_obs_dim(include_action_mask=False)
+        self.feats = torch.empty((T, B, N, F), device=dev)
+        self.masks = torch.empty((T, B, N, 5), dtype=torch.int8, device=dev)
+        self.actions = torch.empty((T, B, N), dtype=torch.int64, device=dev)
+        self.logp = torch.empty((T, B, N), device=dev)
+        self.values = torch.empty((T, B, N), device=dev)
+        self.rewards = torch.empty((T, B, N), device=dev)
+        self.term = torch.empty((T, B), dtype=torch.uint8, device=dev)
+        self.trunc = torch.empty((T, B), dtype=torch.uint8, device=dev)
+        self.last_value = torch.empty((B, N), device=dev)
+        self._C, self._nat, self._lib = C, nat, nat.lib()
+        vp = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+        o = env.out
+
+        def policy_args(t):
+            last = t == T
+            return nat.MapfPolicyArgs(
+                num_envs=B, num_agents=N, v2=env.V * env.V, feature_dim=fused.F,
+                no_masking=int(bool(fused.policy.no_masking)), reserved=0, seed=fused.seed, counter=0,
+                env_id_base=int(env.cfg.env_id_base), local_obs=vp(o["local_obs"]), goal_delta=vp(o["goal_delta"]),
+                blocking_prev=vp(o["blocking_prev"]) if fused.with_bp else None, action_mask=vp(o["action_mask"]),
+                weights=vp(fused._dev), actions=vp(fused.actions),
+                actions64=vp(fused.actions64 if last else self.actions[t]), logp=vp(fused.logp if last else self.logp[t]),
+                value=vp(self.last_value if last else self.values[t]), logits_out=None,
+                features_out=None if last else vp(self.feats[t]), action_mask_out=None if last else vp(self.masks[t]))
+
+        self._pargs = [policy_args(t) for t in range(T + 1)]   # the last one: bootstrap value of the final observation
+        self._couts = [nat.MapfOutputs(**{k: ((self.rewards[t] if k == "reward" else self.term[t] if k == "terminated"
+                                               else self.trunc[t] if k == "truncated" else o[k]).data_ptr())
+                                          for k in nat.OUTPUT_FIELDS}) for t in range(T)]
+        self._actions_ptr = vp(fused.actions)
+
+    @torch.no_grad()
+    def collect(self) -> Batch:
+        """Roll T steps from the env's current observation (its output buffers, i.e. the last reset / step)."""
+        C, lib, env, fused = self._C, self._lib, self.env, self.fused
+        if getattr(env, "_fused", 0):
+            raise RuntimeError("turn the env's fused uniform sampler off (fuse_sampler(None)) before a policy rollout")
+        stream, h, check = env._stream(), env._h, self._nat.check
+        for t in range(self.T):
+            fused.counter += 1
+            a = self._pargs[t]
+            a.counter = fused.counter
+            check(lib.mapf_policy_act(C.byref(a), stream))
+            check(lib.mapf_step(h, self._actions_ptr, None, None, C.byref(self._couts[t]), 1, stream))
+        fused.counter += 1
+        a = self._pargs[self.T]
+        a.counter = fused.counter
+        check(lib.mapf_policy_act(C.byref(a), stream))
+        dones = (self.term | self.trunc).bool()
+        return Batch(self.feats, self.masks, self.actions, self.logp, self.values, self.rewards, dones, self.last_value)
+
+
 @torch.no_grad()
 def collect_fused(env, fused, steps: int, out=None) -> Batch:
-    """Like :func:`collect`, with policy forward + sampling in ONE CUDA launch per step
-    (:class:`policy_kernels.FusedPolicy`: bf16 tensor-core MLP straight from the env's output channels): per step
-    two launches in total -- the policy kernel and the env step."""
-    B, N = env.B, env.N
-    dev = env.device
-    F = env.flat_obs_dim(include_action_mask=False)
-    T = int(steps)
-    feats = torch.empty((T, B, N, F), device=dev)
-    masks = torch.empty((T, B, N, 5), dtype=torch.int8, device=dev)
-    actions = torch.empty((T, B, N), dtype=torch.int64, device=dev)
-    logp = torch.empty((T, B, N), device=dev)
-    values = torch.empty((T, B, N), device=dev)
-    rewards = torch.empty((T, B, N), device=dev)
-    dones = torch.empty((T, B), dtype=torch.bool, device=dev)
-    if out is None:
-        out = env._output()
-    for t in range(T):
-        masks[t].copy_(out.action_mask)
-        a, _, _ = fused.act(out, features_out=feats[t], logp=logp[t], value=values[t], actions64=actions[t])
-        out = env.step(a, auto_reset=True)
-        rewards[t].copy_(out.reward)
-        dones[t] = (out.terminated | out.truncated).bool()
-    last_value = torch.empty((B, N), device=dev)
-    fused.act(out, value=last_value)
-    return Batch(feats, masks, actions, logp, values, rewards, dones, last_value)
+    """Like :func:`collect`, with policy forward + sampling in ONE CUDA launch per step: two launches per env step in
+    total (fresh buffers per call; keep a :class:`FusedCollector` to reuse them).  ``out`` is accepted for symmetry
+    with :func:`collect`: the rollout always starts from the env's current output buffers."""
+    return FusedCollector(env, fused, steps).collect()
 
 
 @torch.no_grad()
@@ -209,10 +256,11 @@ def benchmark(num_envs: int = 65536, steps: int = 64, device: str = "cuda:0") ->
 
     env.fuse_sampler(None)
     fused = FusedPolicy(policy, env)
-    collect_fused(env, fused, 4)
+    collector = FusedCollector(env, fused, steps)
+    collector.collect()
     torch.cuda.synchronize(env.device)
     t0 = time.perf_counter()
-    collect_fused(env, fused, steps)
+    collector.collect()
     torch.cuda.synchronize(env.device)
     fused_s = time.perf_counter() - t0
     n = num_envs * env.N * steps

@@ -374,6 +374,7 @@ typedef struct mapf_policy_args {
     float *value;                 /* [B,N] value head */
     float *logits_out;            /* [B,N,5] masked logits, may be NULL */
     float *features_out;          /* [B,N,F] float32 feature block for the learner, may be NULL */
+    int8_t *action_mask_out;      /* [B,N,5] copy of action_mask for the rollout buffer, may be NULL */
 } mapf_policy_args;
 
 /* Bytes of the packed weight block for feature_dim F (negative = unsupported F). */

@@ -129,3 +129,36 @@ def test_fused_collect_trains():
     assert all(np.isfinite(v) for v in stats.values())
     fused.refresh()
     fused.act(env._output())
+
+
+def test_fused_collect_rows_are_what_a_manual_loop_sees():
+    """collect_fused hands the rows of its [T,...] buffers to the two kernels (masks via the policy kernel, reward /
+    terminated / truncated via the env step): they equal what a loop with explicit copies records, on an odd agent
+    count (partial mask words at the end of the batch) and across auto-resets."""
+    import torch
+
+    from dl_reference_models_b200.policy_kernels import FusedPolicy
+    from dl_reference_models_b200.rollout import ActionMaskPolicy, collect_fused
+
+    T = 62
+    ea, oa = make_env(B=203, n=7)
+    eb, ob = make_env(B=203, n=7)
+    torch.manual_seed(0)
+    policy = ActionMaskPolicy(ea.flat_obs_dim(include_action_mask=False)).to(ea.device)
+    fa, fb = FusedPolicy(policy, ea, seed=5), FusedPolicy(policy, eb, seed=5)
+    batch = collect_fused(ea, fa, T, oa)
+    out = ob
+    for t in range(T):
+        mask_t = out.action_mask.clone()
+        a, lp, v = fb.act(out)
+        assert torch.equal(batch.masks[t], mask_t), f"step {t}: masks"
+        assert torch.equal(batch.actions[t], a.long()), f"step {t}: actions"
+        assert torch.equal(batch.logp[t], lp), f"step {t}: logp"
+        out = eb.step(a, auto_reset=True)
+        assert torch.equal(batch.rewards[t], out.reward), f"step {t}: reward"
+        assert torch.equal(batch.dones[t], (out.terminated | out.truncated).bool()), f"step {t}: dones"
+    assert bool(batch.dones.any()), "the run crosses an episode end"
+    for k in ea.state:
+        assert torch.equal(ea.state[k], eb.state[k]), k
+    with pytest.raises(ValueError):
+        ea.step(None, reward_out=torch.zeros(3, device=ea.device))
