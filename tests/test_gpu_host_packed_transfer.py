@@ -171,3 +171,26 @@ def test_python_step_host_api_matches_device_api_and_oracle(monkeypatch):
         assert np.allclose(ob.buf["reward"], hb["reward"], atol=1e-6), f"step {s}: reward"
         if (ob.buf["terminated"] | ob.buf["truncated"]).any():
             break
+
+
+def test_pageable_host_arrays(monkeypatch):
+    """Plain numpy arrays (not pinned) as destinations and as the action source: the packed path stages in the
+    library's own pinned block and expands into whatever memory the caller gave."""
+    import numpy as np
+    import torch
+
+    monkeypatch.setenv("MAPF_HOST_PACK", "1")
+    B = 8192 + 64
+    cfg = c3()
+    a, b = make(cfg, B), make(cfg, B)
+    a.reset()
+    b.reset()
+    host = {k: np.full(tuple(v.shape), 111, dtype=v.cpu().numpy().dtype) for k, v in b.out.items()}
+    cout = nat.MapfOutputs(**{k: host[k].ctypes.data for k in nat.OUTPUT_FIELDS})
+    rng = np.random.default_rng(3)
+    for s in range(12):
+        acts = rng.integers(0, 5, (B, a.N)).astype(np.int8)
+        oa = a.step(torch.from_numpy(acts).cuda(), auto_reset=True)
+        nat.check(nat.lib().mapf_step_host(b._h, C.c_void_p(acts.ctypes.data), None, None, C.byref(cout), 1))
+        for k in OUT_KEYS:
+            assert np.array_equal(getattr(oa, k).cpu().numpy(), host[k]), f"step {s}: {k}"
