@@ -47,13 +47,40 @@ def default_traffic(kind: int):
     return {1: 54.3e6, 2: 75.3e6}.get(kind)
 
 
+SHAPES = {
+    # BASELINE.json configs[2] (the one `metric` is quoted on): the default
+    "c3": {"envs": 65536, "agents": 16, "lifelong": True, "steps_per_episode": 256, "map": "32x32",
+           "what": "32x32 map (30% obstacles, seed 2026), lifelong goal resampling"},
+    # configs[1]: the parity-replay shape, reported for throughput too
+    "c2": {"envs": 4096, "agents": 4, "lifelong": False, "steps_per_episode": 100, "map": "10x20",
+           "what": "ReferenceModel-2-1 map (10x20), episodic (terminate when all agents are home)"},
+    # configs[3]: deadlock-heavy corridors
+    "c4": {"envs": 65536, "agents": 32, "lifelong": False, "steps_per_episode": 256, "map": "32x32 corridors",
+           "what": "32x32 map of 1-wide corridors, episodic, deadlock-heavy"},
+}
+
+
+def apply_shape(args):
+    sh = SHAPES[args.shape]
+    if args.envs is None:
+        args.envs = sh["envs"]
+    if args.agents is None:
+        args.agents = sh["agents"]
+
+
 def workload(args) -> tuple[dict, np.ndarray]:
     from dl_reference_models_b200 import maps
 
-    grid = maps.random_obstacle_grid(32, 32, 0.30, 2026, min_free=2 * args.agents)
+    sh = SHAPES[args.shape]
+    if args.shape == "c2":
+        grid = maps.get_grid("ReferenceModel-2-1")
+    elif args.shape == "c4":
+        grid = maps.corridor_grid(32, 32)
+    else:
+        grid = maps.random_obstacle_grid(32, 32, 0.30, 2026, min_free=2 * args.agents)
     cfg = {
-        "num_agents": args.agents, "sensor_range": args.sensor_range, "steps_per_episode": 256,
-        "lifelong_mapf": True, "enable_lock_metrics": True, "deterministic": False, "seed": 999,
+        "num_agents": args.agents, "sensor_range": args.sensor_range, "steps_per_episode": sh["steps_per_episode"],
+        "lifelong_mapf": sh["lifelong"], "enable_lock_metrics": True, "deterministic": False, "seed": 999,
         "deadlock_window_steps": 8, "livelock_window_steps": 16,
     }
     return cfg, grid
@@ -61,10 +88,12 @@ def workload(args) -> tuple[dict, np.ndarray]:
 
 def config_dict(args, n_gpus: int) -> dict:
     return {
-        "workload": f"C3: {args.envs} envs x {args.agents} agents per GPU, 32x32 map (30% obstacles, seed 2026), "
-                    f"sensor_range {args.sensor_range}, lifelong goal resampling, lock metrics on, "
-                    "256 steps/episode, in-launch auto-reset, masked-uniform actions sampled on device",
-        "envs_per_gpu": args.envs, "num_agents": args.agents, "map": "32x32", "sensor_range": args.sensor_range,
+        "workload": f"{args.shape.upper()}: {args.envs} envs x {args.agents} agents per GPU, {SHAPES[args.shape]['what']}, "
+                    f"sensor_range {args.sensor_range}, lock metrics on, "
+                    f"{SHAPES[args.shape]['steps_per_episode']} steps/episode, in-launch auto-reset, "
+                    "masked-uniform actions sampled on device",
+        "envs_per_gpu": args.envs, "num_agents": args.agents, "map": SHAPES[args.shape]["map"],
+        "sensor_range": args.sensor_range,
         "sharding": f"envs x{n_gpus} (independent shards, no data-path collective)",
         "l2": f"{args.replicas} rotating replicas of the batch (working set > 126 MB L2 between launches)",
     }
@@ -334,7 +363,7 @@ def run_b200(args, rank: int, local_rank: int, world: int):
             "dtype": "int16/u8", "data": "synthetic", "impl": "b200", "config": config_dict(args, world),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": args.traffic_bytes if args.traffic_bytes is not None else (
-                             default_traffic(kind) if (B, N, V) == (65536, 16, 5) else None),
+                             default_traffic(kind) if (args.shape, B, N, V) == ("c3", 65536, 16, 5) else None),
                          "kernel": KERNEL_NAMES[kind], "kernel_ms": kernel_ms,
                          "algorithmic_bytes_per_launch": alg_bytes, "bytes_per_agent_step": bytes_per_as,
                          "peak_source": peak_src},
@@ -362,8 +391,10 @@ def main():
     ap.add_argument("--steps", type=int, default=4000)
     ap.add_argument("--warmup", type=int, default=100)
     ap.add_argument("--impl", choices=("b200", "reference"), default="b200")
-    ap.add_argument("--envs", type=int, default=65536, help="envs per GPU")
-    ap.add_argument("--agents", type=int, default=16)
+    ap.add_argument("--shape", choices=tuple(SHAPES), default="c3",
+                    help="named shape of BASELINE.json (default c3: the one the metric is quoted on)")
+    ap.add_argument("--envs", type=int, default=None, help="envs per GPU (default: the shape's)")
+    ap.add_argument("--agents", type=int, default=None)
     ap.add_argument("--sensor-range", type=int, default=2)
     ap.add_argument("--replicas", type=int, default=4, help="independent batches rotated between launches (L2 defeat)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
@@ -371,6 +402,7 @@ def main():
     ap.add_argument("--traffic-bytes", type=float, default=None,
                     help="dram bytes per step-kernel launch from the committed ncu --set full capture")
     args = ap.parse_args()
+    apply_shape(args)
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

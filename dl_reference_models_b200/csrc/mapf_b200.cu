@@ -536,7 +536,11 @@ int mapf_create(const mapf_config *cfg, mapf_handle **out) {
         // pays once the batch fills the GPU several times over (measured cross-over ~50k envs of 16 agents on 148 SMs);
         // below that the lane-per-agent kernel has 16x more warps in flight and wins.
         const long long ntiles = (c.num_envs + 31) / 32;
-        h->use_env_kernel = h->env_threads && (want_kernel == 2 || (want_kernel == 0 && ntiles >= 12LL * (nsm > 0 ? nsm : 1)));
+        // ... and only up to 16 agents: its chain grows with N and its shared-memory footprint per warp too (fewer
+        // resident warps, a second wave).  Measured at 65 536 envs, us per launch env-per-thread / lane-per-agent:
+        // N=4 24.9 / 36.0, N=8 35.3 / 47.4, N=16 64.9 / 84.3, N=24 157 / 147, N=32 237 / 154.
+        h->use_env_kernel = h->env_threads && (want_kernel == 2 || (want_kernel == 0 && c.num_agents <= 16 &&
+                                                                    ntiles >= 12LL * (nsm > 0 ? nsm : 1)));
         (void)ntiles;
     }
     cudaError_t e3 = cudaMalloc(&h->d_err, 4);
