@@ -188,3 +188,11 @@ def test_generic_instantiation_on_the_fast_configuration(monkeypatch):
     compile-time); MAPF_ENV_FAST=0 keeps the generic one on the same configuration -- still the same function."""
     monkeypatch.setenv("MAPF_ENV_FAST", "0")
     run_pair(c3(steps_per_episode=25), 2048 + 5, 60)
+
+
+@pytest.mark.parametrize("n", [4, 12])
+def test_full_quads_other_agent_counts(n):
+    """N % 4 == 0 takes the quad path without per-agent bound tests (and, lifelong + lock metrics, the FAST
+    instantiation): 1 and 3 quads per env, besides the 2 and 4 of the other tests."""
+    run_pair(c3(num_agents=n, steps_per_episode=30), 1024 + 9, 70)
+    run_pair(c3(num_agents=n, steps_per_episode=30, lifelong_mapf=False), 512 + 3, 70, masked=False)
