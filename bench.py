@@ -41,10 +41,10 @@ UNIT = "agent-steps/s"
 KERNEL_NAMES = {1: "mapf_step_kernel<16,2> (lane-per-agent)", 2: "mapf_step_env_kernel<2,true> (env-per-thread)"}
 
 
-def default_traffic(kind: int):
-    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the step kernel at the default C3 shape, from the
-    committed `ncu --set full` captures (profiles/README.md); None for other shapes."""
-    return {1: 54.3e6, 2: 75.3e6}.get(kind)
+def default_traffic(kind: int, shape: str = "c3"):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the step kernel at the named shape's default
+    size, from the committed `ncu --set full` captures (profiles/README.md); None where there is no capture."""
+    return {("c3", 1): 54.3e6, ("c3", 2): 75.3e6, ("c4", 1): 140.8e6}.get((shape, kind))
 
 
 SHAPES = {
@@ -363,7 +363,7 @@ def run_b200(args, rank: int, local_rank: int, world: int):
             "dtype": "int16/u8", "data": "synthetic", "impl": "b200", "config": config_dict(args, world),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": args.traffic_bytes if args.traffic_bytes is not None else (
-                             default_traffic(kind) if (args.shape, B, N, V) == ("c3", 65536, 16, 5) else None),
+                             default_traffic(kind, args.shape) if (B, N, V) == (65536, SHAPES[args.shape]["agents"], 5) else None),
                          "kernel": KERNEL_NAMES[kind], "kernel_ms": kernel_ms,
                          "algorithmic_bytes_per_launch": alg_bytes, "bytes_per_agent_step": bytes_per_as,
                          "peak_source": peak_src},
