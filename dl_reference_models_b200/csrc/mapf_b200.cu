@@ -60,7 +60,22 @@ KernelFn reset_for_sr(int sr) {
     }
     return nullptr;
 }
-KernelFn pick_step(int G, int sr) {
+// the default sensor range also comes with the lifelong / episodic switches compiled in (mode 1 / 2, lock metrics on)
+template <int G>
+KernelFn step_for_mode(int mode) {
+    if (mode == 1) return mapf::mapf_step_kernel<G, 2, 1>;
+    if (mode == 2) return mapf::mapf_step_kernel<G, 2, 2>;
+    return nullptr;
+}
+KernelFn pick_step(int G, int sr, int mode = 0) {
+    if (sr == 2 && mode != 0) {
+        switch (G) {
+            case 4: return step_for_mode<4>(mode);
+            case 8: return step_for_mode<8>(mode);
+            case 16: return step_for_mode<16>(mode);
+            case 32: return step_for_mode<32>(mode);
+        }
+    }
     switch (G) {
         case 4: return step_for_sr<4>(sr);
         case 8: return step_for_sr<8>(sr);
@@ -456,7 +471,11 @@ int mapf_create(const mapf_config *cfg, mapf_handle **out) {
     h->wpr = (c.cols + 2 * mapf::PAD + 31) / 32 + 1;
     h->map_words = (c.rows + 2 * mapf::PAD) * h->wpr;
     h->fw = (c.rows * c.cols + 31) / 32;
-    h->step_fn = pick_step(h->G, h->SR);
+    {
+        int mode = c.enable_lock_metrics ? (c.lifelong_mapf ? 1 : 2) : 0;
+        if (const char *ov = getenv("MAPF_LANE_FAST")) mode = atoi(ov) != 0 ? mode : 0;
+        h->step_fn = pick_step(h->G, h->SR, mode);
+    }
     h->reset_fn = pick_reset(h->G, h->SR);
     h->threads = 0;
     for (int t = 256; t >= 32; t >>= 1) {

@@ -465,8 +465,12 @@ __device__ __forceinline__ void draw_layout(const Philox &ph, uint32_t &rng_coun
 #ifndef MAPF_STEP_MIN_CTAS
 #define MAPF_STEP_MIN_CTAS 4
 #endif
-template <int G, int SR>
+// MODE: 0 = lifelong / lock-metric switches read from the parameters; 1 = lifelong + lock metrics, 2 = episodic +
+// lock metrics as compile-time constants (the untaken branches and their uniform tests drop out; same results).
+template <int G, int SR, int MODE = 0>
 __global__ void __launch_bounds__(256, MAPF_STEP_MIN_CTAS) mapf_step_kernel(const KParams p) {
+    const bool kLifelong = MODE == 1 ? true : MODE == 2 ? false : p.lifelong;
+    const bool kLock = MODE != 0 ? true : p.lock_enabled;
     constexpr int V = 2 * SR + 1, V2 = V * V;
     using WB = typename WinBits<V>::type;
     extern __shared__ __align__(16) uint32_t smem[];
@@ -553,7 +557,7 @@ __global__ void __launch_bounds__(256, MAPF_STEP_MIN_CTAS) mapf_step_kernel(cons
     if (lock_head < 0 || lock_head >= p.lw) lock_head = 0;
     const int slot_new = lock_head;
     const int slot_next = (lock_head + 1 == p.lw) ? 0 : lock_head + 1;
-    if (p.lock_enabled && act) {
+    if (kLock && act) {
         gpr = p.lock_gp[ai]; mvr = p.lock_mv[ai]; fmr = p.lock_fm[ai];
         if (count_after >= p.lw && p.lw > 1)  // slot_next still holds the oldest row of the window, ENV:432
             ring_old = (int)p.lock_dist[((size_t)env * p.lw + slot_next) * N + gl];
@@ -626,7 +630,7 @@ __global__ void __launch_bounds__(256, MAPF_STEP_MIN_CTAS) mapf_step_kernel(cons
     bool gstep = false;
     uint32_t goal_new = goal;
     unsigned arrivals = 0;
-    if (!p.lifelong) {
+    if (!kLifelong) {
         if (on_goal && !(aflags & MAPF_AF_REACHED)) {
             aflags |= MAPF_AF_REACHED | MAPF_AF_COMPLETED_ONCE;
             reward_x2 += 1; gstep = true;
@@ -680,18 +684,18 @@ __global__ void __launch_bounds__(256, MAPF_STEP_MIN_CTAS) mapf_step_kernel(cons
         }
         goals_total += __popc(arrivals);
     }
-    if (!p.lifelong) goals_total += __popc(__ballot_sync(full, gstep) & gmask);
+    if (!kLifelong) goals_total += __popc(__ballot_sync(full, gstep) & gmask);
     const bool reassigned = arrivals != 0;
     // ENV:555: an arrived lifelong agent is no longer "on goal"; others keep their test
     bool cur_on_goal = act && newpos == goal_new;
-    const bool reached_goal_scratch = p.lifelong ? false : cur_on_goal;
+    const bool reached_goal_scratch = kLifelong ? false : cur_on_goal;
 
     // ---------------------------------------------------------------- lock bookkeeping, ENV:581-594
     int dist_now = abs(prow(goal_new) - prow(newpos)) + abs(pcol(goal_new) - pcol(newpos));
     int delta = 0;
-    if (p.lock_enabled) {
-        const bool prev_on_goal = p.lifelong ? false : (pos == goal_new);
-        const bool gp = p.lifelong ? gstep : (!prev_on_goal && cur_on_goal);
+    if (kLock) {
+        const bool prev_on_goal = kLifelong ? false : (pos == goal_new);
+        const bool gp = kLifelong ? gstep : (!prev_on_goal && cur_on_goal);
         gpr = (gpr << 1) | (gp ? 1u : 0u);
         mvr = (mvr << 1) | (moved ? 1u : 0u);
         fmr = (fmr << 1) | (failed ? 1u : 0u);
@@ -749,7 +753,7 @@ __global__ void __launch_bounds__(256, MAPF_STEP_MIN_CTAS) mapf_step_kernel(cons
 
     // ---------------------------------------------------------------- lock detection, ENV:400-438,595-606
     bool dl_step = false, ll_step = false, dl_event = false, ll_event = false;
-    if (p.lock_enabled) {
+    if (kLock) {
         const uint32_t mdw = p.dw >= 32 ? full : ((1u << p.dw) - 1u);
         const uint32_t mlw = p.lw >= 32 ? full : ((1u << p.lw) - 1u);
         const unsigned Gd = (__ballot_sync(full, (gpr & mdw) != 0) & gmask) >> gbase;
@@ -798,10 +802,10 @@ __global__ void __launch_bounds__(256, MAPF_STEP_MIN_CTAS) mapf_step_kernel(cons
     reward_x2 -= 2 * po.colocated;
     const int n_on = __popc(__ballot_sync(full, act && reached_goal_scratch) & gmask);
     bool terminated = false, truncated = false;
-    if (!p.lifelong && n_on == N) {
+    if (!kLifelong && n_on == N) {
         reward_x2 += 2; terminated = true;
     } else if (step_count >= p.steps_per_episode) {
-        if (!p.lifelong && !reached_goal_scratch) reward_x2 -= 2;
+        if (!kLifelong && !reached_goal_scratch) reward_x2 -= 2;
         terminated = true; truncated = true;  // F6
     }
     if (!act) reward_x2 = 0;
@@ -828,7 +832,7 @@ __global__ void __launch_bounds__(256, MAPF_STEP_MIN_CTAS) mapf_step_kernel(cons
     if (env_ok && gl == 0) {
         if (p.o_info) {  // integer sources of info["__all__"], ENV:639-656
             int4 *io = p.o_info + (size_t)env * 4;
-            io[0] = make_int4(goals_step, p.lifelong ? goals_total : __popc(reach), blocking_step, blocking_total);
+            io[0] = make_int4(goals_step, kLifelong ? goals_total : __popc(reach), blocking_step, blocking_total);
             io[1] = make_int4(dl_step, ll_step, dl_event, ll_event);
             io[2] = make_int4(dl_events, ll_events, dl_steps, ll_steps);
             io[3] = make_int4(__popc(comp), step_count, __popc(reach), wfg_steps);
@@ -849,7 +853,7 @@ __global__ void __launch_bounds__(256, MAPF_STEP_MIN_CTAS) mapf_step_kernel(cons
     {
         if (done && gl == 0) {
             double *m = p.env_metrics + (size_t)env * MAPF_METRIC_COUNT;
-            const double gt = p.lifelong ? (double)goals_total : (double)__popc(reach);  // ENV:630-633
+            const double gt = kLifelong ? (double)goals_total : (double)__popc(reach);  // ENV:630-633
             m[MAPF_M_EPISODES] += 1.0;
             m[MAPF_M_RETURN_SUM] += 0.5 * (double)ep_return_x2;
             m[MAPF_M_LENGTH_SUM] += (double)step_count;
@@ -935,7 +939,7 @@ __global__ void __launch_bounds__(256, MAPF_STEP_MIN_CTAS) mapf_step_kernel(cons
         if (out_goal != goal) p.goals[ai] = out_goal;
         if (write_start) p.starts[ai] = out_start;
         p.agent_flags[ai] = (uint8_t)aflags;
-        if (p.lock_enabled) { p.lock_gp[ai] = gpr; p.lock_mv[ai] = mvr; p.lock_fm[ai] = fmr; }
+        if (kLock) { p.lock_gp[ai] = gpr; p.lock_mv[ai] = mvr; p.lock_fm[ai] = fmr; }
     }
     if (env_ok && gl == 0) {
         int4 *ew = p.env_words + (size_t)env * 4;
