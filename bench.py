@@ -274,8 +274,6 @@ def run_b200(args, rank: int, local_rank: int, world: int):
     for i in range(W):
         e = envs[i % len(envs)]
         e.step(e._next, auto_reset=True)
-    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
-    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = sum(e.launch_count for e in envs)
     sampler = ClockSampler(local_rank)
@@ -287,9 +285,7 @@ def run_b200(args, rank: int, local_rank: int, world: int):
     t_begin.record()
     for i in range(K):
         e = envs[(W + i) % len(envs)]
-        ev0[i].record()
         e.step(e._next, auto_reset=True)
-        ev1[i].record()
     t_end.record()
     barrier()
     sampler.mark_end()
@@ -297,7 +293,11 @@ def run_b200(args, rank: int, local_rank: int, world: int):
     launches = sum(e.launch_count for e in envs) - launches0
     kind = int(nat.lib().mapf_step_kernel_kind(envs[0]._h))
     ms_total = t_begin.elapsed_time(t_end)
-    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in zip(ev0, ev1)]))
+    # one step = ONE launch of the step kernel (checked below), so the kernel's average launch duration is the
+    # CUDA-event time of the region / K -- launch gaps included; no events between the launches (they would
+    # serialise the stream and keep the next launch's ramp-up from overlapping this launch's tail)
+    kernel_ms = ms_total / K
+    assert launches == K, (launches, K)
     for e in envs:
         e.raise_on_device_errors()
 

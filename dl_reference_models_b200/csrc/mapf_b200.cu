@@ -140,7 +140,7 @@ struct mapf_handle {
     EnvKernelFn env_fn;
     mapf::EnvLayout env_layout;
     int env_threads, env_grid;
-    bool use_env_kernel;
+    bool use_env_kernel, env_pdl;
     uint32_t *d_map_rows, *d_free_bits;
     uint32_t *d_env_tables;
     int32_t *d_num_free;
@@ -291,8 +291,39 @@ void fill_outputs(mapf::KParams &p, const mapf_outputs *o) {
 }
 
 int launch_env_step(mapf_handle *h, const mapf::KParams &p, cudaStream_t s) {
-    h->env_fn<<<h->env_grid, h->env_threads, h->env_layout.total_bytes, s>>>(p, h->env_layout);
-    CUDA_TRY(cudaGetLastError());
+    // launched with programmatic stream serialization: back-to-back steps overlap the next launch's ramp-up and
+    // table copy with this launch's tail (the kernel waits with griddepcontrol.wait before it touches env state)
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)h->env_grid);
+    cfg.blockDim = dim3((unsigned)h->env_threads);
+    cfg.dynamicSmemBytes = (size_t)h->env_layout.total_bytes;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = h->env_pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, h->env_fn, p, h->env_layout));
+    h->launches++;
+    return MAPF_OK;
+}
+
+// The step kernels contain griddepcontrol.wait and are launched with programmatic stream serialization (see
+// launch_env_step); every other kernel is launched the plain way (full stream order).
+int launch_lane_step(mapf_handle *h, const mapf::KParams &p, unsigned grid, cudaStream_t s) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3((unsigned)h->threads);
+    cfg.dynamicSmemBytes = h->smem_bytes;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = h->env_pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, h->step_fn, p));
     h->launches++;
     return MAPF_OK;
 }
@@ -303,6 +334,7 @@ int launch(mapf_handle *h, KernelFn fn, const mapf::KParams &p, cudaStream_t s) 
     unsigned grid = (unsigned)((h->cfg.num_envs + groups - 1) / groups);
     // the step kernel is persistent: one wave of resident CTAs walks over the env tiles
     if (fn == h->step_fn && h->step_grid_cap > 0 && grid > (unsigned)h->step_grid_cap) grid = (unsigned)h->step_grid_cap;
+    if (fn == h->step_fn) return launch_lane_step(h, p, grid, s);
     fn<<<grid, h->threads, h->smem_bytes, s>>>(p);
     CUDA_TRY(cudaGetLastError());
     h->launches++;
@@ -328,10 +360,7 @@ int launch_step_range(mapf_handle *h, mapf::KParams p, int64_t e0, int n, cudaSt
     const int groups = h->threads / h->G;
     unsigned grid = (unsigned)((n + groups - 1) / groups);
     if (h->step_grid_cap > 0 && grid > (unsigned)h->step_grid_cap) grid = (unsigned)h->step_grid_cap;
-    h->step_fn<<<grid, h->threads, h->smem_bytes, s>>>(p);
-    CUDA_TRY(cudaGetLastError());
-    h->launches++;
-    return MAPF_OK;
+    return launch_lane_step(h, p, grid, s);
 }
 
 int ensure_io(mapf_handle *h) {
@@ -510,6 +539,8 @@ int mapf_create(const mapf_config *cfg, mapf_handle **out) {
     // variable MAPF_STEP_KERNEL=lane|env overrides "auto").  Both are sm_100a kernels with identical results.
     h->env_threads = 0;
     h->use_env_kernel = false;
+    h->env_pdl = true;
+    if (const char *ov = getenv("MAPF_ENV_PDL")) h->env_pdl = atoi(ov) != 0;
     if (e1 == cudaSuccess && c.cols <= 32 && c.rows <= mapf::ENV_MAX_ROWS && !c.per_env_maps) {
         int lpe_mode = 1;   // MAPF_ENV_LPE=0: several lanes per env where the shape allows (experimental)
         if (const char *ov = getenv("MAPF_ENV_LPE")) lpe_mode = atoi(ov) == 0 ? 0 : 1;

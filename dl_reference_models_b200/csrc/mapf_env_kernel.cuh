@@ -347,6 +347,11 @@ __global__ void __launch_bounds__(LPE == 1 ? 448 : 512, 1) mapf_step_env_kernel(
         uint4 *dst = reinterpret_cast<uint4 *>(esm);
         for (int i = tid; i < (E.tables_bytes >> 4); i += blockDim.x) dst[i] = src[i];
     }
+    // Programmatic dependent launch: the next launch in the stream may place its CTAs as ours exit and run the
+    // table copy above (the tables are immutable between launches) while the slowest CTAs of this launch finish;
+    // everything that touches env state waits here for the previous launch to complete and flush.
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     __syncthreads();
     const char *t1b = reinterpret_cast<const char *>(esm + ENV_T1_OFF);
     const uint8_t *kth = esm + ENV_KTH_OFF;

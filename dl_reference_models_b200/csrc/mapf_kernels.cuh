@@ -503,6 +503,11 @@ __global__ void __launch_bounds__(256, MAPF_STEP_MIN_CTAS) mapf_step_kernel(cons
         for (int i = tid; i < p.fw; i += blockDim.x) fb[i] = p.free_bits[i];
         rows = mr; freebm = fb;
     }
+    // Programmatic dependent launch (the step is launched with stream serialization relaxed): the tables above are
+    // immutable between launches, so this much may run while the previous launch's last CTAs finish; env state is
+    // touched only after the previous launch has completed and flushed.
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     __syncthreads();
     uint8_t *stage = reinterpret_cast<uint8_t *>(smem + L.stage_off + warp * L.stage_words);
     const int envs_per_warp = 32 / G;
