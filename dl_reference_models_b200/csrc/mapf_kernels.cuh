@@ -160,7 +160,7 @@ __host__ __device__ inline SmemLayout make_layout(int G, int V2, int N, int wpr,
     L.gdt_off = o; L.gdt_words = (2 * R - 1) + (2 * C - 1); o += L.gdt_words;
     o = (o + 3) & ~3;
     int g = 0;
-    int GA = G;  // arrays padded to G entries (G is a multiple of 4)
+    int GA = G;  // arrays padded to G entries (G is a multiple of 4); the kernels rely on these five coming first
     L.g_new = g; g += GA;
     L.g_snap = g; g += GA;
     L.g_goal = g; g += GA;
@@ -486,8 +486,9 @@ __global__ void __launch_bounds__(256, MAPF_STEP_MIN_CTAS) mapf_step_kernel(cons
     constexpr int KB = bucket_pad(SR);
     const SmemLayout &L = p.L;
     uint32_t *gsm = smem + L.grp_off + grp * L.grp_words;
-    uint32_t *s_new = gsm + L.g_new, *s_snap = gsm + L.g_snap, *s_goal = gsm + L.g_goal;
-    uint32_t *s_int = gsm + L.g_int, *s_delta = gsm + L.g_delta, *s_scratch = gsm + L.g_scratch;
+    // the five per-agent arrays open the group block at fixed offsets (make_layout: G words each) -> immediates
+    uint32_t *s_new = gsm, *s_snap = gsm + G, *s_goal = gsm + 2 * G;
+    uint32_t *s_int = gsm + 3 * G, *s_delta = gsm + 4 * G, *s_scratch = gsm + L.g_scratch;
     uint32_t *s_rowm = gsm + L.g_rowm, *s_colm = gsm + L.g_colm;
     uint32_t *s_growm = gsm + L.g_growm, *s_gcolm = gsm + L.g_gcolm;
     uint32_t *s_orow = gsm + L.g_orow, *s_ocol = gsm + L.g_ocol;
@@ -978,8 +979,8 @@ __global__ void __launch_bounds__(256) mapf_reset_kernel(const KParams p) {
 
     const SmemLayout &L = p.L;
     uint32_t *gsm = smem + L.grp_off + grp * L.grp_words;
-    uint32_t *s_new = gsm + L.g_new, *s_snap = gsm + L.g_snap, *s_goal = gsm + L.g_goal;
-    uint32_t *s_int = gsm + L.g_int, *s_delta = gsm + L.g_delta;
+    uint32_t *s_new = gsm, *s_snap = gsm + G, *s_goal = gsm + 2 * G;
+    uint32_t *s_int = gsm + 3 * G, *s_delta = gsm + 4 * G;
     const float *gdt = reinterpret_cast<const float *>(smem + L.gdt_off);
     fill_goal_delta_table(reinterpret_cast<float *>(smem + L.gdt_off), p.R, p.C, p.normalize, p.den0, p.den1,
                           tid, blockDim.x);
