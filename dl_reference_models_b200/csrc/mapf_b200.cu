@@ -501,7 +501,8 @@ int mapf_create(const mapf_config *cfg, mapf_handle **out) {
     h->map_words = (c.rows + 2 * mapf::PAD) * h->wpr;
     h->fw = (c.rows * c.cols + 31) / 32;
     {
-        int mode = c.enable_lock_metrics ? (c.lifelong_mapf ? 1 : 2) : 0;
+        // compile-time modes: lock metrics on, lifelong (1) or episodic (2), map up to 32 x 32 (fixed mask layout)
+        int mode = (c.enable_lock_metrics && c.rows <= 32 && c.cols <= 32) ? (c.lifelong_mapf ? 1 : 2) : 0;
         if (const char *ov = getenv("MAPF_LANE_FAST")) mode = atoi(ov) != 0 ? mode : 0;
         h->step_fn = pick_step(h->G, h->SR, mode);
     }

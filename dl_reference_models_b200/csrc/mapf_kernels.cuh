@@ -167,14 +167,18 @@ __host__ __device__ inline SmemLayout make_layout(int G, int V2, int N, int wpr,
     L.g_int = g; g += GA;
     L.g_delta = g; g += GA;
     const int KB = bucket_pad(SR);
-    L.g_rowm = g; g += R + 2 * KB;
-    L.g_colm = g; g += C + 2 * KB;
-    L.g_growm = g; g += R + 2 * KB;
-    L.g_gcolm = g; g += C + 2 * KB;
-    L.g_orow = g; g += R + 2 * KB;
-    L.g_ocol = g; g += C + 2 * KB;
-    L.g_trow = g; g += R + 2 * KB;
-    L.g_tcol = g; g += C + 2 * KB;
+    // maps up to 32 x 32 get the same mask size whatever their shape: the kernels' compile-time modes address the
+    // eight masks (and the scratch bitmap behind them) with immediates
+    const int small_map = R <= 32 && C <= 32;
+    const int mrw = (small_map ? 32 : R) + 2 * KB, mcw = (small_map ? 32 : C) + 2 * KB;
+    L.g_rowm = g; g += mrw;
+    L.g_colm = g; g += mcw;
+    L.g_growm = g; g += mrw;
+    L.g_gcolm = g; g += mcw;
+    L.g_orow = g; g += mrw;
+    L.g_ocol = g; g += mcw;
+    L.g_trow = g; g += mrw;
+    L.g_tcol = g; g += mcw;
     g = (g + 3) & ~3;
     L.g_mask_words = g - L.g_rowm;
     L.g_scratch = g; g += fw;
@@ -488,11 +492,15 @@ __global__ void __launch_bounds__(256, MAPF_STEP_MIN_CTAS) mapf_step_kernel(cons
     uint32_t *gsm = smem + L.grp_off + grp * L.grp_words;
     // the five per-agent arrays open the group block at fixed offsets (make_layout: G words each) -> immediates
     uint32_t *s_new = gsm, *s_snap = gsm + G, *s_goal = gsm + 2 * G;
-    uint32_t *s_int = gsm + 3 * G, *s_delta = gsm + 4 * G, *s_scratch = gsm + L.g_scratch;
-    uint32_t *s_rowm = gsm + L.g_rowm, *s_colm = gsm + L.g_colm;
-    uint32_t *s_growm = gsm + L.g_growm, *s_gcolm = gsm + L.g_gcolm;
-    uint32_t *s_orow = gsm + L.g_orow, *s_ocol = gsm + L.g_ocol;
-    uint32_t *s_trow = gsm + L.g_trow, *s_tcol = gsm + L.g_tcol;
+    // MODE != 0 is only chosen for maps up to 32 x 32: fixed mask size MS (make_layout), everything an immediate
+    constexpr int MS = 32 + 2 * KB, MASK_WORDS = (8 * MS + 3) & ~3;
+    uint32_t *s_int = gsm + 3 * G, *s_delta = gsm + 4 * G;
+    uint32_t *s_scratch = MODE ? gsm + 5 * G + MASK_WORDS : gsm + L.g_scratch;
+    uint32_t *s_rowm = MODE ? gsm + 5 * G : gsm + L.g_rowm, *s_colm = MODE ? gsm + 5 * G + MS : gsm + L.g_colm;
+    uint32_t *s_growm = MODE ? gsm + 5 * G + 2 * MS : gsm + L.g_growm, *s_gcolm = MODE ? gsm + 5 * G + 3 * MS : gsm + L.g_gcolm;
+    uint32_t *s_orow = MODE ? gsm + 5 * G + 4 * MS : gsm + L.g_orow, *s_ocol = MODE ? gsm + 5 * G + 5 * MS : gsm + L.g_ocol;
+    uint32_t *s_trow = MODE ? gsm + 5 * G + 6 * MS : gsm + L.g_trow, *s_tcol = MODE ? gsm + 5 * G + 7 * MS : gsm + L.g_tcol;
+    const int mask_quads = MODE ? (MASK_WORDS >> 2) : (L.g_mask_words >> 2);
     const float *gdt = reinterpret_cast<const float *>(smem + L.gdt_off);
     // CTA-wide tables, loaded once; the CTA then walks over tiles of `groups` envs (persistent grid)
     fill_goal_delta_table(reinterpret_cast<float *>(smem + L.gdt_off), p.R, p.C, p.normalize, p.den0, p.den1,
@@ -524,7 +532,7 @@ __global__ void __launch_bounds__(256, MAPF_STEP_MIN_CTAS) mapf_step_kernel(cons
     const bool act = env_ok && gl < N;
     {   // clear the group's bucket masks (contiguous, 16-byte aligned, multiple of 4 words)
         uint4 *mz = reinterpret_cast<uint4 *>(s_rowm);
-        for (int i = gl; i < (L.g_mask_words >> 2); i += G) mz[i] = make_uint4(0, 0, 0, 0);
+        for (int i = gl; i < mask_quads; i += G) mz[i] = make_uint4(0, 0, 0, 0);
     }
     if (p.per_env_maps && env_ok) {
         uint32_t *mr = gsm + L.g_map, *fb = gsm + L.g_free;
