@@ -522,6 +522,7 @@ int mapf_create(const mapf_config *cfg, mapf_handle **out) {
         delete h;
         return fail(MAPF_ERR_UNSUPPORTED, "map %dx%d needs more shared memory than one SM has", c.rows, c.cols);
     }
+    if (h->threads != 256) h->step_fn = pick_step(h->G, h->SR, 0);   // the compile-time modes assume 256-thread CTAs
     cudaError_t e1 = cudaFuncSetAttribute(reinterpret_cast<const void *>(h->step_fn),
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
     cudaError_t e2 = cudaFuncSetAttribute(reinterpret_cast<const void *>(h->reset_fn),

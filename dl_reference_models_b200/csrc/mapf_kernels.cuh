@@ -481,7 +481,7 @@ __global__ void __launch_bounds__(256, MAPF_STEP_MIN_CTAS) mapf_step_kernel(cons
     const unsigned full = 0xFFFFFFFFu;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int gl = tid % G, grp = tid / G;
-    const int groups = blockDim.x / G;
+    const int groups = MODE ? 256 / G : blockDim.x / G;   // MODE != 0 is only chosen for 256-thread CTAs
     const unsigned gbase = (unsigned)(lane / G) * G;
     const unsigned gmask = (G == 32) ? full : (((1u << G) - 1u) << gbase);
     const int N = p.N;
