@@ -585,14 +585,15 @@ int mapf_create(const mapf_config *cfg, mapf_handle **out) {
                         c.rows, c.cols, c.per_env_maps);
         }
         // auto: the env-per-thread kernel is one latency chain per warp (~50 us on B200, whatever the batch), so it only
-        // pays once the batch fills the GPU several times over (measured cross-over ~50k envs of 16 agents on 148 SMs);
+        // pays once the batch fills the GPU several times over (measured at 16 agents on 148 SMs, us per step env / lane:
+        // 32 768 envs 49.4 / 35.0, 49 152 envs 46.7 / 51.0, 65 536 envs 59.9 / 66.2 => from 10 tiles of 32 envs per SM);
         // below that the lane-per-agent kernel has 16x more warps in flight and wins.
         const long long ntiles = (c.num_envs + 31) / 32;
         // ... and only up to 16 agents: its chain grows with N and its shared-memory footprint per warp too (fewer
         // resident warps, a second wave).  Measured at 65 536 envs, us per launch env-per-thread / lane-per-agent:
         // N=4 24.9 / 36.0, N=8 35.3 / 47.4, N=16 64.9 / 84.3, N=24 157 / 147, N=32 237 / 154.
         h->use_env_kernel = h->env_threads && (want_kernel == 2 || (want_kernel == 0 && c.num_agents <= 16 &&
-                                                                    ntiles >= 12LL * (nsm > 0 ? nsm : 1)));
+                                                                    ntiles >= 10LL * (nsm > 0 ? nsm : 1)));
         (void)ntiles;
     }
     cudaError_t e3 = cudaMalloc(&h->d_err, 4);
