@@ -38,7 +38,11 @@ sys.path.insert(0, str(REPO))
 METRIC = "agent_steps_per_sec"
 UNIT = "agent-steps/s"
 # mapf_step_kernel_kind() -> kernel symbol (include/mapf_b200.h)
-KERNEL_NAMES = {1: "mapf_step_kernel<16,2> (lane-per-agent)", 2: "mapf_step_env_kernel<2,true> (env-per-thread)"}
+def kernel_name(kind: int, num_agents: int, sensor_range: int) -> str:
+    if kind == 2:
+        return f"mapf_step_env_kernel<{sensor_range},...> (env-per-thread)"
+    g = 4 if num_agents <= 4 else 8 if num_agents <= 8 else 16 if num_agents <= 16 else 32
+    return f"mapf_step_kernel<{g},{sensor_range},...> (lane-per-agent)"
 
 
 def default_traffic(kind: int, shape: str = "c3"):
@@ -364,7 +368,7 @@ def run_b200(args, rank: int, local_rank: int, world: int):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": args.traffic_bytes if args.traffic_bytes is not None else (
                              default_traffic(kind, args.shape) if (B, N, V) == (65536, SHAPES[args.shape]["agents"], 5) else None),
-                         "kernel": KERNEL_NAMES[kind], "kernel_ms": kernel_ms,
+                         "kernel": kernel_name(kind, N, args.sensor_range), "kernel_ms": kernel_ms,
                          "algorithmic_bytes_per_launch": alg_bytes, "bytes_per_agent_step": bytes_per_as,
                          "peak_source": peak_src},
             "e2e": {"value": world * B * N * Ke / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
