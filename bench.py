@@ -45,12 +45,6 @@ def kernel_name(kind: int, num_agents: int, sensor_range: int) -> str:
     return f"mapf_step_kernel<{g},{sensor_range},...> (lane-per-agent)"
 
 
-def default_traffic(kind: int, shape: str = "c3"):
-    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the step kernel at the named shape's default
-    size, from the committed `ncu --set full` captures (profiles/README.md); None where there is no capture."""
-    return {("c3", 1): 54.3e6, ("c3", 2): 75.3e6, ("c4", 1): 140.8e6}.get((shape, kind))
-
-
 SHAPES = {
     # BASELINE.json configs[2] (the one `metric` is quoted on): the default
     "c3": {"envs": 65536, "agents": 16, "lifelong": True, "steps_per_episode": 256, "map": "32x32",
@@ -131,7 +125,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-i", str(self.index),
-                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "10"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except OSError:
@@ -238,17 +232,175 @@ def run_reference(args, rank: int, world: int):
         "data": "synthetic", "impl": "reference", "config": config_dict(args, args.gpus), "cpu_baseline": cb,
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "cpu_baseline_python": python_reference_run(args, seconds=10.0),
     }
     print(json.dumps(line), flush=True)
 
 
+def source_sha16() -> str:
+    """Hash of the kernel sources: ncu-derived numbers (roofline.traffic) are only valid for the build they came from."""
+    import hashlib
+
+    h = hashlib.sha256()
+    for f in sorted((REPO / "dl_reference_models_b200" / "csrc").glob("*")):
+        if f.suffix in (".cu", ".cuh", ".cpp", ".h"):
+            h.update(f.read_bytes())
+    return h.hexdigest()[:16]
+
+
+def committed_traffic(shape: str, kind: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
+    (profiles/traffic.json), only if it was taken on THIS build of the kernels; else None and the reason."""
+    f = REPO / "profiles" / "traffic.json"
+    if not f.exists():
+        return None, "no capture committed (profiles/traffic.json)"
+    try:
+        t = json.loads(f.read_text())
+    except Exception as exc:
+        return None, f"profiles/traffic.json unreadable: {exc}"
+    key = f"{shape}_{ {1: 'lane', 2: 'env'}.get(kind) }"
+    ent = t.get(key)
+    if not ent:
+        return None, f"no capture for {key} in profiles/traffic.json"
+    if ent.get("sources_sha16") != source_sha16():
+        return None, (f"capture {ent.get('file')} was taken on kernel sources {ent.get('sources_sha16')}, this build is "
+                      f"{source_sha16()}: stale, not reported")
+    return float(ent["dram_bytes_per_launch"]), ent.get("file")
+
+
+class SteadyBatch:
+    """`replicas` independent batches of one shape in benchmark state: episode phases staggered uniformly over the
+    episode length (so 1/steps_per_episode of the envs end -- and are reset inside the launch -- in EVERY step, like
+    run_benchmark's `if done: reset()` in steady state), lock windows full, masked sampler fused into the launch."""
+
+    def __init__(self, args, shape: str, dev, rank: int, replicas: int, burn: int = 64):
+        import copy
+
+        import torch
+
+        from dl_reference_models_b200 import _native as nat
+        from dl_reference_models_b200.batched_env import BatchedMapfEnv
+
+        a = copy.copy(args)
+        a.shape, a.envs, a.agents = shape, (args.envs if shape == args.shape else None), (args.agents if shape == args.shape else None)
+        apply_shape(a)
+        self.args, self.shape = a, shape
+        cfg, grid = workload(a)
+        cfg["grid"] = grid
+        self.cfg = cfg
+        self.B, self.N, self.V = a.envs, a.agents, 2 * a.sensor_range + 1
+        T = int(cfg["steps_per_episode"])
+        self.envs = [BatchedMapfEnv(cfg, self.B, dev, env_id_base=(rank * replicas + r) * self.B) for r in range(replicas)]
+        for r, e in enumerate(self.envs):
+            e.reset()
+            phase = (torch.arange(self.B, device=dev, dtype=torch.int64) * T // self.B + r * T // max(1, replicas)) % T
+            e.state["env_words"][:, nat.W_STEP_COUNT] = phase.to(torch.int32)
+            e._next = e.sample_actions(masked=True)
+            e.fuse_sampler("masked")
+        self.i = 0
+        self.burn_steps = burn
+        for _ in range(burn * replicas):   # untimed: fills the lock windows, gets goal arrivals and resets flowing
+            self.step()
+        self.kind = int(nat.lib().mapf_step_kernel_kind(self.envs[0]._h))
+
+    def step(self):
+        e = self.envs[self.i % len(self.envs)]
+        self.i += 1
+        e.step(e._next, auto_reset=True)
+
+    def launches(self) -> int:
+        return sum(e.launch_count for e in self.envs)
+
+    def metrics_vector(self):
+        v = self.envs[0].metrics_vector().clone()
+        for e in self.envs[1:]:
+            v += e.metrics_vector()
+        return v
+
+    def check(self):
+        for e in self.envs:
+            e.raise_on_device_errors()
+
+    def close(self):
+        for e in self.envs:
+            e.close()
+
+
+def timed_blocks(step, K: int, min_seconds: float, barrier, torch, max_blocks: int = 20000):
+    """Time blocks of EXACTLY K steps (CUDA events on the launching stream, no host sync between blocks) until the
+    region lasts >= min_seconds; returns the per-block times in ms.  One calibration block sizes the region."""
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    for _ in range(K):
+        step()
+    c1.record()
+    torch.cuda.synchronize()
+    est = max(c0.elapsed_time(c1), 1e-3)
+    nblocks = int(min(max_blocks, max(5, -(-min_seconds * 1e3 // est))))
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(nblocks + 1)]
+    barrier()
+    t_host0 = time.perf_counter()
+    ev[0].record()
+    for b in range(nblocks):
+        for _ in range(K):
+            step()
+        ev[b + 1].record()
+    barrier()
+    t_host1 = time.perf_counter()
+    return [ev[b].elapsed_time(ev[b + 1]) for b in range(nblocks)], ev[0].elapsed_time(ev[nblocks]), (t_host0, t_host1)
+
+
+def probe_host_ceilings(torch, dev, barrier, threads: int) -> dict:
+    """What bounds the host-buffer step, measured in this job with every rank probing at once: (1) device-to-host
+    DMA into pinned memory (PCIe and, on a multi-GPU node, the host memory system behind it), (2) host-to-device DMA,
+    (3) the host cores' streaming copy into cached memory (what the expansion threads and any consumer of the
+    delivered arrays have to do).  GB/s per rank."""
+    import numpy as np
+
+    n = 64 << 20
+    d = torch.empty(n, dtype=torch.uint8, device=dev)
+    h = torch.empty(n, dtype=torch.uint8).pin_memory()
+    out = {}
+    for name, (src, dst) in (("d2h_gbs", (d, h)), ("h2d_gbs", (h, d))):
+        dst.copy_(src, non_blocking=True)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(8):
+            dst.copy_(src, non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize()
+        out[name] = 8 * n / (e0.elapsed_time(e1) * 1e-3) / 1e9
+    # host streaming copy on `threads` threads (numpy releases the GIL inside copyto)
+    import concurrent.futures as cf
+
+    a = np.ones(n, np.uint8)
+    b = np.empty(n, np.uint8)
+    chunks = [(i * n // threads, (i + 1) * n // threads) for i in range(threads)]
+
+    def work(c):
+        for _ in range(4):
+            np.copyto(b[c[0]:c[1]], a[c[0]:c[1]])
+
+    with cf.ThreadPoolExecutor(threads) as ex:
+        list(ex.map(work, chunks))
+        barrier()
+        t0 = time.perf_counter()
+        list(ex.map(work, chunks))
+        dt = time.perf_counter() - t0
+    out["host_copy_gbs"] = 4 * n / dt / 1e9
+    out["host_copy_threads"] = threads
+    return out
+
+
 def run_b200(args, rank: int, local_rank: int, world: int):
+    import ctypes as C
+
     import torch
     import torch.distributed as dist
 
     from dl_reference_models_b200 import _native as nat
-    from dl_reference_models_b200.batched_env import BatchedMapfEnv
-    from dl_reference_models_b200.metrics import allreduce_metrics
+    from dl_reference_models_b200.metrics import AsyncMetrics, summarize
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (this framework has no CPU fallback; use --impl reference "
@@ -257,12 +409,6 @@ def run_b200(args, rank: int, local_rank: int, world: int):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    cfg, grid = workload(args)
-    cfg["grid"] = grid
-    B, N, V = args.envs, args.agents, 2 * args.sensor_range + 1
-    envs = [BatchedMapfEnv(cfg, B, dev, env_id_base=(rank * args.replicas + r) * B) for r in range(args.replicas)]
-    for e in envs:
-        e.reset()
     K, W = args.steps, args.warmup
 
     def barrier():
@@ -270,44 +416,69 @@ def run_b200(args, rank: int, local_rank: int, world: int):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    # the benchmark's masked action sampler is fused into the step launch: one kernel per env step
-    for e in envs:
-        e._next = e.sample_actions(masked=True)
-        e.fuse_sampler("masked")
+    def reduce_max(x: float) -> float:
+        if world == 1:
+            return float(x)
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
-    for i in range(W):
-        e = envs[i % len(envs)]
-        e.step(e._next, auto_reset=True)
-    t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    launches0 = sum(e.launch_count for e in envs)
+    def reduce_sum(x: float) -> float:
+        if world == 1:
+            return float(x)
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def reduced_metrics(sb) -> tuple[dict, dict]:
+        """The ONE collective of the path, checked on the hardware it runs on: all-reduce(sum) of the per-shard metric
+        vector against the sum of the per-rank vectors gathered separately."""
+        local = sb.metrics_vector()
+        am = AsyncMetrics(local, world, stream=torch.cuda.Stream(dev) if world > 1 else None)
+        total = am.result()
+        if world > 1:
+            parts = [torch.zeros_like(local) for _ in range(world)]
+            dist.all_gather(parts, local)
+            ref = torch.stack(parts).sum(0)
+        else:
+            ref = local
+        ref_s = summarize(ref)
+        keys = ("episodes", "length_sum", "goals_reached_sum", "deadlock_steps_sum", "livelock_steps_sum")
+        ok = all(total[k] == ref_s[k] for k in keys) and abs(total["throughput_sum"] - ref_s["throughput_sum"]) <= 1e-9 * max(
+            1.0, abs(ref_s["throughput_sum"]))
+        chk = {"ok": bool(ok), "ranks": world, "episodes_allreduced": total["episodes"], "episodes_sum_of_ranks": ref_s["episodes"],
+               "length_sum_allreduced": total["length_sum"], "length_sum_sum_of_ranks": ref_s["length_sum"]}
+        if not ok:
+            raise SystemExit(f"bench.py: metric all-reduce disagrees with the sum of the per-rank vectors: {chk}")
+        return total, chk
+
+    # ------------------------------------------------------------------ headline shape: device-resident steps
+    sb = SteadyBatch(args, args.shape, dev, rank, args.replicas)
+    B, N, V = sb.B, sb.N, sb.V
+    for _ in range(W):
+        sb.step()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
         sampler.wait_first_sample()
-    barrier()
+    launches0 = sb.launches()
     sampler.mark_begin()
-    t_begin.record()
-    for i in range(K):
-        e = envs[(W + i) % len(envs)]
-        e.step(e._next, auto_reset=True)
-    t_end.record()
-    barrier()
+    blocks, region_ms, _ = timed_blocks(sb.step, K, args.min_seconds, barrier, torch)
     sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
-    launches = sum(e.launch_count for e in envs) - launches0
-    kind = int(nat.lib().mapf_step_kernel_kind(envs[0]._h))
-    ms_total = t_begin.elapsed_time(t_end)
-    # one step = ONE launch of the step kernel (checked below), so the kernel's average launch duration is the
-    # CUDA-event time of the region / K -- launch gaps included; no events between the launches (they would
-    # serialise the stream and keep the next launch's ramp-up from overlapping this launch's tail)
-    kernel_ms = ms_total / K
-    assert launches == K, (launches, K)
-    for e in envs:
-        e.raise_on_device_errors()
+    launches = sb.launches() - launches0
+    nblocks = len(blocks)
+    # one step = ONE launch of the step kernel (checked below): a block's CUDA-event time / K is the kernel's average
+    # launch duration, launch gaps included
+    assert launches == K * (nblocks + 1), (launches, K, nblocks)   # + the calibration block
+    sb.check()
+    block_ms = float(np.median(blocks))
+    block_ms_max = reduce_max(block_ms)                      # slowest rank
+    kernel_ms = block_ms_max / K
+    metrics, allreduce_check = reduced_metrics(sb)
 
-    # ---- e2e: the C ABI's host-buffer entry point, pinned host memory, copies inside the timed region
-    import ctypes as C
-    e2e_env = envs[0]
+    # ------------------------------------------------------------------ e2e: the C ABI's host-buffer entry point
+    e2e_env = sb.envs[0]
     e2e_env.fuse_sampler(None)
     host_out = {
         "local_obs": torch.empty((B, N, V, V), dtype=torch.uint8).pin_memory(),
@@ -328,72 +499,282 @@ def run_b200(args, rank: int, local_rank: int, world: int):
     for i in range(We):
         nat.check(lib.mapf_step_host(e2e_env._h, C.c_void_p(host_actions[i % 4].data_ptr()), None, None,
                                      C.byref(cout), 1))
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(Ke):
-        nat.check(lib.mapf_step_host(e2e_env._h, C.c_void_p(host_actions[i % 4].data_ptr()), None, None,
-                                     C.byref(cout), 1))
-    torch.cuda.synchronize(dev)
-    e2e_s = time.perf_counter() - t0
+    e2e_blocks = []
+    for rep in range(3):
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(Ke):
+            nat.check(lib.mapf_step_host(e2e_env._h, C.c_void_p(host_actions[i % 4].data_ptr()), None, None,
+                                         C.byref(cout), 1))
+        torch.cuda.synchronize(dev)
+        e2e_blocks.append(reduce_max((time.perf_counter() - t0) * 1e3))
+    e2e_ms = float(np.median(e2e_blocks))
     checksum = float(host_out["reward"].sum())  # the step's result is really on the host
     # bytes that crossed PCIe in one call (the big per-agent channels travel bit-packed and are expanded into the
     # host arrays by the library's host threads inside the call; `delivered` is the size of the arrays filled)
     c_h2d, c_d2h = C.c_int64(0), C.c_int64(0)
     nat.check(lib.mapf_host_transfer_bytes(e2e_env._h, C.byref(c_h2d), C.byref(c_d2h)))
     h2d, d2h = int(c_h2d.value), int(c_d2h.value)
+    ncores = len(os.sched_getaffinity(0))
+    ceil = probe_host_ceilings(torch, dev, barrier, max(1, min(16, ncores // max(1, world))))
+    ceil = {k: (reduce_sum(v) if k.endswith("_gbs") else v) for k, v in ceil.items()}   # aggregate over the ranks
 
-    # ---- reduce over ranks (max time), metric all-reduce off the step path
-    t = torch.tensor([ms_total, kernel_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
-    nl = torch.tensor([float(launches)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(nl, op=dist.ReduceOp.SUM)
-    ms_total, kernel_ms, e2e_ms = (float(x) for x in t.tolist())
-    launches = int(nl.item())
-    mvec = envs[0].metrics_vector().clone()
-    for e in envs[1:]:
-        mvec += e.metrics_vector()
-    metrics = allreduce_metrics(mvec, world)
+    # ------------------------------------------------------------------ the other named shapes, same N (BASELINE configs 4, 5)
+    extra = {}
+    if not args.no_extra_shapes:
+        extra = extra_shapes(args, dev, rank, world, barrier, reduce_max, torch, dist)
 
     if rank == 0:
         peak, peak_src = measured_peaks()
         bytes_per_as = algorithmic_bytes_per_agent_step(N, V, True, 0)
         alg_bytes = bytes_per_as * B * N
         achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
-        value = world * B * N * K / (ms_total * 1e-3)
+        value = world * B * N * K / (block_ms_max * 1e-3)
+        traffic, traffic_src = (args.traffic_bytes, "--traffic-bytes") if args.traffic_bytes is not None else \
+            committed_traffic(args.shape, sb.kind)
+        e2e_value = world * B * N * Ke / (e2e_ms * 1e-3)
+        pcie_floor_ms = (d2h / 1e9) / max(ceil["d2h_gbs"] / world, 1e-9) * 1e3 + (h2d / 1e9) / max(ceil["h2d_gbs"] / world, 1e-9) * 1e3
+        host_floor_ms = (delivered / 1e9) / max(ceil["host_copy_gbs"] / world, 1e-9) * 1e3 if d2h < delivered else 0.0
+        floor_ms = max(pcie_floor_ms, host_floor_ms)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": block_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int16/u8", "data": "synthetic", "impl": "b200", "config": config_dict(args, world),
+            "timing": {"blocks": nblocks, "steps_per_block": K, "block_ms_median": block_ms_max,
+                       "block_ms_min_rank0": float(np.min(blocks)), "block_ms_max_rank0": float(np.max(blocks)),
+                       "region_ms_rank0": region_ms, "burn_in_steps_per_replica": sb.burn_steps,
+                       "note": "median block of exactly `steps` launches (slowest rank); steady state: episode phases "
+                               "staggered, 1/steps_per_episode of the envs reset inside every launch"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": args.traffic_bytes if args.traffic_bytes is not None else (
-                             default_traffic(kind, args.shape) if (B, N, V) == (65536, SHAPES[args.shape]["agents"], 5) else None),
-                         "kernel": kernel_name(kind, N, args.sensor_range), "kernel_ms": kernel_ms,
+                         "traffic": traffic, "traffic_source": traffic_src,
+                         "kernel": kernel_name(sb.kind, N, args.sensor_range), "kernel_ms": kernel_ms,
                          "algorithmic_bytes_per_launch": alg_bytes, "bytes_per_agent_step": bytes_per_as,
-                         "peak_source": peak_src},
-            "e2e": {"value": world * B * N * Ke / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                         "peak_source": peak_src, "sources_sha16": source_sha16()},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "delivered_bytes_per_step": delivered, "steps": Ke,
+                    "ms_per_step": e2e_ms / Ke,
                     "api": "mapf_step_host (C ABI, pinned host buffers)",
                     "transfer": ("bit-packed agent records over PCIe, expanded into the host arrays inside the call"
                                  if d2h < delivered else "plain copies"),
-                    "actions": "uniform random from pinned host buffers", "checksum": checksum},
-            "gpu_launches": int(launches), "clocks": clocks, "step_kernel": {1: "lane", 2: "env"}.get(kind),
+                    "actions": "uniform random from pinned host buffers", "checksum": checksum,
+                    "roofline": {"bound": "pcie" if pcie_floor_ms >= host_floor_ms else "host-memory",
+                                 "floor_ms_per_step": floor_ms, "pcie_floor_ms": pcie_floor_ms,
+                                 "host_write_floor_ms": host_floor_ms, "frac": floor_ms / (e2e_ms / Ke),
+                                 "measured_ceilings_aggregate": ceil, "host_cores": ncores,
+                                 "note": "ceilings probed in this job with all ranks at once: pinned D2H / H2D DMA and "
+                                         "the host cores' streaming copy rate; floor = this step's bytes / the rank's "
+                                         "share of them"}},
+            "gpu_launches": int(reduce_sum(launches) if world > 1 else launches), "clocks": clocks,
+            "step_kernel": {1: "lane", 2: "env"}.get(sb.kind),
             "episode_metrics": {k: metrics[k] for k in ("episodes", "goals_reached_mean", "deadlock_steps_mean",
-                                                        "livelock_steps_mean", "throughput_mean")},
+                                                        "livelock_steps_mean", "throughput_mean", "length_mean")},
+            "allreduce_check": allreduce_check,
+            "extra_shapes": extra,
         }
-        if world == 1 and not args.no_cpu_baseline:
+    else:
+        reduce_sum(launches) if world > 1 else None
+    sb.close()
+    if rank == 0:
+        if not args.no_cpu_baseline:   # rank 0 at every N: the other ranks wait at the barrier below
             line["cpu_baseline"] = cpu_port_run(args, seconds=args.cpu_seconds)
+            line["cpu_baseline_python"] = python_reference_run(args, seconds=min(20.0, 2 * args.cpu_seconds))
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+def extra_shapes(args, dev, rank, world, barrier, reduce_max, torch, dist) -> dict:
+    """BASELINE configs[3] and [4] at the same N, short: C4 = 32 agents on corridors with the metric all-reduce issued
+    every 256 steps on a side stream WHILE the steps keep launching; C5 = the on-device rollout loop (policy forward +
+    env step) beside the env-only rate.  Each with its own roofline entry."""
+    from dl_reference_models_b200 import policy_kernels
+    from dl_reference_models_b200.metrics import AsyncMetrics
+    from dl_reference_models_b200.rollout import ActionMaskPolicy, FusedCollector, collect
+
+    peak, _ = measured_peaks()
+    out = {}
+    # ---- C4
+    sb = SteadyBatch(args, "c4", dev, rank, replicas=2, burn=48)
+    steps, every = 768, 256
+    side = torch.cuda.Stream(dev)
+    pending = []
+    for _ in range(8):
+        sb.step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        sb.step()
+        if (i + 1) % every == 0:   # the reporting interval: snapshot + all-reduce on the side stream, steps go on
+            pending.append(AsyncMetrics(sb.metrics_vector(), world, stream=side if world > 1 else None))
+    e1.record()
+    barrier()
+    ms = reduce_max(e0.elapsed_time(e1))
+    sb.check()
+    reports = [p.result() for p in pending]
+    bpa = algorithmic_bytes_per_agent_step(sb.N, sb.V, True, 0)
+    if rank == 0:
+        ach = bpa * sb.B * sb.N / (ms / steps * 1e-3) / 1e9
+        out["c4"] = {"workload": config_dict(sb.args, world)["workload"], "value": world * sb.B * sb.N * steps / (ms * 1e-3),
+                     "unit": UNIT, "ms_per_step": ms / steps, "steps": steps, "step_kernel": {1: "lane", 2: "env"}.get(sb.kind),
+                     "metric_allreduces_during_stepping": len(reports), "allreduce_every_steps": every,
+                     "episodes_reported": [r["episodes"] for r in reports],
+                     "deadlock_steps_mean": reports[-1]["deadlock_steps_mean"], "livelock_steps_mean": reports[-1]["livelock_steps_mean"],
+                     "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                                  "bytes_per_agent_step": bpa, "kernel": kernel_name(sb.kind, sb.N, args.sensor_range)}}
+    sb.close()
+    # ---- C5: rollout loop on the C3 envs
+    sb = SteadyBatch(args, "c3", dev, rank, replicas=1, burn=32)
+    env = sb.envs[0]
+    T = 32
+    # env only (fused uniform sampler), same batch
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(T):
+        sb.step()
+    e1.record()
+    barrier()
+    env_ms = reduce_max(e0.elapsed_time(e1))
+    env.fuse_sampler(None)
+    torch.manual_seed(1234 + rank)
+    policy = ActionMaskPolicy(env.flat_obs_dim(include_action_mask=False)).to(dev)
+    # (a) PyTorch model forward + CUDA env step, as BASELINE words it
+    collect(env, policy, 2)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    collect(env, policy, 8)
+    e1.record()
+    barrier()
+    torch_ms = reduce_max(e0.elapsed_time(e1))
+    # (b) the fused policy kernel (bf16 tensor-core MLP + masked draw) + env step: two launches per step
+    fused = policy_kernels.FusedPolicy(policy, env)
+    col = FusedCollector(env, fused, T)
+    col.collect()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    col.collect()
+    e1.record()
+    barrier()
+    fused_ms = reduce_max(e0.elapsed_time(e1))
+    sb.check()
+    if rank == 0:
+        n = world * sb.B * sb.N
+        F = env.flat_obs_dim(include_action_mask=False)
+        # bytes the two launches of one fused step move per agent: env step + policy reads (window, delta, pressure,
+        # mask) and its batch rows (f32 features, mask, int64 action, logp, value)
+        bpa = algorithmic_bytes_per_agent_step(sb.N, sb.V, True, 0) + (sb.V * sb.V + 8 + 1 + 5) + (4 * F + 5 + 8 + 4 + 4)
+        ach = bpa * sb.B * sb.N / (fused_ms / T * 1e-3) / 1e9
+        out["c5"] = {"workload": f"C5: rollout loop on {sb.B} envs x {sb.N} agents per GPU (C3 envs), action-mask MLP "
+                                 f"{F}-64-64-(5,1)", "unit": UNIT,
+                     "env_only": n * T / (env_ms * 1e-3), "torch_policy_loop": n * 8 / (torch_ms * 1e-3),
+                     "fused_policy_loop": n * T / (fused_ms * 1e-3), "value": n * T / (fused_ms * 1e-3),
+                     "ms_per_step": fused_ms / T, "steps": T,
+                     "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                                  "bytes_per_agent_step": bpa, "kernel": "mapf_policy_act_kernel + step kernel (two launches per step)"}}
+    del col, fused
+    sb.close()
+    return out
+
+
+def python_reference_run(args, seconds: float = 20.0) -> dict:
+    """The reference's own Python env, driven the way scripts/benchmark_multi_agent_env.py:59-107 drives it (`masked`
+    mode, SURVEY F8 workaround: include_action_mask_in_obs=True), on P processes -- when the reference is on this
+    box (/root/reference in the build container; it is not vendored and does not travel to the GPU box)."""
+    import multiprocessing as mp
+
+    root = None
+    for cand in (Path("/root/reference"), REPO / "baseline" / "_ref"):
+        if (cand / "src" / "environments" / "reference_model_multi_agent.py").exists():
+            root = cand
+            break
+    if root is None:
+        return {"available": False, "why": "absent on this box: the Python reference is not vendored (looked for "
+                                           "/root/reference and baseline/_ref); the C port above is the CPU baseline"}
+    P = len(os.sched_getaffinity(0))
+    cfg, grid = workload(args)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_python_reference_worker, args=(str(root), cfg, grid, seconds, 123 + i, q)) for i in range(P)]
+    t0 = time.perf_counter()
+    for p in procs:
+        p.start()
+    res = [q.get() for _ in procs]
+    for p in procs:
+        p.join()
+    wall = time.perf_counter() - t0
+    bad = [r for r in res if "error" in r]
+    if bad:
+        return {"available": False, "why": f"reference import failed: {bad[0]['error']}"}
+    env_steps = sum(r["steps"] for r in res)
+    rate = sum(r["steps"] / r["elapsed"] for r in res)
+    cpu = ""
+    try:
+        cpu = next(l.split(":", 1)[1].strip() for l in open("/proc/cpuinfo") if l.startswith("model name"))
+    except Exception:
+        pass
+    return {"available": True, "value": rate * args.agents, "unit": UNIT, "kind": "reference", "cores": P, "cpu": cpu,
+            "per_process_env_steps_per_s": rate / P,
+            "sample": f"{P} processes x run_benchmark-style loop (masked actions, resets inside) of the unmodified "
+                      f"reference env at {root}, {env_steps} env-steps in {wall:.1f} s wall, same workload"}
+
+
+def _python_reference_worker(root, cfg, grid, seconds, seed, q):
+    try:
+        import logging
+
+        logging.disable(logging.CRITICAL)
+        sys.path.insert(0, str(REPO / "oracle" / "ref_stubs"))
+        sys.path.insert(1, root)
+        from src.environments import get_grid as ref_get_grid
+        from src.environments.reference_model_multi_agent import ReferenceModel
+
+        rcfg = {"env_name": "ReferenceModel-2-1", "num_agents": cfg["num_agents"], "sensor_range": cfg["sensor_range"],
+                "steps_per_episode": cfg["steps_per_episode"], "lifelong_mapf": cfg["lifelong_mapf"],
+                "enable_lock_metrics": True, "deterministic": False, "seed": seed, "render_env": False,
+                "deadlock_window_steps": cfg["deadlock_window_steps"], "livelock_window_steps": cfg["livelock_window_steps"],
+                "include_action_mask_in_obs": True, "training_execution_mode": "CTDE"}
+        orig = ref_get_grid.get_grid
+        ref_get_grid.get_grid = lambda name: np.array(grid, dtype=np.uint8)   # synthetic map (SURVEY F10)
+        try:
+            env = ReferenceModel(rcfg)
+        finally:
+            ref_get_grid.get_grid = orig
+        rng = np.random.default_rng(999 + seed)
+        sl = env._obs_slices["action_mask"]
+        obs, _ = env.reset()
+
+        def do_step(obs):
+            acts = {}
+            for a in env.agents:   # scripts/benchmark_multi_agent_env.py:42-57
+                valid = np.flatnonzero(obs[a][sl] > 0.5)
+                acts[a] = int(rng.choice(valid)) if valid.size else 0
+            obs, _, term, trunc, _ = env.step(acts)
+            if term["__all__"] or trunc["__all__"]:
+                obs, _ = env.reset()
+            return obs
+
+        for _ in range(50):
+            obs = do_step(obs)
+        t0 = time.perf_counter()
+        n = 0
+        while time.perf_counter() - t0 < seconds:
+            for _ in range(20):
+                obs = do_step(obs)
+            n += 20
+        q.put({"steps": n, "elapsed": time.perf_counter() - t0})
+    except Exception as exc:  # noqa: BLE001
+        q.put({"error": f"{type(exc).__name__}: {exc}"})
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=4000)
-    ap.add_argument("--warmup", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", choices=("b200", "reference"), default="b200")
     ap.add_argument("--shape", choices=tuple(SHAPES), default="c3",
                     help="named shape of BASELINE.json (default c3: the one the metric is quoted on)")
@@ -403,6 +784,9 @@ def main():
     ap.add_argument("--replicas", type=int, default=4, help="independent batches rotated between launches (L2 defeat)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra-shapes", action="store_true", help="skip the C4 / C5 legs of the JSON line")
+    ap.add_argument("--min-seconds", type=float, default=0.5,
+                    help="the timed region repeats blocks of --steps launches until it lasts this long (median block reported)")
     ap.add_argument("--traffic-bytes", type=float, default=None,
                     help="dram bytes per step-kernel launch from the committed ncu --set full capture")
     args = ap.parse_args()

@@ -36,7 +36,7 @@ DEV_ERR_INVALID_ACTION, DEV_ERR_NO_GOAL_CELL, DEV_ERR_TOO_FEW_CELLS = 1, 2, 4
  W_LIVELOCK_EVENTS, W_DEADLOCK_STEPS, W_LIVELOCK_STEPS, W_RNG_COUNTER, W_EPISODE_RETURN_X2,
  W_WFG_CYCLE_STEPS, W_EPISODES, W_LOCK_HEAD) = range(14)
 
-AF_REACHED, AF_COMPLETED_ONCE, AF_BLOCKING_PREV = 1, 2, 4
+AF_REACHED, AF_COMPLETED_ONCE, AF_BLOCKING_PREV, AF_NOT_OWNER = 1, 2, 4, 8
 
 METRIC_NAMES = (
     "episodes", "return_sum", "length_sum", "success_sum", "goals_reached_sum",
@@ -176,6 +176,7 @@ def lib():
     L.mapf_reset_host.argtypes = [vp, vp, vp, vp, C.POINTER(MapfOutputs)]
     L.mapf_step_host.argtypes = [vp, vp, vp, vp, C.POINTER(MapfOutputs), i32]
     L.mapf_host_transfer_bytes.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    L.mapf_host_wait_stream.argtypes = [vp, vp]
     L.mapf_packed_record_bytes.argtypes = [i32]
     L.mapf_unpack_records.argtypes = [vp, C.c_int64, i32, i32, vp, vp, vp, vp, C.c_float, C.c_float]
     L.mapf_flat_obs_dim.argtypes = [vp, i32, i32, i32]
@@ -209,7 +210,7 @@ EXPORTS = (
     "mapf_version", "mapf_last_error", "mapf_create", "mapf_destroy", "mapf_set_map",
     "mapf_state_nbytes", "mapf_bind_state", "mapf_alloc_state", "mapf_get_state_host",
     "mapf_set_state_host", "mapf_reset", "mapf_step", "mapf_reset_host", "mapf_step_host",
-    "mapf_host_transfer_bytes", "mapf_packed_record_bytes", "mapf_unpack_records",
+    "mapf_host_transfer_bytes", "mapf_host_wait_stream", "mapf_packed_record_bytes", "mapf_unpack_records",
     "mapf_observe", "mapf_observe_host",
     "mapf_flat_obs_dim", "mapf_pack_flat_obs", "mapf_sample_masked_actions",
     "mapf_sample_random_actions", "mapf_set_fused_sampler", "mapf_metrics_reduce", "mapf_poll_errors", "mapf_launch_count",

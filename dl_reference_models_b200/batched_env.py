@@ -239,6 +239,7 @@ class BatchedMapfEnv:
             s = np.ascontiguousarray(np.broadcast_to(np.asarray(starts, dtype=np.int16), (B, N, 2)))
             g = np.ascontiguousarray(np.broadcast_to(np.asarray(goals, dtype=np.int16), (B, N, 2)))
         vp = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)  # noqa: E731
+        nat.check(self._lib.mapf_host_wait_stream(self._h, self._stream()))   # torch work queued before this call
         nat.check(self._lib.mapf_reset_host(self._h, vp(m), vp(s), vp(g), C.byref(self._chost)))
         return self._host_np
 
@@ -257,6 +258,7 @@ class BatchedMapfEnv:
                 raise ValueError(f"expected actions of shape {(self.B, self.N)}, got {src.shape}")
             np.copyto(self._host_actions.numpy(), src, casting="unsafe")
             a = C.c_void_p(self._host_actions.data_ptr())
+        nat.check(self._lib.mapf_host_wait_stream(self._h, self._stream()))   # torch work queued before this call
         nat.check(self._lib.mapf_step_host(self._h, a, None, None, C.byref(self._chost), int(bool(auto_reset))))
         return self._host_np
 

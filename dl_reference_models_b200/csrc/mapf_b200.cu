@@ -42,21 +42,27 @@ int fail(int code, const char *fmt, ...) {
 
 using KernelFn = void (*)(const mapf::KParams);
 
+// MAPF_DEV_MINIMAL (kernel A/B experiments only, tools/build_variant.sh): instantiate sensor range 2 alone, so that
+// a variant library builds in a fraction of the time; every other shape then fails loudly in mapf_create.
 template <int G>
 KernelFn step_for_sr(int sr) {
     switch (sr) {
+#ifndef MAPF_DEV_MINIMAL
         case 1: return mapf::mapf_step_kernel<G, 1>;
-        case 2: return mapf::mapf_step_kernel<G, 2>;
         case 3: return mapf::mapf_step_kernel<G, 3>;
+#endif
+        case 2: return mapf::mapf_step_kernel<G, 2>;
     }
     return nullptr;
 }
 template <int G>
 KernelFn reset_for_sr(int sr) {
     switch (sr) {
+#ifndef MAPF_DEV_MINIMAL
         case 1: return mapf::mapf_reset_kernel<G, 1>;
-        case 2: return mapf::mapf_reset_kernel<G, 2>;
         case 3: return mapf::mapf_reset_kernel<G, 3>;
+#endif
+        case 2: return mapf::mapf_reset_kernel<G, 2>;
     }
     return nullptr;
 }
@@ -70,15 +76,19 @@ KernelFn step_for_mode(int mode) {
 KernelFn pick_step(int G, int sr, int mode = 0) {
     if (sr == 2 && mode != 0) {
         switch (G) {
+#ifndef MAPF_DEV_MINIMAL
             case 4: return step_for_mode<4>(mode);
             case 8: return step_for_mode<8>(mode);
+#endif
             case 16: return step_for_mode<16>(mode);
             case 32: return step_for_mode<32>(mode);
         }
     }
     switch (G) {
+#ifndef MAPF_DEV_MINIMAL
         case 4: return step_for_sr<4>(sr);
         case 8: return step_for_sr<8>(sr);
+#endif
         case 16: return step_for_sr<16>(sr);
         case 32: return step_for_sr<32>(sr);
     }
@@ -86,8 +96,10 @@ KernelFn pick_step(int G, int sr, int mode = 0) {
 }
 KernelFn pick_reset(int G, int sr) {
     switch (G) {
+#ifndef MAPF_DEV_MINIMAL
         case 4: return reset_for_sr<4>(sr);
         case 8: return reset_for_sr<8>(sr);
+#endif
         case 16: return reset_for_sr<16>(sr);
         case 32: return reset_for_sr<32>(sr);
     }
@@ -98,26 +110,24 @@ constexpr size_t kMaxSmem = 200 * 1024;
 constexpr size_t kMaxSmemEnv = 227 * 1024;  // opt-in limit of one sm_100 CTA
 
 using EnvKernelFn = void (*)(const mapf::KParams, const mapf::EnvLayout);
-template <bool VEC, int LPE>
+template <bool VEC, bool FAST>
 EnvKernelFn env_step_for_sr(int sr) {
     switch (sr) {
-        case 1: return mapf::mapf_step_env_kernel<1, VEC, LPE>;
-        case 2: return mapf::mapf_step_env_kernel<2, VEC, LPE>;
-        case 3: return mapf::mapf_step_env_kernel<3, VEC, LPE>;
+#ifndef MAPF_DEV_MINIMAL
+        case 1: return mapf::mapf_step_env_kernel<1, VEC, FAST>;
+        case 3: return mapf::mapf_step_env_kernel<3, VEC, FAST>;
+#endif
+        case 2: return mapf::mapf_step_env_kernel<2, VEC, FAST>;
     }
     return nullptr;
 }
-EnvKernelFn pick_env_step(int sr, bool vec, int lpe, bool fast) {
-    if (fast && vec && lpe == 1) {   // lifelong + lock metrics as compile-time constants
-        switch (sr) {
-            case 1: return mapf::mapf_step_env_kernel<1, true, 1, true>;
-            case 2: return mapf::mapf_step_env_kernel<2, true, 1, true>;
-            case 3: return mapf::mapf_step_env_kernel<3, true, 1, true>;
-        }
-    }
-    if (lpe == 4) return env_step_for_sr<true, 4>(sr);
-    if (lpe == 2) return env_step_for_sr<true, 2>(sr);
-    return vec ? env_step_for_sr<true, 1>(sr) : env_step_for_sr<false, 1>(sr);
+EnvKernelFn pick_env_step(int sr, bool vec, bool fast) {
+    if (fast && vec) return env_step_for_sr<true, true>(sr);   // lifelong + lock metrics as compile-time constants
+#ifndef MAPF_DEV_MINIMAL
+    return vec ? env_step_for_sr<true, false>(sr) : env_step_for_sr<false, false>(sr);
+#else
+    return vec ? env_step_for_sr<true, false>(sr) : nullptr;
+#endif
 }
 
 }  // namespace
@@ -165,6 +175,18 @@ struct mapf_handle {
     uint32_t ticket_seq;
     float gdt_row[256], gdt_col[256];
     int64_t last_h2d_bytes, last_d2h_bytes;
+    // tuning knobs of the host-buffer path, read from the environment ONCE (mapf_create), not per call
+    int knob_host_threads;      // MAPF_HOST_THREADS (0 = derive from the affinity mask)
+    int knob_host_pack;         // MAPF_HOST_PACK: -1 unset, 0 off, 1 on
+    int knob_host_slices;       // MAPF_HOST_SLICES (0 = default)
+    int knob_plan_n, knob_plan[kMaxHostSlices];   // MAPF_HOST_PLAN=w0,w1,...
+    int knob_raw32;             // MAPF_HOST_RAW_32NDS
+    bool knob_trace;            // MAPF_HOST_TRACE
+    int local_world;            // LOCAL_WORLD_SIZE (ranks sharing this node's cores), >= 1
+    // ordering of the *_host entry points (private streams) against work the caller queued on ITS stream
+    cudaEvent_t ev_user;
+    cudaStream_t last_user_stream;
+    bool user_dirty;
 };
 
 namespace {
@@ -290,6 +312,8 @@ void fill_outputs(mapf::KParams &p, const mapf_outputs *o) {
     p.o_info = reinterpret_cast<int4 *>(o->info);
 }
 
+void note_user_stream(mapf_handle *h, cudaStream_t s);
+
 int launch_env_step(mapf_handle *h, const mapf::KParams &p, cudaStream_t s) {
     // launched with programmatic stream serialization: back-to-back steps overlap the next launch's ramp-up and
     // table copy with this launch's tail (the kernel waits with griddepcontrol.wait before it touches env state)
@@ -329,6 +353,7 @@ int launch_lane_step(mapf_handle *h, const mapf::KParams &p, unsigned grid, cuda
 }
 
 int launch(mapf_handle *h, KernelFn fn, const mapf::KParams &p, cudaStream_t s) {
+    note_user_stream(h, s);
     if (fn == h->step_fn && h->use_env_kernel) return launch_env_step(h, p, s);
     const int groups = h->threads / h->G;
     unsigned grid = (unsigned)((h->cfg.num_envs + groups - 1) / groups);
@@ -404,21 +429,54 @@ int copy_outputs_back(mapf_handle *h, const mapf_outputs *host) {
     return MAPF_OK;
 }
 
-int host_threads_default() {
-    if (const char *ov = getenv("MAPF_HOST_THREADS")) {
-        const int v = atoi(ov);
-        if (v >= 1) return v > 64 ? 64 : v;
+void read_knobs(mapf_handle *h) {
+    h->knob_host_threads = 0; h->knob_host_pack = -1; h->knob_host_slices = 0; h->knob_plan_n = 0; h->knob_raw32 = 0;
+    h->knob_trace = getenv("MAPF_HOST_TRACE") != nullptr;
+    h->local_world = 1;
+    if (const char *ov = getenv("MAPF_HOST_THREADS")) { const int v = atoi(ov); if (v >= 1) h->knob_host_threads = v > 64 ? 64 : v; }
+    if (const char *ov = getenv("MAPF_HOST_PACK")) h->knob_host_pack = atoi(ov) != 0 ? 1 : 0;
+    if (const char *ov = getenv("MAPF_HOST_SLICES")) { const int v = atoi(ov); if (v >= 1) h->knob_host_slices = v > kMaxHostSlices ? kMaxHostSlices : v; }
+    if (const char *ov = getenv("MAPF_HOST_PLAN")) {
+        int k = 0;
+        for (const char *q = ov; *q && k < kMaxHostSlices;) {
+            const int v = atoi(q);
+            if (v >= 1) h->knob_plan[k++] = v;
+            while (*q && *q != ',') ++q;
+            if (*q == ',') ++q;
+        }
+        h->knob_plan_n = k;
     }
+    if (const char *ov = getenv("MAPF_HOST_RAW_32NDS")) { const int v = atoi(ov); if (v >= 0 && v <= 16) h->knob_raw32 = v; }
+    // one process per GPU: the ranks of a node share its cores (torchrun exports LOCAL_WORLD_SIZE)
+    if (const char *lw = getenv("LOCAL_WORLD_SIZE")) { const int w = atoi(lw); if (w > 1) h->local_world = w; }
+}
+
+int host_threads_default(const mapf_handle *h) {
+    if (h->knob_host_threads >= 1) return h->knob_host_threads;
     int n = 0;
     cpu_set_t set;
     if (sched_getaffinity(0, sizeof(set), &set) == 0) n = CPU_COUNT(&set);
-    // one process per GPU: the ranks of a node share its cores (torchrun exports LOCAL_WORLD_SIZE)
-    if (const char *lw = getenv("LOCAL_WORLD_SIZE")) {
-        const int w = atoi(lw);
-        if (w > 1) n /= w;
-    }
+    n /= h->local_world;
     if (n < 1) n = 1;
     return n > 16 ? 16 : n;
+}
+
+// The *_host entry points run on the handle's private streams.  Whatever the caller queued before -- through the
+// stream-taking entry points (remembered in last_user_stream) or on a stream it names with mapf_host_wait_stream --
+// must be ordered in front of them: one event, two waits, only when something is pending.
+int order_after_user_work(mapf_handle *h) {
+    if (!h->user_dirty) return MAPF_OK;
+    if (!h->ev_user) CUDA_TRY(cudaEventCreateWithFlags(&h->ev_user, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventRecord(h->ev_user, h->last_user_stream));
+    if (h->hstream) CUDA_TRY(cudaStreamWaitEvent(h->hstream, h->ev_user, 0));
+    if (h->hstream2) CUDA_TRY(cudaStreamWaitEvent(h->hstream2, h->ev_user, 0));
+    h->user_dirty = false;
+    return MAPF_OK;
+}
+void note_user_stream(mapf_handle *h, cudaStream_t s) {
+    if (s == h->hstream || s == h->hstream2) return;   // our own launches
+    h->last_user_stream = s;
+    h->user_dirty = true;
 }
 
 // The bit-packed transfer applies when the four big per-agent channels are all requested, the integer goal
@@ -430,8 +488,8 @@ int host_threads_default() {
 bool host_pack_applies(const mapf_handle *h, const mapf_outputs *host) {
     if (!host || !host->local_obs || !host->action_mask || !host->goal_delta || !host->reward) return false;
     if (h->cfg.rows > 128 || h->cfg.cols > 128 || h->cfg.num_envs < 8192) return false;
-    if (const char *ov = getenv("MAPF_HOST_PACK")) return atoi(ov) != 0;
-    return host_threads_default() >= 12;
+    if (h->knob_host_pack >= 0) return h->knob_host_pack != 0;
+    return host_threads_default(h) >= 12;
 }
 
 int ensure_pack(mapf_handle *h) {
@@ -448,7 +506,7 @@ int ensure_pack(mapf_handle *h) {
         h->gdt_row[d + 128] = h->cfg.normalize_goal_delta ? (float)d / den0 : (float)d;  // d / 1 == d
         h->gdt_col[d + 128] = h->cfg.normalize_goal_delta ? (float)d / den1 : (float)d;
     }
-    h->pool = mapf::host_pool_create(host_threads_default());
+    h->pool = mapf::host_pool_create(host_threads_default(h));
     h->pack_alloc = true;
     return MAPF_OK;
 }
@@ -492,6 +550,7 @@ int mapf_create(const mapf_config *cfg, mapf_handle **out) {
     if (!h) return fail(MAPF_ERR_STATE, "out of host memory");
     memset(h, 0, sizeof(*h));
     h->cfg = c;
+    read_knobs(h);
     h->G = c.num_agents <= 4 ? 4 : c.num_agents <= 8 ? 8 : c.num_agents <= 16 ? 16 : 32;
     h->SR = c.sensor_range;
     h->V2 = (2 * c.sensor_range + 1) * (2 * c.sensor_range + 1);
@@ -523,6 +582,11 @@ int mapf_create(const mapf_config *cfg, mapf_handle **out) {
         return fail(MAPF_ERR_UNSUPPORTED, "map %dx%d needs more shared memory than one SM has", c.rows, c.cols);
     }
     if (h->threads != 256) h->step_fn = pick_step(h->G, h->SR, 0);   // the compile-time modes assume 256-thread CTAs
+    if (!h->step_fn || !h->reset_fn) {
+        delete h;
+        return fail(MAPF_ERR_UNSUPPORTED, "no kernel instantiation for %d agents at sensor range %d in this build",
+                    c.num_agents, c.sensor_range);
+    }
     cudaError_t e1 = cudaFuncSetAttribute(reinterpret_cast<const void *>(h->step_fn),
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
     cudaError_t e2 = cudaFuncSetAttribute(reinterpret_cast<const void *>(h->reset_fn),
@@ -544,17 +608,14 @@ int mapf_create(const mapf_config *cfg, mapf_handle **out) {
     h->env_pdl = true;
     if (const char *ov = getenv("MAPF_ENV_PDL")) h->env_pdl = atoi(ov) != 0;
     if (e1 == cudaSuccess && c.cols <= 32 && c.rows <= mapf::ENV_MAX_ROWS && !c.per_env_maps) {
-        int lpe_mode = 1;   // MAPF_ENV_LPE=0: several lanes per env where the shape allows (experimental)
-        if (const char *ov = getenv("MAPF_ENV_LPE")) lpe_mode = atoi(ov) == 0 ? 0 : 1;
-        const int lpe = mapf::make_env_layout(c.num_agents, c.rows, c.cols, h->SR, h->fw, 1, lpe_mode).lpe;
-        const int epw = 32 / lpe, max_warps = lpe == 1 ? 14 : 16;   // __launch_bounds__ of mapf_step_env_kernel
-        const int ntiles = (c.num_envs + epw - 1) / epw;
+        const int max_warps = 14;   // __launch_bounds__ of mapf_step_env_kernel
+        const int ntiles = (c.num_envs + 31) / 32;
         int want = (ntiles + (nsm > 0 ? nsm : 1) - 1) / (nsm > 0 ? nsm : 1);  // warps per CTA for one resident wave
         if (want > max_warps) want = max_warps;
         if (want < 1) want = 1;
         if (const char *ov = getenv("MAPF_ENV_WARPS")) { const int v = atoi(ov); if (v >= 1 && v <= max_warps) want = v; }
         for (int w = want; w >= 1; --w) {
-            mapf::EnvLayout E = mapf::make_env_layout(c.num_agents, c.rows, c.cols, h->SR, h->fw, w, lpe_mode);
+            mapf::EnvLayout E = mapf::make_env_layout(c.num_agents, c.rows, c.cols, h->SR, h->fw, w);
             if ((size_t)E.total_bytes <= kMaxSmemEnv) {
                 h->env_threads = 32 * w;
                 h->env_layout = E;
@@ -564,7 +625,10 @@ int mapf_create(const mapf_config *cfg, mapf_handle **out) {
         if (h->env_threads) {
             bool fast = c.lifelong_mapf != 0 && c.enable_lock_metrics != 0;
             if (const char *ov = getenv("MAPF_ENV_FAST")) fast = fast && atoi(ov) != 0;
-            h->env_fn = pick_env_step(h->SR, c.num_agents % 4 == 0, lpe, fast);
+            h->env_fn = pick_env_step(h->SR, c.num_agents % 4 == 0, fast);
+            if (!h->env_fn) h->env_threads = 0;
+        }
+        if (h->env_threads) {
             e1 = cudaFuncSetAttribute(reinterpret_cast<const void *>(h->env_fn),
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmemEnv);
             const int w = h->env_threads / 32;
@@ -626,6 +690,7 @@ int mapf_destroy(mapf_handle *h) {
     }
     if (h->hstream) cudaStreamDestroy(h->hstream);
     if (h->hstream2) cudaStreamDestroy(h->hstream2);
+    if (h->ev_user) cudaEventDestroy(h->ev_user);
     cudaFree(h->d_map_rows); cudaFree(h->d_free_bits); cudaFree(h->d_num_free); cudaFree(h->d_err);
     cudaFree(h->d_env_tables);
     delete h;
@@ -676,7 +741,7 @@ int mapf_set_map(mapf_handle *h, const uint8_t *grid) {
         const mapf::EnvLayout &E = h->env_layout;
         std::vector<unsigned char> img((size_t)E.tables_bytes, 0);
         mapf::build_env_tables(h->SR, R, C, h->wpr, h->fw, rows.data(), freeb.data(), h->cfg.normalize_goal_delta != 0,
-                               (float)(R - 1 > 1 ? R - 1 : 1), (float)(C - 1 > 1 ? C - 1 : 1), img.data());
+                               (float)(R - 1 > 1 ? R - 1 : 1), (float)(C - 1 > 1 ? C - 1 : 1), img.data(), E.t2_off);
         CUDA_TRY(cudaMalloc(&h->d_env_tables, img.size()));
         CUDA_TRY(cudaMemcpy(h->d_env_tables, img.data(), img.size(), cudaMemcpyHostToDevice));
     }
@@ -731,9 +796,12 @@ int mapf_get_state_host(mapf_handle *h, const mapf_state *host) {
     state_sizes(h, n);
     mapf_state hs = *host;
     CUDA_TRY(cudaDeviceSynchronize());
+    if (!h->hstream) CUDA_TRY(cudaStreamCreateWithFlags(&h->hstream, cudaStreamNonBlocking));
     for (int i = 0; i < 10; ++i)
         if (*state_member(&hs, i))
-            CUDA_TRY(cudaMemcpy(*state_member(&hs, i), *state_member(&h->st, i), (size_t)n[i], cudaMemcpyDeviceToHost));
+            CUDA_TRY(cudaMemcpyAsync(*state_member(&hs, i), *state_member(&h->st, i), (size_t)n[i], cudaMemcpyDeviceToHost,
+                                     h->hstream));
+    CUDA_TRY(cudaStreamSynchronize(h->hstream));
     return MAPF_OK;
 }
 
@@ -745,9 +813,15 @@ int mapf_set_state_host(mapf_handle *h, const mapf_state *host) {
     state_sizes(h, n);
     mapf_state hs = *host;
     CUDA_TRY(cudaDeviceSynchronize());
+    // Pageable sources: a blocking cudaMemcpy may return once the data is staged, before the DMA has landed, and the
+    // next *_host call launches on a non-blocking stream that the legacy stream does not order.  Copy on the stream
+    // those calls use and wait for it: when this returns the state IS on the device.
+    if (!h->hstream) CUDA_TRY(cudaStreamCreateWithFlags(&h->hstream, cudaStreamNonBlocking));
     for (int i = 0; i < 10; ++i)
         if (*state_member(&hs, i))
-            CUDA_TRY(cudaMemcpy(*state_member(&h->st, i), *state_member(&hs, i), (size_t)n[i], cudaMemcpyHostToDevice));
+            CUDA_TRY(cudaMemcpyAsync(*state_member(&h->st, i), *state_member(&hs, i), (size_t)n[i], cudaMemcpyHostToDevice,
+                                     h->hstream));
+    CUDA_TRY(cudaStreamSynchronize(h->hstream));
     return MAPF_OK;
 }
 
@@ -787,6 +861,8 @@ int mapf_observe_host(mapf_handle *h, const mapf_outputs *out_host) {
     if (!out_host) return fail(MAPF_ERR_INVALID_ARG, "null outputs");
     DeviceGuard guard(h->cfg.device);
     rc = ensure_io(h);
+    if (rc) return rc;
+    rc = order_after_user_work(h);
     if (rc) return rc;
     mapf_outputs want;
     memset(&want, 0, sizeof(want));
@@ -831,6 +907,8 @@ int mapf_reset_host(mapf_handle *h, const uint8_t *reset_mask, const int16_t *st
     DeviceGuard guard(h->cfg.device);
     rc = ensure_io(h);
     if (rc) return rc;
+    rc = order_after_user_work(h);
+    if (rc) return rc;
     const size_t B = h->cfg.num_envs, BN = B * h->cfg.num_agents;
     if (reset_mask) CUDA_TRY(cudaMemcpyAsync(h->io_reset_mask, reset_mask, B, cudaMemcpyHostToDevice, h->hstream));
     if (starts_override) {
@@ -856,6 +934,8 @@ int mapf_step_host(mapf_handle *h, const int8_t *actions, const int16_t *goal_ov
     if (rc) return rc;
     DeviceGuard guard(h->cfg.device);
     rc = ensure_io(h);
+    if (rc) return rc;
+    rc = order_after_user_work(h);
     if (rc) return rc;
     const int64_t B = h->cfg.num_envs, N = h->cfg.num_agents;
     mapf_outputs dev;
@@ -892,28 +972,15 @@ int mapf_step_host(mapf_handle *h, const int8_t *actions, const int16_t *goal_ov
         nslices = 5;
         for (int i = 0; i < 5; ++i) weights[i] = taper[i];
     }
-    if (const char *ov = getenv("MAPF_HOST_SLICES")) {
-        const int v = atoi(ov);
-        if (v >= 1) {
-            nslices = v > kMaxHostSlices ? kMaxHostSlices : v;
-            for (int i = 0; i < kMaxHostSlices; ++i) weights[i] = 1;
-        }
+    if (h->knob_host_slices >= 1) {
+        nslices = h->knob_host_slices;
+        for (int i = 0; i < kMaxHostSlices; ++i) weights[i] = 1;
     }
-    if (const char *ov = getenv("MAPF_HOST_PLAN")) {
-        int k = 0;
-        for (const char *q = ov; *q && k < kMaxHostSlices;) {
-            const int v = atoi(q);
-            if (v >= 1) weights[k++] = v;
-            while (*q && *q != ',') ++q;
-            if (*q == ',') ++q;
-        }
-        if (k >= 1) nslices = k;
+    if (h->knob_plan_n >= 1) {
+        nslices = h->knob_plan_n;
+        for (int i = 0; i < nslices; ++i) weights[i] = h->knob_plan[i];
     }
-    int raw32 = 0;
-    if (const char *ov = getenv("MAPF_HOST_RAW_32NDS")) {
-        const int v = atoi(ov);
-        if (packed && v >= 0 && v <= 16) raw32 = v;
-    }
+    const int raw32 = packed ? h->knob_raw32 : 0;
     struct HostSlice { int64_t e0, n; bool packed; };
     HostSlice plan[kMaxHostSlices + 1];
     int S = 0;
@@ -941,7 +1008,7 @@ int mapf_step_host(mapf_handle *h, const int8_t *actions, const int16_t *goal_ov
     const float inv1 = h->cfg.normalize_goal_delta ? (float)(h->cfg.cols - 1 > 1 ? h->cfg.cols - 1 : 1) : 1.f;
     int64_t h2d = 0, d2h = 0;
     const uint32_t ticket = ++h->ticket_seq;
-    const bool trace = packed && getenv("MAPF_HOST_TRACE") != nullptr;
+    const bool trace = packed && h->knob_trace;
     const int64_t t_begin = std::chrono::steady_clock::now().time_since_epoch().count();
     // closes the step for the host threads on every exit path (an early error return must not leave them polling)
     struct PoolStep {
@@ -1062,6 +1129,13 @@ int mapf_step_host(mapf_handle *h, const int8_t *actions, const int16_t *goal_ov
     return MAPF_OK;
 }
 
+int mapf_host_wait_stream(mapf_handle *h, void *stream) {
+    if (!h) return fail(MAPF_ERR_INVALID_ARG, "null handle");
+    h->last_user_stream = static_cast<cudaStream_t>(stream);
+    h->user_dirty = true;
+    return MAPF_OK;
+}
+
 int mapf_host_transfer_bytes(const mapf_handle *h, int64_t *h2d_bytes, int64_t *d2h_bytes) {
     if (!h) return fail(MAPF_ERR_INVALID_ARG, "null handle");
     if (h2d_bytes) *h2d_bytes = h->last_h2d_bytes;
@@ -1112,6 +1186,7 @@ int mapf_pack_flat_obs(mapf_handle *h, const mapf_outputs *ch, int32_t include_g
     const long long total = BN * D;
     const int threads = 256;
     const unsigned grid = (unsigned)((total + threads - 1) / threads);
+    note_user_stream(h, static_cast<cudaStream_t>(stream));
     mapf::mapf_pack_flat_kernel<<<grid, threads, 0, static_cast<cudaStream_t>(stream)>>>(
         ch->local_obs, reinterpret_cast<const float2 *>(ch->goal_delta), ch->blocking_prev, ch->action_mask, flat,
         BN, h->V2, include_goal_distance ? 1 : 0, include_blocking_pressure ? 1 : 0, include_action_mask ? 1 : 0, D);
@@ -1126,6 +1201,7 @@ static int sample_actions(mapf_handle *h, const int8_t *mask, int8_t *actions, u
     const long long BN = (long long)h->cfg.num_envs * h->cfg.num_agents;
     const int threads = 256;
     const unsigned grid = (unsigned)((BN + threads - 1) / threads);
+    note_user_stream(h, static_cast<cudaStream_t>(stream));
     mapf::mapf_sample_actions_kernel<<<grid, threads, 0, static_cast<cudaStream_t>(stream)>>>(
         mask, actions, BN, h->cfg.num_agents, h->cfg.seed, h->cfg.env_id_base, counter);
     CUDA_TRY(cudaGetLastError());

@@ -329,7 +329,8 @@ __device__ __forceinline__ void scan_candidates(const uint32_t *s_new, const uin
         const uint32_t ps = (a <= gl) ? an : s_snap[a];  // snapshot position of agent a as seen by me (F3)
         uint32_t d = ps - origin;
         uint32_t t1 = d & 1023u, t2 = d >> 10;
-        if (t1 < (uint32_t)V && t2 < (uint32_t)V) o.occ |= (WB)1 << (t2 * V + t1);
+        // a lower-index agent on MY cell (injected states only, ENV:658-666) does not own it (ENV:200-205): skip it
+        if (t1 < (uint32_t)V && t2 < (uint32_t)V && !(a < gl && ps == my_new_lin)) o.occ |= (WB)1 << (t2 * V + t1);
         d = an - nb_origin;
         t1 = d & 1023u; t2 = d >> 10;
         if (t1 <= nb_side && t2 <= nb_side) {

@@ -53,6 +53,40 @@ def allreduce_metrics(vec: torch.Tensor, world_size: int | None = None, group=No
     return summarize(v)
 
 
+class AsyncMetrics:
+    """A metric all-reduce in flight on a side stream: the step stream never waits for it.
+
+    ``start`` snapshots the shard's metric vector (the snapshot kernel is ordered on the CURRENT stream, behind the
+    steps already queued), hands the collective to ``stream`` and returns at once; later step launches on the
+    current stream overlap with the collective.  ``result()`` blocks the HOST on the collective's event and returns
+    sums + means (``summarize``).  This is the reporting path BASELINE config 4 names: "NCCL metric all-reduce,
+    kept off the step path"."""
+
+    def __init__(self, vec: torch.Tensor, world_size: int | None = None, group=None, stream=None):
+        import torch.distributed as dist
+
+        if world_size is None:
+            world_size = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.local = vec.detach().clone()          # on the current stream: behind the steps queued so far
+        self.total = self.local.clone()
+        self._event = None
+        if world_size > 1:
+            if stream is not None and self.total.is_cuda:
+                stream.wait_stream(torch.cuda.current_stream(self.total.device))
+                with torch.cuda.stream(stream):
+                    dist.all_reduce(self.total, op=dist.ReduceOp.SUM, group=group)
+                    self._event = torch.cuda.Event()
+                    self._event.record(stream)
+                self.total.record_stream(stream)
+            else:
+                dist.all_reduce(self.total, op=dist.ReduceOp.SUM, group=group)
+
+    def result(self) -> dict:
+        if self._event is not None:
+            self._event.synchronize()
+        return summarize(self.total)
+
+
 def shard_range(num_envs_total: int, rank: int, world_size: int) -> tuple[int, int]:
     """Contiguous block of global env ids owned by ``rank`` (first ranks get the remainder)."""
     base, rem = divmod(int(num_envs_total), int(world_size))

@@ -123,6 +123,12 @@ class ReferenceModel(MultiAgentEnv):
         dev = cfg.get("device", "cuda:0")
         dev_index = int(str(dev).split(":")[1]) if ":" in str(dev) else 0
         ccfg = nat.make_config(cfg, R, Cc, 1, dev_index, int(cfg.get("env_id_base", 0)), False)
+        if ccfg.step_kernel == 0 and Cc <= 32 and R <= 64:
+            # B = 1: launch-latency bound either way.  The env-per-thread kernel keeps the reference's owner-grid
+            # semantics even for injected states with several agents on one cell (its occupancy board IS
+            # "_occupancy_owner != -1", and agent_flags carries who owns a shared cell), so the wrapper -- the
+            # place where tests inject such states -- takes it whenever the map fits (all eight reference maps do).
+            ccfg.step_kernel = 2
         # Layouts reach the kernels as `starts`/`goals` overrides (deterministic table, numpy draw), so
         # the handle runs its restore-starts reset path; only the Philox backend draws in-kernel.
         in_kernel_draw = (not self.deterministic) and self._rng_backend == "philox"
@@ -265,6 +271,12 @@ class ReferenceModel(MultiAgentEnv):
         af = (self._reached_arr.astype(np.uint8) * nat.AF_REACHED
               | self._completed_once_arr.astype(np.uint8) * nat.AF_COMPLETED_ONCE
               | (self._blocking_pressure_prev_arr != 0).astype(np.uint8) * nat.AF_BLOCKING_PREV)
+        # the occupancy-owner grid is an input like the other mirrors (the reference's tests rebuild it after
+        # writing positions, tests/test_reference_model_multi_agent_invariants.py:28-38): an agent that does not own
+        # the cell it stands on (only possible when several were injected onto one cell) is flagged for the kernel
+        p = self._positions_arr
+        own = self._occupancy_owner[p[:, 0].astype(np.intp), p[:, 1].astype(np.intp)]
+        af = af | ((own != np.arange(self._num_agents)).astype(np.uint8) * nat.AF_NOT_OWNER)
         self._hs["agent_flags"][0] = af
         w = self._hs["env_words"][0]
         w[nat.W_STEP_COUNT] = int(self.step_count)
@@ -295,7 +307,11 @@ class ReferenceModel(MultiAgentEnv):
         for a, i in self._agent_index.items():
             self.goal_reached_once[a] = bool(self._completed_once_arr[i])
         self._rebuild_goal_owner()
-        self._rebuild_occupancy_owner()
+        self._occupancy_owner.fill(self.UNASSIGNED_OWNER)   # ENV:102: the grid outlives the step, non-owners included
+        p = self._positions_arr
+        for idx in range(self._num_agents):
+            if not (af[idx] & nat.AF_NOT_OWNER):
+                self._occupancy_owner[p[idx, 0], p[idx, 1]] = idx
 
     _MIRRORED = ("positions", "goals", "starts", "agent_flags", "env_words")
 

@@ -97,6 +97,11 @@ enum {
 #define MAPF_AF_REACHED 1u        /* ENV:86 _reached_arr (sticky) */
 #define MAPF_AF_COMPLETED_ONCE 2u /* ENV:87 _completed_once_arr */
 #define MAPF_AF_BLOCKING_PREV 4u  /* ENV:89 _blocking_pressure_prev_arr (as 0/1) */
+/* ENV:102 _occupancy_owner, the part positions do not determine: the agent stands on a cell it does not own.
+ * Never set by a legal step (ENV:516-521 keeps agents apart); only after several agents were injected onto one
+ * cell (the states ENV:658-666 penalises): the highest index owns the cell (ENV:200-205), a leaving agent clears
+ * the owner for everybody (ENV:523).  Honoured and maintained by the env-per-thread step kernel. */
+#define MAPF_AF_NOT_OWNER 8u
 
 /* Device-resident state, caller-owned (torch tensors).  Layout mirrors ENV:82-120. */
 typedef struct mapf_state {
@@ -245,6 +250,17 @@ int mapf_step(mapf_handle *h, const int8_t *actions, const int16_t *goal_overrid
  * which returns after the results are in the host buffers. */
 int mapf_reset_host(mapf_handle *h, const uint8_t *reset_mask, const int16_t *starts_override,
                     const int16_t *goals_override, const mapf_outputs *out_host);
+/* STREAM ORDER of the *_host entry points.  They run on two private non-blocking streams of the handle and are
+ * synchronous: when they return, their results are in the host buffers and the device state is final, so anything
+ * queued AFTER them (on any stream) is ordered.  For work queued BEFORE them the rule is: everything enqueued
+ * through this handle's stream-taking entry points (mapf_reset / mapf_step / mapf_observe / samplers / flat pack)
+ * is waited for automatically -- the handle remembers the last such stream and makes its private streams wait on
+ * an event recorded there.  Work the library cannot see (a caller's own kernels or copies into the bound state
+ * tensors, e.g. torch ops) must be announced with mapf_host_wait_stream(h, stream) before the next *_host call;
+ * BatchedMapfEnv.step_host / reset_host do that with torch's current stream.  mapf_set_state_host /
+ * mapf_get_state_host synchronise the whole device before and their own copies after: on return the state is on
+ * the device (resp. in the host arrays) even when the host arrays are pageable. */
+int mapf_host_wait_stream(mapf_handle *h, void *stream);
 int mapf_step_host(mapf_handle *h, const int8_t *actions, const int16_t *goal_override,
                    const int32_t *goal_rank, const mapf_outputs *out_host, int32_t auto_reset);
 

@@ -30,6 +30,11 @@ struct oracle_env {
     double ep_dl_events, ep_ll_events, ep_dl_steps, ep_ll_steps; /* ENV:64-67 */
     int dl_prev, ll_prev;                /* ENV:68-69 */
     uint64_t rng;
+    /* device-RNG replay (oracle_set_philox): the draws of the CUDA kernels, restated */
+    int ph_on;
+    uint64_t ph_seed;
+    int64_t ph_stream;
+    uint32_t ph_counter;
     /* scratch, ENV:90-101 */
     int16_t *prev_pos, *intended;
     uint8_t *reached_goal, *moved, *failed, *gprog, *prev_on_goal, *cur_on_goal;
@@ -54,6 +59,52 @@ static uint32_t rng_below(uint64_t *s, uint32_t n) { /* unbiased, rejection */
     for (;;) {
         uint32_t x = (uint32_t)(splitmix64(s) >> 32);
         if (lim == 0 || x < lim) return x % n;
+    }
+}
+
+/* ---------------------------------------------------------------- device-RNG replay
+ * The reference draws with numpy PCG64 (ENV:76-78,277,300); the CUDA kernels draw with
+ * Philox4x32-10 keyed by (seed, global env id).  North-star accepts a different stream, so this
+ * part has no reference counterpart: it restates the KERNELS' documented draw discipline
+ * (include/mapf_b200.h "RNG") so that the benchmarked mode -- Philox goal draws, in-launch
+ * auto-reset, fused masked sampler -- can be compared bit for bit over whole episodes. */
+static void philox4x32_10(uint32_t k0, uint32_t k1, uint32_t c[4]) {
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c[0], p1 = (uint64_t)0xCD9E8D57u * c[2];
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0, n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1, n3 = (uint32_t)p0;
+        c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+}
+void oracle_philox_raw(uint32_t k0, uint32_t k1, uint32_t ctr[4]) { philox4x32_10(k0, k1, ctr); }
+/* key = seed ^ golden * (stream + 1), stream = global env id */
+static void philox_env(uint64_t seed, int64_t stream, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                       uint32_t out[4]) {
+    uint64_t k = seed ^ (0x9E3779B97F4A7C15ull * (uint64_t)(stream + 1));
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+    philox4x32_10((uint32_t)k, (uint32_t)(k >> 32), out);
+}
+static uint32_t mulhi32(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+
+void oracle_set_philox(oracle_env *e, int on, uint64_t seed, int64_t env_global, uint32_t counter) {
+    e->ph_on = on; e->ph_seed = seed; e->ph_stream = env_global; e->ph_counter = counter;
+}
+uint32_t oracle_get_philox_counter(const oracle_env *e) { return e->ph_counter; }
+
+/* the benchmark's samplers (scripts/benchmark_multi_agent_env.py:38-57) with the kernels' draws: one
+ * Philox block per agent quad, word a & 3; masked = uniform over the set bits of the 5-entry mask */
+void oracle_sample_actions_philox(const oracle_env *e, uint64_t call_counter, int masked,
+                                  const int8_t *mask /* [N,5] */, int8_t *actions /* [N] */) {
+    for (int a = 0; a < e->N; ++a) {
+        uint32_t x4[4];
+        philox_env(e->ph_seed ^ 0xA511E9B3ull, e->ph_stream, (uint32_t)call_counter,
+                   (uint32_t)(call_counter >> 32), (uint32_t)(a >> 2), 0x41435421u, x4);
+        uint32_t x = x4[a & 3];
+        if (!masked) { actions[a] = (int8_t)mulhi32(x, 5u); continue; }
+        int valid[5], nv = 0;
+        for (int k = 0; k < 5; ++k) if (mask[5 * a + k]) valid[nv++] = k;
+        actions[a] = nv ? (int8_t)valid[mulhi32(x, (uint32_t)nv)] : 0;
     }
 }
 
@@ -266,6 +317,40 @@ static void emit_agent_obs(oracle_env *e, int idx, oracle_outputs *out) {
 static int draw_layout(oracle_env *e) { /* ENV:267-282 with the oracle's own RNG */
     int need = 2 * e->N;
     if (e->F < need) return ORACLE_ERR_TOO_FEW_CELLS;
+    if (e->ph_on) {
+        /* Symmetric rejection, the kernels' rule: every slot (starts 0..N-1, then goals) draws a uniform free
+         * cell; a slot that equals a lower-numbered slot redraws in the next round.  Round t of this env uses
+         * Philox counter (ph_counter + t, agent, "RESE", 0): word 0 -> start, word 1 -> goal. */
+        int N = e->N;
+        int *cs = e->perm, *cg = e->perm + N;
+        uint32_t rs = N >= 32 ? 0xFFFFFFFFu : ((1u << N) - 1u), rg = rs, rounds = 0;
+        while (rs | rg) {
+            for (int a = 0; a < N; ++a) {
+                if (!(((rs | rg) >> a) & 1u)) continue;
+                uint32_t x[4];
+                philox_env(e->ph_seed, e->ph_stream, e->ph_counter + rounds, (uint32_t)a, 0x52455345u, 0, x);
+                if ((rs >> a) & 1u) cs[a] = (int)mulhi32(x[0], (uint32_t)e->F);
+                if ((rg >> a) & 1u) cg[a] = (int)mulhi32(x[1], (uint32_t)e->F);
+            }
+            rs = 0; rg = 0;
+            for (int g = 0; g < N; ++g)
+                for (int a = 0; a < N; ++a) {
+                    if (a < g && cs[a] == cs[g]) rs |= 1u << g;
+                    if (cs[a] == cg[g]) rg |= 1u << g;
+                    if (a < g && cg[a] == cg[g]) rg |= 1u << g;
+                }
+            rounds++;
+        }
+        e->ph_counter += rounds;
+        for (int a = 0; a < N; ++a) {
+            e->starts[2 * a] = e->free_pos[2 * cs[a]]; e->starts[2 * a + 1] = e->free_pos[2 * cs[a] + 1];
+            e->goals[2 * a] = e->free_pos[2 * cg[a]];  e->goals[2 * a + 1] = e->free_pos[2 * cg[a] + 1];
+        }
+        memcpy(e->positions, e->starts, sizeof(int16_t) * 2 * N);
+        rebuild_goal_owner(e);
+        rebuild_occupancy_owner(e);
+        return ORACLE_OK;
+    }
     for (int i = 0; i < e->F; ++i) e->perm[i] = i;
     for (int i = 0; i < need; ++i) { /* partial Fisher-Yates: uniform without replacement */
         int j = i + (int)rng_below(&e->rng, (uint32_t)(e->F - i));
@@ -331,7 +416,14 @@ static int assign_new_goal(oracle_env *e, int idx, int rank, const int16_t *over
         if (!in_grid(e, r, c)) return ORACLE_ERR_BAD_ARG;
     } else {
         if (n == 0) return ORACLE_ERR_NO_GOAL_CELL; /* ENV:296-298 */
-        int k = rank >= 0 ? rank : (int)rng_below(&e->rng, (uint32_t)n); /* ENV:300 */
+        int k;
+        if (rank >= 0) k = rank;
+        else if (e->ph_on) { /* the kernels' draw: counter (ph_counter, agent, "GOAL", 0), word 0 scaled to [0, n) */
+            uint32_t x[4];
+            philox_env(e->ph_seed, e->ph_stream, e->ph_counter, (uint32_t)idx, 0x474F414Cu, 0, x);
+            k = (int)mulhi32(x[0], (uint32_t)n);
+            e->ph_counter++;
+        } else k = (int)rng_below(&e->rng, (uint32_t)n); /* ENV:300 */
         if (k >= n) return ORACLE_ERR_BAD_ARG;
         e->last_rank[idx] = k;
         r = e->free_pos[2 * e->perm[k]];
@@ -676,6 +768,15 @@ void oracle_get_state_many(oracle_env **envs, int num_envs, int16_t *positions, 
                          blocking_prev ? blocking_prev + (size_t)b * N : NULL,
                          step_count ? step_count + b : NULL,
                          episode_counters ? episode_counters + (size_t)b * 6 : NULL);
+    }
+}
+
+void oracle_sample_actions_philox_many(oracle_env **envs, int num_envs, uint64_t call_counter, int masked,
+                                       const int8_t *mask, int8_t *actions) {
+    for (int b = 0; b < num_envs; ++b) {
+        int N = envs[b]->N;
+        oracle_sample_actions_philox(envs[b], call_counter, masked, mask ? mask + (size_t)b * N * 5 : NULL,
+                                     actions + (size_t)b * N);
     }
 }
 

@@ -129,6 +129,19 @@ void oracle_get_last_candidate_counts(const oracle_env *env, int32_t *out);
  * agent, -1 where none happened; lets a recorded oracle run be replayed through goal_rank. [N] */
 void oracle_get_last_ranks(const oracle_env *env, int32_t *out);
 
+/* Device-RNG replay (no reference counterpart: the reference draws with numpy PCG64, the kernels with
+ * Philox4x32-10 keyed by (seed, global env id); see include/mapf_b200.h).  With `on` != 0 every later
+ * layout draw (oracle_reset mode 2) and lifelong goal draw (oracle_step without rank/override) follows
+ * the kernels' documented draw discipline, starting at the env's RNG counter `counter`. */
+void oracle_set_philox(oracle_env *env, int on, uint64_t seed, int64_t env_global, uint32_t counter);
+uint32_t oracle_get_philox_counter(const oracle_env *env);
+void oracle_sample_actions_philox(const oracle_env *env, uint64_t call_counter, int masked,
+                                  const int8_t *mask /* [N,5] */, int8_t *actions /* [N] */);
+void oracle_sample_actions_philox_many(oracle_env **envs, int num_envs, uint64_t call_counter, int masked,
+                                       const int8_t *mask /* [B,N,5] */, int8_t *actions /* [B,N] */);
+/* one Philox4x32-10 block (known-answer tests) */
+void oracle_philox_raw(uint32_t k0, uint32_t k1, uint32_t ctr[4]);
+
 /* Batched variants for parity tests at B > 1: env b uses slice b of every [B, ...] array. */
 int oracle_reset_many(oracle_env **envs, int num_envs, int mode, const int16_t *starts,
                       const int16_t *goals, const uint8_t *mask, oracle_outputs *out);

@@ -114,6 +114,12 @@ def lib():
         L.oracle_step_many.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.POINTER(_Outputs), C.c_void_p]
         L.oracle_get_state_many.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 8
+        L.oracle_set_philox.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_int64, C.c_uint32]
+        L.oracle_get_philox_counter.restype = C.c_uint32
+        L.oracle_get_philox_counter.argtypes = [C.c_void_p]
+        L.oracle_sample_actions_philox.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]
+        L.oracle_sample_actions_philox_many.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]
+        L.oracle_philox_raw.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p]
         L.oracle_bench_run.restype = C.c_int64
         L.oracle_bench_run.argtypes = [
             C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int,
@@ -324,6 +330,25 @@ class OracleBatch:
                                                 C.byref(self._out), _ptr(self.ranks)))
         return self.buf
 
+    # -- device-RNG replay (Philox draws of the CUDA kernels; no reference counterpart)
+    def set_philox(self, seed: int, env_id_base: int = 0, counters=None):
+        """Env b draws its layouts / lifelong goals like the kernels do for global env id ``env_id_base + b``."""
+        for b, e in enumerate(self.envs):
+            lib().oracle_set_philox(e.handle, 1, C.c_uint64(seed), C.c_int64(env_id_base + b),
+                                    C.c_uint32(0 if counters is None else int(counters[b])))
+        self._ph_base = env_id_base
+
+    def philox_counters(self) -> np.ndarray:
+        return np.array([lib().oracle_get_philox_counter(e.handle) for e in self.envs], np.uint32)
+
+    def sample_actions(self, call_counter: int, masked: bool = True) -> np.ndarray:
+        """The benchmark samplers with the kernels' draws, from the current ``buf['action_mask']``."""
+        out = np.zeros((self.B, self.N), np.int8)
+        mask = np.ascontiguousarray(self.buf["action_mask"])
+        lib().oracle_sample_actions_philox_many(self._arr, self.B, C.c_uint64(call_counter), int(masked),
+                                                _ptr(mask), _ptr(out))
+        return out
+
     def state(self) -> dict:
         B, N = self.B, self.N
         st = {
@@ -336,6 +361,13 @@ class OracleBatch:
             "positions", "starts", "goals", "reached", "completed_once", "blocking_prev",
             "step_count", "episode_counters")])
         return st
+
+
+def philox_raw(k0: int, k1: int, ctr) -> np.ndarray:
+    """One Philox4x32-10 block (known-answer tests of the replay RNG)."""
+    c = np.array(ctr, np.uint32)
+    lib().oracle_philox_raw(C.c_uint32(k0), C.c_uint32(k1), _ptr(c))
+    return c
 
 
 def flat_obs_batch(buf: dict, include_goal_distance=False, include_blocking_pressure=True,

@@ -148,14 +148,6 @@ def test_sliced_host_step_equals_device_step(monkeypatch):
             assert torch.equal(a.state[k], b.state[k]), f"slices={slices}: state {k}"
 
 
-@pytest.mark.parametrize("n", [8, 16])
-def test_several_lanes_per_env_variant(monkeypatch, n):
-    """MAPF_ENV_LPE=0: the env-per-thread kernel with one lane per agent quad (private occupancy boards, replayed
-    moves, goal reassignment served after the walk) -- off by default, still the same function."""
-    monkeypatch.setenv("MAPF_ENV_LPE", "0")
-    run_pair(c3(num_agents=n, steps_per_episode=30), 1500, 70)
-    run_pair({"env_name": "ReferenceModel-3-1", "num_agents": n, "sensor_range": 1, "steps_per_episode": 50, "seed": 9},
-             300, 120, masked=False)
 
 
 def test_tall_map_null_actions_and_invalid_actions():
