@@ -211,6 +211,32 @@ class BatchedMapfEnv:
                               o["terminated"], o["truncated"], o["step_flags"], o["agent_step_flags"], o["info"])
         return self._output()
 
+    def step_many(self, steps: int, actions=None, auto_reset: bool = True, out: dict | None = None) -> dict:
+        """``steps`` env steps with the fused sampler's actions (:meth:`fuse_sampler` first), in one kernel launch for
+        small batches (``mapf_step_many``).  ``out``: optional dict of [steps, B, ...] device tensors keyed like
+        ``self.out`` -- every step's outputs are kept (a rollout); without it only the last step's are, in the env's
+        own buffers.  Returns the dict written to."""
+        if not getattr(self, "_fused", 0):
+            raise RuntimeError("step_many draws the actions of steps 2..K inside the launch: call fuse_sampler() first")
+        a = self._actions if actions is None else self._dev_tensor(actions, torch.int8, (self.B, self.N))
+        if out is None:
+            cout, stride, ret = self._cout, 0, self.out
+        else:
+            for k in nat.OUTPUT_FIELDS:
+                t = out[k]
+                want = (int(steps),) + tuple(self.out[k].shape)
+                if tuple(t.shape) != want or t.dtype != self.out[k].dtype or not t.is_contiguous() or t.device != self.device:
+                    raise ValueError(f"out[{k!r}] must be a contiguous {self.out[k].dtype} tensor of shape {want} on {self.device}")
+            cout, stride, ret = nat.MapfOutputs(**{k: out[k].data_ptr() for k in nat.OUTPUT_FIELDS}), self.B, out
+        nat.check(self._lib.mapf_step_many(self._h, self._ptr(a), C.byref(cout), int(steps), stride, int(bool(auto_reset)),
+                                           self._stream()))
+        self._sample_counter += int(steps)
+        return ret
+
+    def rollout_buffers(self, steps: int) -> dict:
+        """[steps, B, ...] device tensors for :meth:`step_many`."""
+        return {k: torch.zeros((int(steps),) + tuple(v.shape), dtype=v.dtype, device=self.device) for k, v in self.out.items()}
+
     # ------------------------------------------------------------------ host-buffer transition
     HOST_CHANNELS = ("local_obs", "action_mask", "goal_delta", "blocking_prev", "reward", "terminated", "truncated")
 

@@ -183,6 +183,12 @@ struct mapf_handle {
     int knob_raw32;             // MAPF_HOST_RAW_32NDS
     bool knob_trace;            // MAPF_HOST_TRACE
     int local_world;            // LOCAL_WORLD_SIZE (ranks sharing this node's cores), >= 1
+    int local_rank;             // LOCAL_RANK, 0 when unset
+    int knob_host_pin;          // MAPF_HOST_PIN: -1 unset (pin when the node is shared), 0 off, 1 on
+    // packed-or-plain, decided by measurement: calls 0-2 go packed, 3-5 plain (the first of each untimed), then the
+    // faster one stays -- on THIS host, with whatever else (the other ranks of the node) is running beside it
+    int auto_calls, auto_choice;          // auto_choice: -1 undecided, 0 plain, 1 packed
+    int64_t auto_ns[2];                   // summed call time of the timed calls: [plain, packed]
     // ordering of the *_host entry points (private streams) against work the caller queued on ITS stream
     cudaEvent_t ev_user;
     cudaStream_t last_user_stream;
@@ -300,6 +306,8 @@ void fill_params(const mapf_handle *h, mapf::KParams &p) {
     p.env_metrics = h->st.env_metrics;
     p.err_bits = h->d_err;
     p.L = h->layout;
+    p.inner_steps = 1;
+    p.out_step_stride = 0;
 }
 
 void fill_outputs(mapf::KParams &p, const mapf_outputs *o) {
@@ -449,6 +457,24 @@ void read_knobs(mapf_handle *h) {
     if (const char *ov = getenv("MAPF_HOST_RAW_32NDS")) { const int v = atoi(ov); if (v >= 0 && v <= 16) h->knob_raw32 = v; }
     // one process per GPU: the ranks of a node share its cores (torchrun exports LOCAL_WORLD_SIZE)
     if (const char *lw = getenv("LOCAL_WORLD_SIZE")) { const int w = atoi(lw); if (w > 1) h->local_world = w; }
+    h->local_rank = 0;
+    if (const char *lr = getenv("LOCAL_RANK")) { const int r = atoi(lr); if (r >= 0 && r < h->local_world) h->local_rank = r; }
+    h->knob_host_pin = -1;
+    if (const char *ov = getenv("MAPF_HOST_PIN")) h->knob_host_pin = atoi(ov) != 0 ? 1 : 0;
+    h->auto_calls = 0; h->auto_choice = -1; h->auto_ns[0] = h->auto_ns[1] = 0;
+}
+
+// This rank's share of the cores the process may run on: a contiguous chunk of the affinity mask per local rank.
+int rank_cores(const mapf_handle *h, int *cpus, int cap) {
+    cpu_set_t set;
+    if (sched_getaffinity(0, sizeof(set), &set) != 0) return 0;
+    int all[CPU_SETSIZE], n = 0;
+    for (int c = 0; c < CPU_SETSIZE; ++c) if (CPU_ISSET(c, &set)) all[n++] = c;
+    const int per = n / h->local_world;
+    if (per < 1) return 0;
+    int k = 0;
+    for (int i = h->local_rank * per; i < (h->local_rank + 1) * per && k < cap; ++i) cpus[k++] = all[i];
+    return k;
 }
 
 int host_threads_default(const mapf_handle *h) {
@@ -485,11 +511,10 @@ void note_user_stream(mapf_handle *h, cudaStream_t s) {
 // DRAM are shared by many ranks plain copies win (measured on an 8-GPU / 32-core host: plain 2.24e9, packed
 // 1.76e9 agent-steps/s aggregate; on 1 GPU / 16 cores: plain 1.13e9, packed 2.36e9; 2 GPUs / 24 cores: packed
 // 2.72e9).  MAPF_HOST_PACK=0 / 1 forces it off / on.
-bool host_pack_applies(const mapf_handle *h, const mapf_outputs *host) {
+bool host_pack_eligible(const mapf_handle *h, const mapf_outputs *host) {
     if (!host || !host->local_obs || !host->action_mask || !host->goal_delta || !host->reward) return false;
     if (h->cfg.rows > 128 || h->cfg.cols > 128 || h->cfg.num_envs < 8192) return false;
-    if (h->knob_host_pack >= 0) return h->knob_host_pack != 0;
-    return host_threads_default(h) >= 12;
+    return true;
 }
 
 int ensure_pack(mapf_handle *h) {
@@ -506,7 +531,17 @@ int ensure_pack(mapf_handle *h) {
         h->gdt_row[d + 128] = h->cfg.normalize_goal_delta ? (float)d / den0 : (float)d;  // d / 1 == d
         h->gdt_col[d + 128] = h->cfg.normalize_goal_delta ? (float)d / den1 : (float)d;
     }
-    h->pool = mapf::host_pool_create(host_threads_default(h));
+    {
+        // On a node shared by several ranks every rank keeps to its own cores: the workers are pinned one per core to
+        // this rank's chunk of the affinity mask (its first core is left to the calling thread).  Alone on the node
+        // the scheduler is left to it.  MAPF_HOST_PIN=0 / 1 forces it off / on.
+        int cpus[64];
+        int n = 0;
+        const bool pin = h->knob_host_pin >= 0 ? h->knob_host_pin != 0 : h->local_world > 1;
+        if (pin) n = rank_cores(h, cpus, 64);
+        if (n >= 2) h->pool = mapf::host_pool_create(host_threads_default(h), cpus + 1, n - 1);
+        else h->pool = mapf::host_pool_create(host_threads_default(h));
+    }
     h->pack_alloc = true;
     return MAPF_OK;
 }
@@ -741,7 +776,7 @@ int mapf_set_map(mapf_handle *h, const uint8_t *grid) {
         const mapf::EnvLayout &E = h->env_layout;
         std::vector<unsigned char> img((size_t)E.tables_bytes, 0);
         mapf::build_env_tables(h->SR, R, C, h->wpr, h->fw, rows.data(), freeb.data(), h->cfg.normalize_goal_delta != 0,
-                               (float)(R - 1 > 1 ? R - 1 : 1), (float)(C - 1 > 1 ? C - 1 : 1), img.data(), E.t2_off);
+                               (float)(R - 1 > 1 ? R - 1 : 1), (float)(C - 1 > 1 ? C - 1 : 1), img.data(), E.t2_off, E.pre_off);
         CUDA_TRY(cudaMalloc(&h->d_env_tables, img.size()));
         CUDA_TRY(cudaMemcpy(h->d_env_tables, img.data(), img.size(), cudaMemcpyHostToDevice));
     }
@@ -898,6 +933,51 @@ int mapf_step(mapf_handle *h, const int8_t *actions, const int16_t *goal_overrid
     return launch(h, h->step_fn, p, static_cast<cudaStream_t>(stream));
 }
 
+int mapf_step_many(mapf_handle *h, const int8_t *actions, const mapf_outputs *out, int32_t steps,
+                   int64_t out_step_stride_envs, int32_t auto_reset, void *stream) {
+    int rc = check_ready(h);
+    if (rc) return rc;
+    if (steps < 1) return fail(MAPF_ERR_INVALID_ARG, "steps must be >= 1");
+    if (out_step_stride_envs != 0 && out_step_stride_envs < h->cfg.num_envs)
+        return fail(MAPF_ERR_INVALID_ARG, "out_step_stride_envs must be 0 (overwrite) or >= num_envs");
+    if (steps > 1 && !(h->fused_mode && h->fused_actions))
+        return fail(MAPF_ERR_STATE, "mapf_step_many needs the fused sampler (mapf_set_fused_sampler): the actions of "
+                                    "steps 2..K are drawn inside the launch");
+    DeviceGuard guard(h->cfg.device);
+    mapf::KParams p;
+    fill_params(h, p);
+    fill_outputs(p, out);
+    p.actions = actions;
+    p.auto_reset = auto_reset != 0;
+    if (h->fused_mode && h->fused_actions) {
+        p.o_next_actions = h->fused_actions;
+        p.sample_mode = h->fused_mode;
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (!h->use_env_kernel) {   // lane-per-agent kernel: the K steps run inside one launch
+        p.sample_counter = h->fused_counter;
+        h->fused_counter += (uint64_t)steps;
+        p.inner_steps = steps;
+        p.out_step_stride = out_step_stride_envs;
+        return launch(h, h->step_fn, p, s);
+    }
+    // env-per-thread kernel (GPU-filling batches, where the launch rate is not the bound): K launches, same results
+    const int64_t N = h->cfg.num_agents;
+    for (int t = 0; t < steps; ++t) {
+        mapf::KParams q = p;
+        q.actions = t == 0 ? actions : h->fused_actions;
+        q.sample_counter = h->fused_counter++;
+        const int64_t so = (int64_t)t * out_step_stride_envs;
+        auto adv = [&](auto *&ptr, int64_t elems) { if (ptr) ptr += so * elems; };
+        adv(q.o_local_obs, N * h->V2); adv(q.o_action_mask, N * 5); adv(q.o_goal_delta, N); adv(q.o_blocking_prev, N);
+        adv(q.o_reward, N); adv(q.o_terminated, 1); adv(q.o_truncated, 1); adv(q.o_step_flags, 1);
+        adv(q.o_agent_step_flags, N); adv(q.o_info, 4);
+        rc = launch(h, h->step_fn, q, s);
+        if (rc) return rc;
+    }
+    return MAPF_OK;
+}
+
 int mapf_reset_host(mapf_handle *h, const uint8_t *reset_mask, const int16_t *starts_override,
                     const int16_t *goals_override, const mapf_outputs *out_host) {
     int rc = check_ready(h);
@@ -954,7 +1034,18 @@ int mapf_step_host(mapf_handle *h, const int8_t *actions, const int16_t *goal_ov
     // into the caller's arrays while slice c + 1 is in flight (and while this thread is still enqueueing).
     // MAPF_HOST_RAW_32NDS=k sends the last k/32 of the batch as plain copies behind the packed slices (for hosts
     // with too few cores to keep up with PCIe; measured no gain on the 16-core B200 hosts, so 0 by default).
-    const bool packed = host_pack_applies(h, out_host);
+    // packed or plain: forced by MAPF_HOST_PACK, else measured on the first six eligible calls (see mapf_handle)
+    bool packed = false;
+    int auto_phase = -1;   // >= 0: this call is a timed calibration call for mode auto_phase
+    if (host_pack_eligible(h, out_host)) {
+        if (h->knob_host_pack >= 0) packed = h->knob_host_pack != 0;
+        else if (h->auto_choice >= 0) packed = h->auto_choice != 0;
+        else {
+            const int c = h->auto_calls++;
+            packed = c < 3;
+            if (c != 0 && c != 3) auto_phase = packed ? 1 : 0;
+        }
+    }
     if (packed) {
         rc = ensure_pack(h);
         if (rc) return rc;
@@ -1126,6 +1217,10 @@ int mapf_step_host(mapf_handle *h, const int8_t *actions, const int16_t *goal_ov
     }
     h->last_h2d_bytes = h2d;
     h->last_d2h_bytes = d2h;
+    if (auto_phase >= 0) {
+        h->auto_ns[auto_phase] += std::chrono::steady_clock::now().time_since_epoch().count() - t_begin;
+        if (h->auto_calls >= 6) h->auto_choice = h->auto_ns[1] <= h->auto_ns[0] ? 1 : 0;
+    }
     return MAPF_OK;
 }
 
@@ -1133,6 +1228,19 @@ int mapf_host_wait_stream(mapf_handle *h, void *stream) {
     if (!h) return fail(MAPF_ERR_INVALID_ARG, "null handle");
     h->last_user_stream = static_cast<cudaStream_t>(stream);
     h->user_dirty = true;
+    return MAPF_OK;
+}
+
+int mapf_host_memory_probe(const mapf_handle *h, int64_t bytes, int32_t *threads_out, double *fill_gbs, double *copy_gbs) {
+    if (!h) return fail(MAPF_ERR_INVALID_ARG, "null handle");
+    if (bytes < (1 << 20)) return fail(MAPF_ERR_INVALID_ARG, "probe at least 1 MiB");
+    int cpus[64];
+    int n = 0;
+    const bool pin = h->knob_host_pin >= 0 ? h->knob_host_pin != 0 : h->local_world > 1;
+    if (pin) n = rank_cores(h, cpus, 64);
+    const int threads = host_threads_default(h);
+    mapf::host_memory_probe(threads, bytes, n > 0 ? cpus : nullptr, n, fill_gbs, copy_gbs);
+    if (threads_out) *threads_out = threads;
     return MAPF_OK;
 }
 

@@ -52,6 +52,7 @@ __host__ __device__ constexpr int env_stage_stride(int V2) { return ((4 * V2 + 2
 struct EnvLayout {
     int tables_bytes;  // multiple of 16
     int t2_off;        // two-plane window-row table (V <= 5), behind the obstacle-window table
+    int pre_off;       // prefix counts of the free-cell bitmap (reset draws)
     int warp_bytes;    // per-warp block: [stage][occupancy boards][goal boards][agent records]
     int board_rows;    // max(R, C, N) + 2 * ENV_ROW_PAD
     int nq;            // ceil(N / 4)
@@ -62,7 +63,8 @@ __host__ __device__ inline EnvLayout make_env_layout(int N, int R, int C, int SR
     const int V = 2 * SR + 1, V2 = V * V;
     EnvLayout E;
     E.t2_off = (ENV_LUT_OFF + R * 32 * (V > 5 ? 8 : 4) + 15) & ~15;
-    E.tables_bytes = E.t2_off + (V <= 5 ? (4 << (2 * V)) : 0);   // u32[1 << 2V]: two V-bit planes -> V nibbles
+    E.pre_off = E.t2_off + (V <= 5 ? (4 << (2 * V)) : 0);         // u32[1 << 2V]: two V-bit planes -> V nibbles
+    E.tables_bytes = E.pre_off + 65 * 4 + 12;                     // u32[fw + 1]: free cells in front of bitmap word w (fw <= 64)
     E.board_rows = R > C ? R : C;
     if (N > E.board_rows) E.board_rows = N;
     E.board_rows += 2 * ENV_ROW_PAD;
@@ -169,8 +171,16 @@ __device__ __forceinline__ uint4 sample_quad(unsigned long long seed, long long 
 // the lane-per-agent kernel (bit c + PAD of row r + PAD = obstacle or out of bounds, ENV:718).
 inline void build_env_tables(int SR, int R, int C, int wpr, int fw, const uint32_t *rows,
                              const uint32_t *free_bits, int normalize, float den0, float den1, unsigned char *img,
-                             int t2_off) {
+                             int t2_off, int pre_off) {
     const int V = 2 * SR + 1;
+    {
+        uint32_t *pre = reinterpret_cast<uint32_t *>(img + pre_off);
+        uint32_t acc = 0;
+        for (int w = 0; w <= 64; ++w) {
+            pre[w] = acc;
+            if (w < fw) acc += (uint32_t)__builtin_popcount(free_bits[w]);
+        }
+    }
     if (V <= 5) {
         // index = plane0 | plane1 << V with plane0 = obstacle | other-goal, plane1 = other-agent | other-goal
         // (the three sets are disjoint, ENV:730-745): nibble j = 1 obstacle, 2 agent, 4 other's goal
@@ -325,6 +335,15 @@ __global__ void __launch_bounds__(448, 1) mapf_step_env_kernel(const KParams p, 
     const uint32_t esm_s = (uint32_t)__cvta_generic_to_shared(esm);
     const uint32_t t1_s = esm_s + ENV_T1_OFF, kth_s = esm_s + ENV_KTH_OFF, lut_s = esm_s + ENV_LUT_OFF;
     const uint32_t t2_s = esm_s + (uint32_t)E.t2_off;
+    const uint32_t *freepre = reinterpret_cast<const uint32_t *>(esm + E.pre_off);
+    // k-th free cell (cell-linear order, ENV:82) by binary search over the prefix counts
+    auto kth_free = [&](int k) -> int {
+        int lo = 0;
+#pragma unroll
+        for (int stp = 32; stp >= 1; stp >>= 1)
+            if (lo + stp < p.fw && (int)freepre[lo + stp] <= k) lo += stp;
+        return lo * 32 + (int)__fns(freebits[lo], 0, k - (int)freepre[lo] + 1);
+    };
 
     unsigned char *wsm = esm + E.tables_bytes + warp * E.warp_bytes;
     uint32_t *stage_w = reinterpret_cast<uint32_t *>(wsm);                              // [lane][STRIDE] words
@@ -435,12 +454,8 @@ __global__ void __launch_bounds__(448, 1) mapf_step_env_kernel(const KParams p, 
     uint32_t solo_m = 0xFFFFFFFFu;
     // ---------------------------------------------------------------- pre-pass: agent records and owner boards of the state before the step
     for (int r = 0; r < E.board_rows; ++r) { occ[r * 32] = 0u; goalb[r * 32] = 0u; }
-    for (int q = 0; q < NQ; ++q) {
-        const int i0 = 4 * q;
-        const uint4 pq = ldq32<VEC>(p.positions, ab + i0, i0, N, ok, 0u);
-        const uint4 gq = ldq32<VEC>(p.goals, ab + i0, i0, N, ok, 0u);
-        const uint32_t act4 = p.actions ? ldq8<VEC>(reinterpret_cast<const uint8_t *>(p.actions), ab + i0, i0, N, ok) : 0u;
-        const uint32_t fl4 = ldq8<VEC>(p.agent_flags, ab + i0, i0, N, ok);
+    uint32_t dup = 0;
+    auto prepass_quad = [&](int i0, const uint4 &pq, const uint4 &gq, uint32_t act4, uint32_t fl4) {
         reached_m |= gather4(fl4, 0) << i0;      // MAPF_AF_REACHED
         completed_m |= gather4(fl4, 1) << i0;    // MAPF_AF_COMPLETED_ONCE
         bprev_m |= gather4(fl4, 2) << i0;        // MAPF_AF_BLOCKING_PREV
@@ -457,17 +472,32 @@ __global__ void __launch_bounds__(448, 1) mapf_step_env_kernel(const KParams p, 
                 const uint32_t tblocked = ((uint32_t)lut[code] >> nbi) & 1u;
                 rec[(i0 + k) * 32] = code | ((uint32_t)a << 11) | (tblocked << 14) | (gcode << 16);   // goal rides in the (still unused) delta half
                 if (ok) {
+                    // shared-memory atomics instead of read-modify-write chains: the 2N board updates of the pre-pass
+                    // are independent instructions in flight together (the returned word is only looked at afterwards)
                     if (!((fl4 >> (8 * k + 3)) & 1u)) {   // only the owner of a cell marks it (always, in legal states)
-                        uint32_t *orow0 = &occ[(code >> 5) * 32];
-                        const uint32_t ob0 = *orow0, cb0 = 1u << (code & 31u);
-                        degen |= (ob0 & cb0) != 0;   // two agents on one cell: an injected state (ENV:658-666)
-                        *orow0 = ob0 | cb0;
+                        const uint32_t cb0 = 1u << (code & 31u);
+                        dup |= atomicOr(&occ[(code >> 5) * 32], cb0) & cb0;   // two agents on one cell: an injected state (ENV:658-666)
                     } else degen = true;
-                    goalb[(gcode >> 5) * 32] |= 1u << (gcode & 31u);
+                    atomicOr(&goalb[(gcode >> 5) * 32], 1u << (gcode & 31u));
                 }
             }
         }
+    };
+    for (int q = 0; q < NQ; q += 2) {   // two quads per turn: eight state loads in flight before the first is needed
+        const int i0 = 4 * q, i1 = i0 + 4;
+        const bool two = q + 1 < NQ;
+        const uint4 pq0 = ldq32<VEC>(p.positions, ab + i0, i0, N, ok, 0u);
+        const uint4 gq0 = ldq32<VEC>(p.goals, ab + i0, i0, N, ok, 0u);
+        const uint32_t ac0 = p.actions ? ldq8<VEC>(reinterpret_cast<const uint8_t *>(p.actions), ab + i0, i0, N, ok) : 0u;
+        const uint32_t fl0 = ldq8<VEC>(p.agent_flags, ab + i0, i0, N, ok);
+        const uint4 pq1 = ldq32<VEC>(p.positions, ab + i1, i1, N, ok && two, 0u);
+        const uint4 gq1 = ldq32<VEC>(p.goals, ab + i1, i1, N, ok && two, 0u);
+        const uint32_t ac1 = p.actions ? ldq8<VEC>(reinterpret_cast<const uint8_t *>(p.actions), ab + i1, i1, N, ok && two) : 0u;
+        const uint32_t fl1 = ldq8<VEC>(p.agent_flags, ab + i1, i1, N, ok && two);
+        prepass_quad(i0, pq0, gq0, ac0, fl0);
+        if (two) prepass_quad(i1, pq1, gq1, ac1, fl1);
     }
+    degen |= dup != 0;
     if (degen) {   // rare: among agents that claim the same cell the highest index owns it (ENV:200-205)
         const uint32_t claim = solo_m;
         for (int i = 0; i < N; ++i)
@@ -480,19 +510,26 @@ __global__ void __launch_bounds__(448, 1) mapf_step_env_kernel(const KParams p, 
     const unsigned act_w = __ballot_sync(full, ok);
 
     // ---------------------------------------------------------------- the agent walk (ENV:502-563), a quad at a time
+    // lock history of the quad AFTER the one being walked: its loads are issued behind phase A and land during
+    // phase B and the flush (one warp has ~3 others to hide a DRAM round trip behind -- not enough)
+    uint4 gp_n = make_uint4(0, 0, 0, 0), mv_n = gp_n, fm_n = gp_n;
+    uint2 ring_n = make_uint2(0u, 0u);
+    auto load_lock = [&](int i0) {
+        if (!kLock) return;
+        gp_n = ldq32<VEC>(p.lock_gp, ab + i0, i0, N, ok, 0u);
+        mv_n = ldq32<VEC>(p.lock_mv, ab + i0, i0, N, ok, 0u);
+        fm_n = ldq32<VEC>(p.lock_fm, ab + i0, i0, N, ok, 0u);
+        if (use_ring) ring_n = ldq16<VEC>(p.lock_dist, ((size_t)(ok ? env : 0) * p.lw + slot_next) * N + i0, i0, N, ok);
+    };
+    load_lock(0);
+    int4 w0 = make_int4(0, 0, 0, 0), w1 = w0, w2 = w0, w3 = w0;   // the rest of the env words: needed behind the walk
     for (int q = 0; q < NQ; ++q) {
         const int i0 = 4 * q;
         uint32_t rv4[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) rv4[k] = (VEC || i0 + k < N) ? rec[(i0 + k) * 32] : 0u;
-        uint4 gpq = make_uint4(0, 0, 0, 0), mvq = gpq, fmq = gpq;
-        uint2 ringq = make_uint2(0u, 0u);
-        if (kLock) {
-            gpq = ldq32<VEC>(p.lock_gp, ab + i0, i0, N, ok, 0u);
-            mvq = ldq32<VEC>(p.lock_mv, ab + i0, i0, N, ok, 0u);
-            fmq = ldq32<VEC>(p.lock_fm, ab + i0, i0, N, ok, 0u);
-            if (use_ring) ringq = ldq16<VEC>(p.lock_dist, ((size_t)(ok ? env : 0) * p.lw + slot_next) * N + i0, i0, N, ok);
-        }
+        uint4 gpq = gp_n, mvq = mv_n, fmq = fm_n;
+        const uint2 ringq = ring_n;
         uint4 rnd = make_uint4(0, 0, 0, 0);
         if (p.sample_mode) rnd = sample_quad(p.seed, env_global, q, p.sample_counter);
         uint32_t ds[4] = {0, 0, 0, 0}, cd[4] = {0, 0, 0, 0}, gc[4] = {0, 0, 0, 0};
@@ -634,6 +671,11 @@ __global__ void __launch_bounds__(448, 1) mapf_step_env_kernel(const KParams p, 
             stq16<VEC>(p.lock_dist, ((size_t)(ok ? env : 0) * p.lw + slot_new) * N + i0, i0, N, ok,
                        make_uint2(ds[0] | (ds[1] << 16), ds[2] | (ds[3] << 16)));
         }
+        if (q + 1 < NQ) load_lock(i0 + 4);
+        else if (ok) {
+            const int4 *ew4 = p.env_words + (size_t)env * 4;
+            w0 = ew4[0]; w1 = ew4[1]; w2 = ew4[2]; w3 = ew4[3];
+        }
         // Phase B -- the look-ups (immutable tables: independent of every store, all of them can be in flight at
         // once) and the byte rows of the four agents into my stage row.
         if constexpr (V <= 5) {
@@ -757,11 +799,6 @@ __global__ void __launch_bounds__(448, 1) mapf_step_env_kernel(const KParams p, 
     }
 
     // ---------------------------------------------------------------- the rest of the env words
-    int4 w0 = make_int4(0, 0, 0, 0), w1 = w0, w2 = w0, w3 = w0;
-    if (ok) {
-        const int4 *ew4 = p.env_words + (size_t)env * 4;
-        w0 = ew4[0]; w1 = ew4[1]; w2 = ew4[2]; w3 = ew4[3];
-    }
     int step_count = w0.x + 1;  // ENV:475
     int lock_prev = w0.z, goals_total = w0.w;
     int blocking_total = w1.x, dl_events = w1.y, ll_events = w1.z, dl_steps = w1.w;
@@ -890,8 +927,8 @@ __global__ void __launch_bounds__(448, 1) mapf_step_env_kernel(const KParams p, 
 #pragma unroll 1
         for (int i = 0; i < N; ++i) {
             const uint32_t code = rec[i * 32] & REC_CODE;
-            rowm[((code >> 5) + PADR) * 32] |= 1u << i;
-            colm[((code & 31u) + PADR) * 32] |= 1u << i;
+            atomicOr(&rowm[((code >> 5) + PADR) * 32], 1u << i);   // reductions without a return value: no dependent chain
+            atomicOr(&colm[((code & 31u) + PADR) * 32], 1u << i);
         }
     }
     uint32_t coloc_any = 0, wf_alive = 0, flags_any = 0;   // flags_any: bit 0 deadlock, bit 1 livelock participant set found
@@ -1113,16 +1150,27 @@ __global__ void __launch_bounds__(448, 1) mapf_step_env_kernel(const KParams p, 
                 while (__any_sync(full, rs || rgn)) {
                     if (rs || rgn) {
                         const uint4 x = ph(rc_e + rounds, (uint32_t)lane, 0x52455345u /* "RESE" */, 0);
-                        if (rs) cs = select_kth(freebits, p.fw, (int)__umulhi(x.x, (uint32_t)F));
-                        if (rgn) cg = select_kth(freebits, p.fw, (int)__umulhi(x.y, (uint32_t)F));
+                        if (rs) cs = kth_free((int)__umulhi(x.x, (uint32_t)F));
+                        if (rgn) cg = kth_free((int)__umulhi(x.y, (uint32_t)F));
                     }
                     rs = false; rgn = false;
-                    for (int a = 0; a < N; ++a) {
-                        const int os = __shfl_sync(full, cs, a), og = __shfl_sync(full, cg, a);
-                        if (mine) {
-                            if (a < lane && os == cs) rs = true;   // lower start slot
-                            if (os == cg) rgn = true;              // every start slot is lower than a goal slot
-                            if (a < lane && og == cg) rgn = true;  // lower goal slot
+                    if (N <= 16) {
+                        // all 2N slots side by side (starts in lanes 0..15, goals in lanes 16..31): one match tells every
+                        // slot whether a lower-numbered one holds the same cell
+                        const int gv = __shfl_sync(full, cg, (lane - 16) & 31);
+                        const unsigned same = __match_any_sync(full, lane < 16 ? cs : gv);
+                        const bool dupl = (same & ((1u << lane) - 1u)) != 0;
+                        const bool dupg = __shfl_sync(full, (int)dupl, (lane + 16) & 31) != 0;
+                        rs = mine && dupl;
+                        rgn = mine && dupg;
+                    } else {
+                        for (int a = 0; a < N; ++a) {
+                            const int os = __shfl_sync(full, cs, a), og = __shfl_sync(full, cg, a);
+                            if (mine) {
+                                if (a < lane && os == cs) rs = true;   // lower start slot
+                                if (os == cg) rgn = true;              // every start slot is lower than a goal slot
+                                if (a < lane && og == cg) rgn = true;  // lower goal slot
+                            }
                         }
                     }
                     rounds++;

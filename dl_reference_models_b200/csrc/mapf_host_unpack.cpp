@@ -12,6 +12,10 @@
 #include <mutex>
 #include <thread>
 #include <vector>
+#if defined(__linux__)
+#include <pthread.h>
+#include <sched.h>
+#endif
 
 #if defined(__x86_64__)
 #include <immintrin.h>
@@ -308,7 +312,7 @@ struct HostPool {
     }
 };
 
-HostPool *host_pool_create(int threads) {
+HostPool *host_pool_create(int threads, const int *cpus, int ncpus) {
     HostPool *p = new HostPool();
     p->nthreads = threads < 1 ? 1 : threads;
     p->nchunks = p->nthreads * 4;  // fixed for the pool's lifetime
@@ -322,7 +326,17 @@ HostPool *host_pool_create(int threads) {
         if (cap < p->isa) p->isa = cap;
     }
 #endif
-    for (int i = 1; i < p->nthreads; ++i) p->workers.emplace_back([p] { p->worker(); });
+    for (int i = 1; i < p->nthreads; ++i) {
+        p->workers.emplace_back([p] { p->worker(); });
+#if defined(__linux__)
+        if (cpus && ncpus > 0) {   // one core per worker, inside this rank's share of the node (no migration, no sharing)
+            cpu_set_t set;
+            CPU_ZERO(&set);
+            CPU_SET(cpus[(i - 1) % ncpus], &set);
+            pthread_setaffinity_np(p->workers.back().native_handle(), sizeof(set), &set);
+        }
+#endif
+    }
     return p;
 }
 
@@ -379,6 +393,50 @@ bool host_pool_finish(HostPool *p) {
 void host_pool_job_times(const HostPool *p, int q, int64_t *first_ns, int64_t *last_ns) {
     *first_ns = p->jobs[q].t_first.load(std::memory_order_relaxed);
     *last_ns = p->jobs[q].t_last.load(std::memory_order_relaxed);
+}
+
+// What the host side of mapf_step_host can hope for on THIS machine: streaming fill (write-only) and copy rates of
+// `threads` threads over private chunks of a buffer far larger than the caches (best of three passes, GB/s of bytes
+// written).  The expansion writes every delivered byte once, so delivered bytes / fill rate is its floor.
+void host_memory_probe(int threads, int64_t bytes, const int *cpus, int ncpus, double *fill_gbs, double *copy_gbs) {
+    if (threads < 1) threads = 1;
+    const int64_t chunk = (bytes / threads) & ~int64_t(63);
+    std::vector<uint8_t> a((size_t)(chunk * threads) + 64), b((size_t)(chunk * threads) + 64);
+    memset(a.data(), 1, a.size());
+    memset(b.data(), 2, b.size());
+    double best[2] = {0.0, 0.0};
+    for (int mode = 0; mode < 2; ++mode)
+        for (int rep = 0; rep < 4; ++rep) {
+            std::atomic<int> ready{0};
+            std::atomic<bool> go{false};
+            std::vector<std::thread> ts;
+            for (int t = 0; t < threads; ++t)
+                ts.emplace_back([&, t] {
+                    ready.fetch_add(1);
+                    while (!go.load(std::memory_order_acquire)) cpu_relax();
+                    uint8_t *dst = b.data() + (size_t)t * chunk;
+                    if (mode == 0) memset(dst, rep, (size_t)chunk);
+                    else memcpy(dst, a.data() + (size_t)t * chunk, (size_t)chunk);
+                });
+#if defined(__linux__)
+            if (cpus && ncpus > 0)
+                for (int t = 0; t < threads; ++t) {
+                    cpu_set_t set;
+                    CPU_ZERO(&set);
+                    CPU_SET(cpus[t % ncpus], &set);
+                    pthread_setaffinity_np(ts[t].native_handle(), sizeof(set), &set);
+                }
+#endif
+            while (ready.load() < threads) cpu_relax();
+            const auto t0 = std::chrono::steady_clock::now();
+            go.store(true, std::memory_order_release);
+            for (auto &t : ts) t.join();
+            const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            const double gbs = (double)(chunk * threads) / dt / 1e9;
+            if (rep > 0 && gbs > best[mode]) best[mode] = gbs;
+        }
+    if (fill_gbs) *fill_gbs = best[0];
+    if (copy_gbs) *copy_gbs = best[1];
 }
 
 void host_pool_unpack(HostPool *p, const UnpackJob &job) {

@@ -30,7 +30,8 @@ struct UnpackJob {
 };
 
 struct HostPool;
-HostPool *host_pool_create(int threads);  // threads >= 1 (the caller's thread counts as one)
+// threads >= 1 (the caller's thread counts as one); cpus / ncpus: optional cores to pin the workers to, one each
+HostPool *host_pool_create(int threads, const int *cpus = nullptr, int ncpus = 0);
 void host_pool_destroy(HostPool *p);
 int host_pool_threads(const HostPool *p);
 // One step = begin, submit (non-blocking, at most 32 jobs; a job starts once *ticket == ticket_value, or at once
@@ -40,6 +41,8 @@ bool host_pool_submit(HostPool *p, const UnpackJob &job, const volatile uint32_t
 bool host_pool_finish(HostPool *p);  // false: a ticket did not arrive within 20 s (the GPU work before it failed)
 // trace: steady_clock nanoseconds at which job q of the last step was started / completed
 void host_pool_job_times(const HostPool *p, int q, int64_t *first_ns, int64_t *last_ns);
+// streaming fill / copy rate of `threads` host threads (GB/s of bytes written), optionally pinned like the pool
+void host_memory_probe(int threads, int64_t bytes, const int *cpus, int ncpus, double *fill_gbs, double *copy_gbs);
 // begin + submit + finish of one job
 void host_pool_unpack(HostPool *p, const UnpackJob &job);
 

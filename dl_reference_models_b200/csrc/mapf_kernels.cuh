@@ -142,6 +142,8 @@ struct KParams {
     int4 *o_info;  // [B, 4] int4 = MAPF_INFO_WORDS int32
     int8_t *o_next_actions;  // fused benchmark sampler (scripts/benchmark_multi_agent_env.py:38-57)
     int sample_mode;         // 0 off, 1 uniform over the new action mask, 2 uniform over 0..4
+    int inner_steps;         // lane-per-agent step kernel: env steps per launch (mapf_step_many), >= 1
+    long long out_step_stride;   // ... and how many envs further each of them writes its outputs
     unsigned long long sample_counter;
     uint32_t *err_bits;
     SmemLayout L;  // computed once on the host (mapf_create)
@@ -531,6 +533,12 @@ __global__ void __launch_bounds__(256, MAPF_STEP_MIN_CTAS) mapf_step_kernel(cons
     const int env = tile * groups + grp;
     const bool env_ok = env < p.B;
     const bool act = env_ok && gl < N;
+    // mapf_step_many: `inner_steps` consecutive env steps in ONE launch (small batches are launch-rate bound).  Step
+    // it > 0 takes the actions the fused sampler drew at the end of step it - 1 (kept in a register) and writes its
+    // outputs `out_step_stride` envs further into the caller's [K, B, ...] buffers (0: every step overwrites).
+    int carried_action = 0;
+    for (int it = 0; it < p.inner_steps; ++it) {
+    const size_t so = (size_t)it * (size_t)p.out_step_stride, aoff = so * (size_t)N;
     {   // clear the group's bucket masks (contiguous, 16-byte aligned, multiple of 4 words)
         uint4 *mz = reinterpret_cast<uint4 *>(s_rowm);
         for (int i = gl; i < mask_quads; i += G) mz[i] = make_uint4(0, 0, 0, 0);
@@ -549,7 +557,7 @@ __global__ void __launch_bounds__(256, MAPF_STEP_MIN_CTAS) mapf_step_kernel(cons
     uint32_t pos = act ? p.positions[ai] : NOCELL;
     uint32_t goal = act ? p.goals[ai] : NOCELL - 1;
     uint32_t aflags = act ? p.agent_flags[ai] : 0u;
-    int action = (act && p.actions) ? (int)p.actions[ai] : 0;
+    int action = it > 0 ? carried_action : ((act && p.actions) ? (int)p.actions[ai] : 0);
     if (action < 0 || action > 4) { errs |= MAPF_DEV_ERR_INVALID_ACTION; action = 0; }
     int4 w0 = make_int4(0, 0, 0, 0), w1 = w0, w2 = w0, w3 = w0;
     if (env_ok) {
@@ -755,8 +763,9 @@ __global__ void __launch_bounds__(256, MAPF_STEP_MIN_CTAS) mapf_step_kernel(cons
     const int my_env_in_warp = lane / G;
     uint8_t *my_stage_obs = nullptr;
     const size_t warp_env0 = (size_t)tile * groups + (size_t)(warp * envs_per_warp);
+    const size_t warp_env0_out = warp_env0 + so;   // where this step's rows go in the output buffers
     if (p.o_local_obs) {
-        uint8_t *dst0 = p.o_local_obs + warp_env0 * N * V2;
+        uint8_t *dst0 = p.o_local_obs + warp_env0_out * N * V2;
         my_stage_obs = stage_obs + ((uintptr_t)dst0 & 15) + (size_t)(my_env_in_warp * N + gl) * V2;
     }
     uint32_t amask = 1u;
@@ -832,11 +841,11 @@ __global__ void __launch_bounds__(256, MAPF_STEP_MIN_CTAS) mapf_step_kernel(cons
 
     // ---------------------------------------------------------------- per-step outputs
     if (act) {
-        if (p.o_goal_delta) p.o_goal_delta[ai] = gd;
-        if (p.o_blocking_prev) p.o_blocking_prev[ai] = (uint8_t)bp_prev_out;
-        if (p.o_reward) p.o_reward[ai] = 0.5f * (float)reward_x2;
+        if (p.o_goal_delta) p.o_goal_delta[ai + aoff] = gd;
+        if (p.o_blocking_prev) p.o_blocking_prev[ai + aoff] = (uint8_t)bp_prev_out;
+        if (p.o_reward) p.o_reward[ai + aoff] = 0.5f * (float)reward_x2;
         if (p.o_agent_step_flags)
-            p.o_agent_step_flags[ai] = (uint8_t)((moved ? MAPF_ASF_MOVED : 0) | (failed ? MAPF_ASF_FAILED_MOVE : 0) |
+            p.o_agent_step_flags[ai + aoff] = (uint8_t)((moved ? MAPF_ASF_MOVED : 0) | (failed ? MAPF_ASF_FAILED_MOVE : 0) |
                                                  (gstep ? MAPF_ASF_GOAL_REACHED : 0) | (blocking ? MAPF_ASF_BLOCKING : 0) |
                                                  (wf_cycle ? MAPF_ASF_WFG_CYCLE : 0) | (cur_on_goal ? MAPF_ASF_ON_GOAL : 0));
     }
@@ -846,16 +855,16 @@ __global__ void __launch_bounds__(256, MAPF_STEP_MIN_CTAS) mapf_step_kernel(cons
     const int blocking_step = __popc(__ballot_sync(full, blocking) & gmask);
     if (env_ok && gl == 0) {
         if (p.o_info) {  // integer sources of info["__all__"], ENV:639-656
-            int4 *io = p.o_info + (size_t)env * 4;
+            int4 *io = p.o_info + ((size_t)env + so) * 4;
             io[0] = make_int4(goals_step, kLifelong ? goals_total : __popc(reach), blocking_step, blocking_total);
             io[1] = make_int4(dl_step, ll_step, dl_event, ll_event);
             io[2] = make_int4(dl_events, ll_events, dl_steps, ll_steps);
             io[3] = make_int4(__popc(comp), step_count, __popc(reach), wfg_steps);
         }
-        if (p.o_terminated) p.o_terminated[env] = terminated;
-        if (p.o_truncated) p.o_truncated[env] = truncated;
+        if (p.o_terminated) p.o_terminated[env + so] = terminated;
+        if (p.o_truncated) p.o_truncated[env + so] = truncated;
         if (p.o_step_flags)
-            p.o_step_flags[env] = (uint8_t)((terminated ? MAPF_SF_TERMINATED : 0) | (truncated ? MAPF_SF_TRUNCATED : 0) |
+            p.o_step_flags[env + so] = (uint8_t)((terminated ? MAPF_SF_TERMINATED : 0) | (truncated ? MAPF_SF_TRUNCATED : 0) |
                                             (dl_step ? MAPF_SF_DEADLOCK_STEP : 0) | (ll_step ? MAPF_SF_LIVELOCK_STEP : 0) |
                                             (dl_event ? MAPF_SF_DEADLOCK_EVENT : 0) | (ll_event ? MAPF_SF_LIVELOCK_EVENT : 0) |
                                             (reassigned ? MAPF_SF_GOAL_REASSIGNED : 0) | (wf_any ? MAPF_SF_WFG_CYCLE : 0));
@@ -915,20 +924,22 @@ __global__ void __launch_bounds__(256, MAPF_STEP_MIN_CTAS) mapf_step_kernel(cons
             if (act) {
                 amask = emit_window<SR>(rows, p.wpr, prow(st), pcol(st), pr.occ, pr.xgoal, lin(gg),
                                         lin(st), my_stage_obs);
-                if (p.o_goal_delta) p.o_goal_delta[ai] = goal_delta(gdt, p.R, p.C, gg, st);
-                if (p.o_blocking_prev) p.o_blocking_prev[ai] = 0;
+                if (p.o_goal_delta) p.o_goal_delta[ai + aoff] = goal_delta(gdt, p.R, p.C, gg, st);
+                if (p.o_blocking_prev) p.o_blocking_prev[ai + aoff] = 0;
             }
         }
     }
 
     // ---------------------------------------------------------------- fused action sampler for the next step
-    if (p.sample_mode && act)
-        p.o_next_actions[ai] = (int8_t)sample_action(p.seed, p.env_id_base + env, gl, p.sample_counter,
-                                                     p.sample_mode == 1 ? (int)amask : -1);
+    if (p.sample_mode && act) {
+        carried_action = sample_action(p.seed, p.env_id_base + env, gl, p.sample_counter + (unsigned long long)it,
+                                       p.sample_mode == 1 ? (int)amask : -1);
+        p.o_next_actions[ai] = (int8_t)carried_action;
+    }
 
     // ---------------------------------------------------------------- byte outputs through staging
     if (p.o_action_mask) {
-        uint8_t *dst0 = reinterpret_cast<uint8_t *>(p.o_action_mask) + warp_env0 * N * 5;
+        uint8_t *dst0 = reinterpret_cast<uint8_t *>(p.o_action_mask) + warp_env0_out * N * 5;
         uint8_t *ms = stage_mask + ((uintptr_t)dst0 & 15) + (size_t)(my_env_in_warp * N + gl) * 5;
         if (act) {
 #pragma unroll
@@ -941,9 +952,9 @@ __global__ void __launch_bounds__(256, MAPF_STEP_MIN_CTAS) mapf_step_kernel(cons
         int nenv = envs_left < 0 ? 0 : (envs_left < envs_per_warp ? (int)envs_left : envs_per_warp);
         if (nenv > 0) {
             if (p.o_local_obs)
-                warp_copy_out(p.o_local_obs + warp_env0 * N * V2, stage_obs, nenv * N * V2, lane);
+                warp_copy_out(p.o_local_obs + warp_env0_out * N * V2, stage_obs, nenv * N * V2, lane);
             if (p.o_action_mask)
-                warp_copy_out(reinterpret_cast<uint8_t *>(p.o_action_mask) + warp_env0 * N * 5,
+                warp_copy_out(reinterpret_cast<uint8_t *>(p.o_action_mask) + warp_env0_out * N * 5,
                               stage_mask, nenv * N * 5, lane);
         }
     }
@@ -964,6 +975,7 @@ __global__ void __launch_bounds__(256, MAPF_STEP_MIN_CTAS) mapf_step_kernel(cons
         ew[3] = make_int4(episodes, lock_head, w3.z, w3.w);
     }
     __syncwarp();
+    }  // inner steps
     }  // tile loop
     errs = __reduce_or_sync(full, errs);
     if (errs && lane == 0) atomicOr(p.err_bits, errs);

@@ -245,6 +245,16 @@ int mapf_observe_host(mapf_handle *h, const mapf_outputs *out_host);
 int mapf_step(mapf_handle *h, const int8_t *actions, const int16_t *goal_override,
               const int32_t *goal_rank, const mapf_outputs *out, int32_t auto_reset, void *stream);
 
+/* `steps` consecutive env steps in one call, for rollouts whose actions come from the fused benchmark sampler
+ * (mapf_set_fused_sampler; scripts/benchmark_multi_agent_env.py:38-57): step 1 takes `actions`, step t + 1 the
+ * actions drawn at the end of step t -- exactly what `steps` calls of mapf_step would do, bit for bit, but small
+ * batches (launch-rate bound: ~10 us per launch for 4 096 x 4) run all of them inside ONE kernel launch.
+ * Step t writes its outputs t * out_step_stride_envs envs further into `out` (pass [steps, B, ...] buffers and
+ * stride B for a rollout, or 0 to keep only the last step's).  The sampler's action buffer holds the actions for
+ * the step after the last.  No replay hooks (goal_override / goal_rank) on this entry point. */
+int mapf_step_many(mapf_handle *h, const int8_t *actions, const mapf_outputs *out, int32_t steps,
+                   int64_t out_step_stride_envs, int32_t auto_reset, void *stream);
+
 /* Host-buffer variants: same semantics, every pointer is HOST memory (NULL = skip).
  * H2D of inputs, the kernel, and D2H of the requested outputs all happen inside the call,
  * which returns after the results are in the host buffers. */
@@ -268,10 +278,18 @@ int mapf_step_host(mapf_handle *h, const int8_t *actions, const int16_t *goal_ov
  * requested (and num_envs >= 8192, rows/cols <= 128) those channels cross PCIe as one bit-packed record per
  * agent (3 bits per window cell, 1 bit per mask entry, the integer goal difference, 2*reward) and host threads
  * inside the call expand them into the caller's arrays -- the delivered arrays are bit for bit the same.
- * It is used when this process has >= 12 host cores to itself (cores / LOCAL_WORLD_SIZE); MAPF_HOST_PACK=0 / 1
- * forces it off / on, MAPF_HOST_THREADS / MAPF_HOST_SLICES tune it.
+ * Whether it pays depends on the host (PCIe rate against what its cores and memory system can expand, with
+ * whatever else -- the other ranks of a multi-GPU node -- runs beside it), so the handle measures: its first six
+ * eligible calls go packed, packed, packed, plain, plain, plain (the first of each untimed) and the faster mode
+ * stays.  MAPF_HOST_PACK=0 / 1 forces it off / on, MAPF_HOST_THREADS / MAPF_HOST_SLICES tune it.  The expansion
+ * threads (cores of this process / LOCAL_WORLD_SIZE, at most 16, the caller's thread included) are pinned one per
+ * core to this rank's chunk of the affinity mask when the node is shared (MAPF_HOST_PIN=0 / 1 overrides).
  * mapf_host_transfer_bytes: bytes that actually crossed PCIe in the last mapf_step_host call. */
 int mapf_host_transfer_bytes(const mapf_handle *h, int64_t *h2d_bytes, int64_t *d2h_bytes);
+/* The host-side ceiling of the packed path, measured: streaming fill (write-only) and copy rate, in GB/s of bytes
+ * written, of the threads mapf_step_host expands with (same count, same pinning) over `bytes` of fresh memory.
+ * The expansion writes every delivered byte once: delivered bytes / fill rate bounds it from below. */
+int mapf_host_memory_probe(const mapf_handle *h, int64_t bytes, int32_t *threads_out, double *fill_gbs, double *copy_gbs);
 /* Packed bytes per agent, and the host-side expansion on its own (no GPU needed; used by the CPU test-suite):
  * packed holds the block of n_agents agents -- [n x window+mask bits][n x (int8 d_row, int8 d_col)][n x int8
  * 2*reward] (csrc/mapf_pack_kernel.cuh); goal_delta = difference / denominator. */

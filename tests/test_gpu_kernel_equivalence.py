@@ -188,3 +188,39 @@ def test_full_quads_other_agent_counts(n):
     instantiation): 1 and 3 quads per env, besides the 2 and 4 of the other tests."""
     run_pair(c3(num_agents=n, steps_per_episode=30), 1024 + 9, 70)
     run_pair(c3(num_agents=n, steps_per_episode=30, lifelong_mapf=False), 512 + 3, 70, masked=False)
+
+
+@pytest.mark.parametrize("kind,B,n", [("lane", 4096, 4), ("lane", 300, 16), ("env", 2048, 8)])
+def test_step_many_equals_single_steps(kind, B, n):
+    """mapf_step_many: K env steps with the fused sampler's actions in ONE launch (lane-per-agent kernel; K launches
+    behind the same call for the env-per-thread kernel) -- every output row of every step and the state afterwards
+    equal K single mapf_step calls, bit for bit, across in-launch resets."""
+    import torch
+
+    K = 24
+    cfg = c3(num_agents=n, steps_per_episode=10) if n != 4 else {
+        "env_name": "ReferenceModel-2-1", "num_agents": 4, "sensor_range": 2, "steps_per_episode": 9, "seed": 11}
+    a, b = make(cfg, B, kind), make(cfg, B, kind)
+    a.reset(); b.reset()
+    for e in (a, b):
+        e._next = e.sample_actions(masked=True)
+        e.fuse_sampler("masked")
+    rows = {k: [] for k in nat.OUTPUT_FIELDS}
+    for _ in range(K):
+        a.step(a._next, auto_reset=True)
+        for k in nat.OUTPUT_FIELDS:
+            rows[k].append(a.out[k].clone())
+    buf = b.rollout_buffers(K)
+    b.step_many(K, out=buf)
+    for k in nat.OUTPUT_FIELDS:
+        assert torch.equal(torch.stack(rows[k]), buf[k]), k
+    for k in a.state:
+        assert torch.equal(a.state[k], b.state[k]), k
+    assert torch.equal(a._actions, b._actions)
+    # and again without a rollout buffer: the env's own buffers hold the last step
+    for _ in range(5):
+        a.step(a._next, auto_reset=True)
+    b.step_many(5)
+    for k in nat.OUTPUT_FIELDS:
+        assert torch.equal(a.out[k], b.out[k]), k
+    assert a.poll_errors() == 0 and b.poll_errors() == 0

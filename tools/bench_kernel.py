@@ -60,7 +60,8 @@ T = int(cfg["steps_per_episode"])
 for e in envs:
     e.reset()
     if not args.no_stagger:
-        e.state["env_words"][:, nat.W_STEP_COUNT] = (torch.arange(args.envs, device=dev) % T).to(torch.int32)
+        g = torch.Generator().manual_seed(2026 + envs.index(e))
+        e.state["env_words"][:, nat.W_STEP_COUNT] = (torch.randperm(args.envs, generator=g) % T).to(device=dev, dtype=torch.int32)
     e._next = e.sample_actions(masked=True)
     e.fuse_sampler("masked")
 for i in range(args.burn * len(envs)):
