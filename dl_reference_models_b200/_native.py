@@ -29,7 +29,7 @@ METRIC_COUNT = 16
 INFO_WORDS = 16
 
 OK, ERR_INVALID_ARG, ERR_CUDA, ERR_UNSUPPORTED, ERR_STATE = 0, -1, -2, -3, -4
-DEV_ERR_INVALID_ACTION, DEV_ERR_NO_GOAL_CELL, DEV_ERR_TOO_FEW_CELLS = 1, 2, 4
+DEV_ERR_INVALID_ACTION, DEV_ERR_NO_GOAL_CELL, DEV_ERR_TOO_FEW_CELLS, DEV_ERR_DUPLICATE_LAYOUT = 1, 2, 4, 8
 
 # env_words indices
 (W_STEP_COUNT, W_LOCK_COUNT, W_LOCK_PREV, W_GOALS_TOTAL, W_BLOCKING_TOTAL, W_DEADLOCK_EVENTS,
@@ -178,6 +178,7 @@ def lib():
     L.mapf_step_many.argtypes = [vp, vp, C.POINTER(MapfOutputs), i32, C.c_int64, i32, vp]
     L.mapf_host_transfer_bytes.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.mapf_host_wait_stream.argtypes = [vp, vp]
+    L.mapf_step_host_records.argtypes = [vp, vp, vp, C.POINTER(MapfOutputs), i32]
     L.mapf_host_memory_probe.argtypes = [vp, C.c_int64, C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.mapf_packed_record_bytes.argtypes = [i32]
     L.mapf_unpack_records.argtypes = [vp, C.c_int64, i32, i32, vp, vp, vp, vp, C.c_float, C.c_float]
@@ -212,7 +213,7 @@ EXPORTS = (
     "mapf_version", "mapf_last_error", "mapf_create", "mapf_destroy", "mapf_set_map",
     "mapf_state_nbytes", "mapf_bind_state", "mapf_alloc_state", "mapf_get_state_host",
     "mapf_set_state_host", "mapf_reset", "mapf_step", "mapf_step_many", "mapf_reset_host", "mapf_step_host",
-    "mapf_host_transfer_bytes", "mapf_host_wait_stream", "mapf_host_memory_probe", "mapf_packed_record_bytes", "mapf_unpack_records",
+    "mapf_host_transfer_bytes", "mapf_host_wait_stream", "mapf_host_memory_probe", "mapf_step_host_records", "mapf_packed_record_bytes", "mapf_unpack_records",
     "mapf_observe", "mapf_observe_host",
     "mapf_flat_obs_dim", "mapf_pack_flat_obs", "mapf_sample_masked_actions",
     "mapf_sample_random_actions", "mapf_set_fused_sampler", "mapf_metrics_reduce", "mapf_poll_errors", "mapf_launch_count",

@@ -288,6 +288,44 @@ class BatchedMapfEnv:
         nat.check(self._lib.mapf_step_host(self._h, a, None, None, C.byref(self._chost), int(bool(auto_reset))))
         return self._host_np
 
+    def step_host_records(self, actions=None, auto_reset: bool = True) -> tuple:
+        """Compact delivery (``mapf_step_host_records``): returns ``(records, small)`` -- ``records`` a pinned uint8 array
+        holding the whole batch's bit-packed agent records (13 B per agent at sensor range 2; expand with
+        :meth:`unpack_records` when and where the plain arrays are needed), ``small`` the dict of the remaining host
+        channels.  Nothing is expanded inside the call."""
+        if getattr(self, "_rec_t", None) is None:
+            rs = int(self._lib.mapf_packed_record_bytes(self.V * self.V))
+            self._rec_t = torch.empty((self.B * self.N * rs,), dtype=torch.uint8).pin_memory()
+            small = ("blocking_prev", "terminated", "truncated", "step_flags", "agent_step_flags", "info")
+            self._small_t = {k: torch.empty_like(self.out[k], device="cpu").pin_memory() for k in small}
+            self._small_np = {k: v.numpy() for k, v in self._small_t.items()}
+            self._csmall = nat.MapfOutputs(**{k: (self._small_t[k].data_ptr() if k in self._small_t else None)
+                                              for k in nat.OUTPUT_FIELDS})
+            self._rec_actions = torch.zeros((self.B, self.N), dtype=torch.int8).pin_memory()
+        a = None
+        if actions is not None:
+            src = actions.numpy() if isinstance(actions, torch.Tensor) else np.asarray(actions)
+            np.copyto(self._rec_actions.numpy(), src, casting="unsafe")
+            a = C.c_void_p(self._rec_actions.data_ptr())
+        nat.check(self._lib.mapf_host_wait_stream(self._h, self._stream()))
+        nat.check(self._lib.mapf_step_host_records(self._h, a, C.c_void_p(self._rec_t.data_ptr()), C.byref(self._csmall),
+                                                   int(bool(auto_reset))))
+        return self._rec_t.numpy(), self._small_np
+
+    def unpack_records(self, records: np.ndarray, threads: int = 4) -> dict:
+        """Expand a records block of :meth:`step_host_records` into plain arrays (``mapf_unpack_records``, host only)."""
+        B, N, V = self.B, self.N, self.V
+        out = {"local_obs": np.empty((B, N, V, V), np.uint8), "action_mask": np.empty((B, N, 5), np.int8),
+               "goal_delta": np.empty((B, N, 2), np.float32), "reward": np.empty((B, N), np.float32)}
+        R, Cc = self.grid.shape[-2:]
+        norm = bool(self.cfg.normalize_goal_delta)
+        den0, den1 = (float(max(R - 1, 1)), float(max(Cc - 1, 1))) if norm else (1.0, 1.0)
+        vp = lambda x: x.ctypes.data_as(C.c_void_p)  # noqa: E731
+        nat.check(self._lib.mapf_unpack_records(vp(records), B * N, V * V, int(threads), vp(out["local_obs"]),
+                                                vp(out["action_mask"]), vp(out["goal_delta"]), vp(out["reward"]),
+                                                C.c_float(den0), C.c_float(den1)))
+        return out
+
     def host_transfer_bytes(self) -> tuple:
         """(host-to-device, device-to-host) bytes that crossed PCIe in the last :meth:`step_host`."""
         h2d, d2h = C.c_int64(0), C.c_int64(0)
@@ -385,6 +423,9 @@ class BatchedMapfEnv:
             raise ValueError("Invalid action (outside 0..4) in the batch")  # ENV:504-506
         if bits & nat.DEV_ERR_TOO_FEW_CELLS:
             raise ValueError("Environment has too few free cells for starts and goals")  # ENV:270-275
+        if bits & nat.DEV_ERR_DUPLICATE_LAYOUT:
+            raise ValueError("starts / goals override repeats a cell: a layout is 2N distinct cells (ENV:277); "
+                             "inject co-located agents through set_state instead")
         if bits & nat.DEV_ERR_NO_GOAL_CELL:
             raise RuntimeError("No valid cell available for lifelong goal reassignment.")  # ENV:296-298
 

@@ -776,7 +776,7 @@ int mapf_set_map(mapf_handle *h, const uint8_t *grid) {
         const mapf::EnvLayout &E = h->env_layout;
         std::vector<unsigned char> img((size_t)E.tables_bytes, 0);
         mapf::build_env_tables(h->SR, R, C, h->wpr, h->fw, rows.data(), freeb.data(), h->cfg.normalize_goal_delta != 0,
-                               (float)(R - 1 > 1 ? R - 1 : 1), (float)(C - 1 > 1 ? C - 1 : 1), img.data(), E.t2_off, E.pre_off);
+                               (float)(R - 1 > 1 ? R - 1 : 1), (float)(C - 1 > 1 ? C - 1 : 1), img.data(), E.pre_off);
         CUDA_TRY(cudaMalloc(&h->d_env_tables, img.size()));
         CUDA_TRY(cudaMemcpy(h->d_env_tables, img.data(), img.size(), cudaMemcpyHostToDevice));
     }
@@ -1008,8 +1008,8 @@ int mapf_reset_host(mapf_handle *h, const uint8_t *reset_mask, const int16_t *st
     return MAPF_OK;
 }
 
-int mapf_step_host(mapf_handle *h, const int8_t *actions, const int16_t *goal_override,
-                   const int32_t *goal_rank, const mapf_outputs *out_host, int32_t auto_reset) {
+static int step_host_impl(mapf_handle *h, const int8_t *actions, const int16_t *goal_override,
+                          const int32_t *goal_rank, const mapf_outputs *out_host, int32_t auto_reset, uint8_t *records_host) {
     int rc = check_ready(h);
     if (rc) return rc;
     DeviceGuard guard(h->cfg.device);
@@ -1020,6 +1020,10 @@ int mapf_step_host(mapf_handle *h, const int8_t *actions, const int16_t *goal_ov
     const int64_t B = h->cfg.num_envs, N = h->cfg.num_agents;
     mapf_outputs dev;
     select_outputs(h, out_host, &dev);
+    if (records_host) {   // the four big channels are computed on the device and leave as records only
+        dev.local_obs = h->io_out.local_obs; dev.action_mask = h->io_out.action_mask;
+        dev.goal_delta = h->io_out.goal_delta; dev.reward = h->io_out.reward;
+    }
     mapf::KParams p;
     fill_params(h, p);
     fill_outputs(p, &dev);
@@ -1037,7 +1041,9 @@ int mapf_step_host(mapf_handle *h, const int8_t *actions, const int16_t *goal_ov
     // packed or plain: forced by MAPF_HOST_PACK, else measured on the first six eligible calls (see mapf_handle)
     bool packed = false;
     int auto_phase = -1;   // >= 0: this call is a timed calibration call for mode auto_phase
-    if (host_pack_eligible(h, out_host)) {
+    const bool records = records_host != nullptr;
+    if (records) packed = true;   // same kernels and slicing as the packed path; nothing is expanded on the host
+    else if (host_pack_eligible(h, out_host)) {
         if (h->knob_host_pack >= 0) packed = h->knob_host_pack != 0;
         else if (h->auto_choice >= 0) packed = h->auto_choice != 0;
         else {
@@ -1056,6 +1062,7 @@ int mapf_step_host(mapf_handle *h, const int8_t *actions, const int16_t *goal_ov
     int weights[kMaxHostSlices];
     int nslices = B >= 8192 ? 2 : 1;
     for (int i = 0; i < kMaxHostSlices; ++i) weights[i] = 1;
+    if (records && B < 8192) nslices = 1;
     if (packed && B >= 32768) {
         // measured on B200 / PCIe Gen5 / 16 host cores at 65 536 x 16 (e9 agent-steps/s): 1,1 1.88 | 1,1,1,1 2.19 |
         // 1,3,4,4,3,1 2.26 | 2,4,4,4,2 2.36 | 1,2,3,4,3,2,1 2.16
@@ -1071,7 +1078,7 @@ int mapf_step_host(mapf_handle *h, const int8_t *actions, const int16_t *goal_ov
         nslices = h->knob_plan_n;
         for (int i = 0; i < nslices; ++i) weights[i] = h->knob_plan[i];
     }
-    const int raw32 = packed ? h->knob_raw32 : 0;
+    const int raw32 = (packed && !records) ? h->knob_raw32 : 0;
     struct HostSlice { int64_t e0, n; bool packed; };
     HostSlice plan[kMaxHostSlices + 1];
     int S = 0;
@@ -1099,17 +1106,18 @@ int mapf_step_host(mapf_handle *h, const int8_t *actions, const int16_t *goal_ov
     const float inv1 = h->cfg.normalize_goal_delta ? (float)(h->cfg.cols - 1 > 1 ? h->cfg.cols - 1 : 1) : 1.f;
     int64_t h2d = 0, d2h = 0;
     const uint32_t ticket = ++h->ticket_seq;
-    const bool trace = packed && h->knob_trace;
+    const bool trace = packed && !records && h->knob_trace;
     const int64_t t_begin = std::chrono::steady_clock::now().time_since_epoch().count();
     // closes the step for the host threads on every exit path (an early error return must not leave them polling)
     struct PoolStep {
         mapf::HostPool *pool = nullptr;
         ~PoolStep() { if (pool) mapf::host_pool_finish(pool); }
     } pool_step;
-    if (packed) {
+    if (packed && !records) {
         mapf::host_pool_begin(h->pool);
         pool_step.pool = h->pool;
     }
+    const int PBr = mapf::pack_obs_bytes(h->V2);   // batch-wide record streams: [BN x PBr bits][BN x 2 diffs][BN x 1 reward]
     for (int c = 0; c < S; ++c) {
         const int64_t e0 = plan[c].e0, n = plan[c].n;
         cudaStream_t st = (c & 1) ? h->hstream2 : h->hstream;
@@ -1132,7 +1140,22 @@ int mapf_step_host(mapf_handle *h, const int8_t *actions, const int16_t *goal_ov
             rc = launch_step_range(h, p, e0, (int)n, st);
         }
         if (rc) return rc;
-        if (plan[c].packed) {
+        if (plan[c].packed && records) {
+            // records delivery: the slice's share of the three batch-wide streams, straight into the caller's buffer
+            const int64_t a0 = e0 * N, na = n * N, BN = B * N;
+            uint8_t *d_bits = h->d_packed + a0 * PBr, *d_diff = h->d_packed + BN * PBr + a0 * 2, *d_rew = h->d_packed + BN * (PBr + 2) + a0;
+            const int threads = 256;
+            mapf::mapf_pack_host_kernel<<<(unsigned)((na + threads - 1) / threads), threads, threads * RS + 4, st>>>(
+                h->io_out.local_obs + a0 * h->V2, h->io_out.action_mask + a0 * 5,
+                reinterpret_cast<const float2 *>(h->io_out.goal_delta) + a0, h->io_out.reward + a0, d_bits, na, h->V2,
+                inv0, inv1, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, d_diff, d_rew);
+            CUDA_TRY(cudaGetLastError());
+            h->launches++;
+            CUDA_TRY(cudaMemcpyAsync(records_host + a0 * PBr, d_bits, (size_t)(na * PBr), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaMemcpyAsync(records_host + BN * PBr + a0 * 2, d_diff, (size_t)(na * 2), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaMemcpyAsync(records_host + BN * (PBr + 2) + a0, d_rew, (size_t)na, cudaMemcpyDeviceToHost, st));
+            d2h += na * RS;
+        } else if (plan[c].packed) {
             // one block, one DMA per slice: the three packed streams, then the requested byte channels as they are
             const int64_t a0 = e0 * N, na = n * N;
             uint8_t *blk = h->d_packed + a0 * (RS + 1) + e0 * 3;
@@ -1154,13 +1177,13 @@ int mapf_step_host(mapf_handle *h, const int8_t *actions, const int16_t *goal_ov
         }
         for (int i = 0; i < 10; ++i) {
             char *dst = static_cast<char *>(*output_member(&host_tmp, i));
-            if (!dst || (plan[c].packed && i <= 7)) continue;  // everything but agent_step_flags / info rides in the block
+            if (!dst || (plan[c].packed && !records && i <= 7)) continue;  // everything but agent_step_flags / info rides in the block
             const int64_t per_env = n_out[i] / B;
             CUDA_TRY(cudaMemcpyAsync(dst + e0 * per_env, static_cast<char *>(*output_member(&h->io_out, i)) + e0 * per_env,
                                      (size_t)(n * per_env), cudaMemcpyDeviceToHost, st));
             d2h += n * per_env;
         }
-        if (plan[c].packed) {
+        if (plan[c].packed && !records) {
             // the slice's ticket: written into pinned host memory behind the block's copy; the host threads start on
             // the job when they see it (no CUDA call, no event wait on their side)
             mapf::mapf_ticket_kernel<<<1, 1, 0, st>>>(h->h_tickets + c, ticket);
@@ -1183,7 +1206,7 @@ int mapf_step_host(mapf_handle *h, const int8_t *actions, const int16_t *goal_ov
         }
     }
     const int64_t t_enq = std::chrono::steady_clock::now().time_since_epoch().count();
-    if (packed) {
+    if (packed && !records) {
         pool_step.pool = nullptr;
         if (!mapf::host_pool_finish(h->pool)) {  // this thread joins in; returns when every slice is expanded
             const cudaError_t e = cudaDeviceSynchronize();
@@ -1229,6 +1252,22 @@ int mapf_host_wait_stream(mapf_handle *h, void *stream) {
     h->last_user_stream = static_cast<cudaStream_t>(stream);
     h->user_dirty = true;
     return MAPF_OK;
+}
+
+int mapf_step_host(mapf_handle *h, const int8_t *actions, const int16_t *goal_override,
+                   const int32_t *goal_rank, const mapf_outputs *out_host, int32_t auto_reset) {
+    return step_host_impl(h, actions, goal_override, goal_rank, out_host, auto_reset, nullptr);
+}
+
+int mapf_step_host_records(mapf_handle *h, const int8_t *actions, uint8_t *records_host, const mapf_outputs *out_host_small,
+                           int32_t auto_reset) {
+    if (!records_host) return fail(MAPF_ERR_INVALID_ARG, "null records buffer");
+    if (h && (h->cfg.rows > 128 || h->cfg.cols > 128))
+        return fail(MAPF_ERR_UNSUPPORTED, "records carry the goal difference as int8: maps up to 128 x 128");
+    if (out_host_small && (out_host_small->local_obs || out_host_small->action_mask || out_host_small->goal_delta ||
+                           out_host_small->reward))
+        return fail(MAPF_ERR_INVALID_ARG, "local_obs / action_mask / goal_delta / reward arrive as records: leave them NULL");
+    return step_host_impl(h, actions, nullptr, nullptr, out_host_small, auto_reset, records_host);
 }
 
 int mapf_host_memory_probe(const mapf_handle *h, int64_t bytes, int32_t *threads_out, double *fill_gbs, double *copy_gbs) {

@@ -51,7 +51,6 @@ __host__ __device__ constexpr int env_stage_stride(int V2) { return ((4 * V2 + 2
 
 struct EnvLayout {
     int tables_bytes;  // multiple of 16
-    int t2_off;        // two-plane window-row table (V <= 5), behind the obstacle-window table
     int pre_off;       // prefix counts of the free-cell bitmap (reset draws)
     int warp_bytes;    // per-warp block: [stage][occupancy boards][goal boards][agent records]
     int board_rows;    // max(R, C, N) + 2 * ENV_ROW_PAD
@@ -62,8 +61,7 @@ struct EnvLayout {
 __host__ __device__ inline EnvLayout make_env_layout(int N, int R, int C, int SR, int fw, int warps) {
     const int V = 2 * SR + 1, V2 = V * V;
     EnvLayout E;
-    E.t2_off = (ENV_LUT_OFF + R * 32 * (V > 5 ? 8 : 4) + 15) & ~15;
-    E.pre_off = E.t2_off + (V <= 5 ? (4 << (2 * V)) : 0);         // u32[1 << 2V]: two V-bit planes -> V nibbles
+    E.pre_off = (ENV_LUT_OFF + R * 32 * (V > 5 ? 8 : 4) + 15) & ~15;
     E.tables_bytes = E.pre_off + 65 * 4 + 12;                     // u32[fw + 1]: free cells in front of bitmap word w (fw <= 64)
     E.board_rows = R > C ? R : C;
     if (N > E.board_rows) E.board_rows = N;
@@ -171,7 +169,7 @@ __device__ __forceinline__ uint4 sample_quad(unsigned long long seed, long long 
 // the lane-per-agent kernel (bit c + PAD of row r + PAD = obstacle or out of bounds, ENV:718).
 inline void build_env_tables(int SR, int R, int C, int wpr, int fw, const uint32_t *rows,
                              const uint32_t *free_bits, int normalize, float den0, float den1, unsigned char *img,
-                             int t2_off, int pre_off) {
+                             int pre_off) {
     const int V = 2 * SR + 1;
     {
         uint32_t *pre = reinterpret_cast<uint32_t *>(img + pre_off);
@@ -179,19 +177,6 @@ inline void build_env_tables(int SR, int R, int C, int wpr, int fw, const uint32
         for (int w = 0; w <= 64; ++w) {
             pre[w] = acc;
             if (w < fw) acc += (uint32_t)__builtin_popcount(free_bits[w]);
-        }
-    }
-    if (V <= 5) {
-        // index = plane0 | plane1 << V with plane0 = obstacle | other-goal, plane1 = other-agent | other-goal
-        // (the three sets are disjoint, ENV:730-745): nibble j = 1 obstacle, 2 agent, 4 other's goal
-        uint32_t *t2 = reinterpret_cast<uint32_t *>(img + t2_off);
-        for (int x = 0; x < (1 << (2 * V)); ++x) {
-            uint32_t sv = 0;
-            for (int j = 0; j < V; ++j) {
-                const int b0 = (x >> j) & 1, b1 = (x >> (V + j)) & 1;
-                sv |= (uint32_t)(b0 && b1 ? 4 : b0 ? 1 : b1 ? 2 : 0) << (4 * j);
-            }
-            t2[x] = sv;
         }
     }
     auto rowbits = [&](int r, int c0, int n) {  // n bits starting at map column c0 of map row r (padding = 1)
@@ -241,6 +226,12 @@ inline void build_env_tables(int SR, int R, int C, int wpr, int fw, const uint32
 __device__ __forceinline__ uint32_t nibbles_to_bytes(uint32_t sel) {
     uint32_t w;
     asm("prmt.b32 %0, %1, %2, %3;" : "=r"(w) : "r"(0x03020100u), "r"(0x00000004u), "r"(sel));
+    return w;
+}
+// nibble j of `sel` (values 0..3) -> byte j of {0, 1, 2, 4}: the two-plane window rows of the walk (3 = both planes = OTHER_GOAL)
+__device__ __forceinline__ uint32_t nibbles_to_bytes_0124(uint32_t sel) {
+    uint32_t w;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(w) : "r"(0x04020100u), "r"(0u), "r"(sel));
     return w;
 }
 // bits 0..3 of m -> bytes 0/1
@@ -334,7 +325,6 @@ __global__ void __launch_bounds__(448, 1) mapf_step_env_kernel(const KParams p, 
     const float *gdt = reinterpret_cast<const float *>(esm + ENV_GDT_OFF);
     const uint32_t esm_s = (uint32_t)__cvta_generic_to_shared(esm);
     const uint32_t t1_s = esm_s + ENV_T1_OFF, kth_s = esm_s + ENV_KTH_OFF, lut_s = esm_s + ENV_LUT_OFF;
-    const uint32_t t2_s = esm_s + (uint32_t)E.t2_off;
     const uint32_t *freepre = reinterpret_cast<const uint32_t *>(esm + E.pre_off);
     // k-th free cell (cell-linear order, ENV:82) by binary search over the prefix counts
     auto kth_free = [&](int k) -> int {
@@ -508,6 +498,7 @@ __global__ void __launch_bounds__(448, 1) mapf_step_env_kernel(const KParams p, 
     uint32_t moved_m = 0, failed_m = 0, gstep_m = 0, ongoal_m = 0;
     uint32_t Gd = 0, Md = 0, Fd = 0, Gl = 0, Ml = 0;
     const unsigned act_w = __ballot_sync(full, ok);
+    const bool masked_sampler = p.sample_mode == 1;
 
     // ---------------------------------------------------------------- the agent walk (ENV:502-563), a quad at a time
     // lock history of the quad AFTER the one being walked: its loads are issued behind phase A and land during
@@ -535,17 +526,15 @@ __global__ void __launch_bounds__(448, 1) mapf_step_env_kernel(const KParams p, 
         uint32_t ds[4] = {0, 0, 0, 0}, cd[4] = {0, 0, 0, 0}, gc[4] = {0, 0, 0, 0};
         uint32_t masks4 = 0, next4 = 0;
         int patch[4];
-        uint32_t ctr_other = 0;
         // Phase A -- everything that has to see the occupancy board as it is right after agent k's own move
         // (snapshot k, ENV:528-536): the move itself and the raw window rows.  Nothing here waits for a table
         // look-up or writes the stage, so the board accesses of the four agents sit back to back in program
         // order and the arithmetic of agent k overlaps the shared-memory latency of agent k + 1.
-        // win[k][wr]: row wr of agent k's window as a table index -- (obstacle | goal) bits and (agent | goal)
-        // bits side by side (V <= 5), or the finished nibble row (V = 7, three look-ups in t1).
+        // win[k][wr]: row wr of agent k's window as V nibbles (codes 1 / 2 / 3, see below).
         uint32_t win[4][V];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            patch[k] = -1;
+            patch[k] = 4 * V2 + 20;
 #pragma unroll
             for (int wr = 0; wr < V; ++wr) win[k][wr] = 0;
             if (!VEC && i0 + k >= N) continue;
@@ -557,28 +546,19 @@ __global__ void __launch_bounds__(448, 1) mapf_step_env_kernel(const KParams p, 
             // ENV:512-526: target cell; obstacle / bounds were resolved by the pre-pass, occupancy comes from the board
             const uint32_t tcode = code + (uint32_t)action_delta(a);
             const bool wants = ok && a != 0 && !(rv4[k] & 0x4000u);
-            bool moves = false;
-            if (wants) {
-                uint32_t *trow = &occ[(tcode >> 5) * 32];
-                const uint32_t tb = 1u << (tcode & 31u);
-                if (!(*trow & tb)) {
-                    moves = true;
-                    occ[(code >> 5) * 32] &= ~(1u << (code & 31u));
-                    *trow |= tb;
-                }
-            }
+            // No branches in here: the body of the k loop is meant to be ONE basic block, so that the scheduler can
+            // interleave the arithmetic of the four agents around the board accesses.  The target row is read
+            // whether or not the agent wants to move (a blocked target may lie one row outside the board: inside
+            // the allocation, ignored), the two board updates are predicated shared-memory reductions.
+            const uint32_t tb = 1u << (tcode & 31u);
+            const uint32_t tv = occ[(tcode >> 5) * 32];
+            const bool moves = wants & ((tv & tb) == 0u);
+            atomicAnd(&occ[(code >> 5) * 32], moves ? ~(1u << (code & 31u)) : 0xFFFFFFFFu);   // neutral when the agent stays
+            atomicOr(&occ[(tcode >> 5) * 32], moves ? tb : 0u);
             const bool failed = ok && a != 0 && !moves;  // ENV:583
-            if (degen) {
-                if (moves) {   // ENV:523: leaving clears the owner of the cell, whoever else stands there
-                    for (int a2 = 0; a2 < N; ++a2)
-                        if ((rec[a2 * 32] & REC_CODE) == ocode) solo_m &= ~(1u << a2);
-                    solo_m |= bit;
-                } else if (!(solo_m & bit) && ((occ[(code >> 5) * 32] >> (code & 31u)) & 1u)) {
-                    ctr_other |= 1u << k;   // my cell belongs to somebody else (ENV:737-739)
-                }
-            }
-            if (moves) { moved_m |= bit; code = tcode; }
-            if (failed) failed_m |= bit;
+            moved_m |= moves ? bit : 0u;
+            failed_m |= failed ? bit : 0u;
+            code = moves ? tcode : code;
             // ENV:538-563.  A lifelong arrival gets its new goal after the walk, in agent order.
             const bool on_goal = ok && code == gcode;
             bool gstep = false, cur_on_goal = on_goal;
@@ -589,8 +569,8 @@ __global__ void __launch_bounds__(448, 1) mapf_step_env_kernel(const KParams p, 
                 completed_m |= bit; reached_m &= ~bit;
                 cur_on_goal = false;   // ENV:555
             }
-            if (gstep) gstep_m |= bit;
-            if (cur_on_goal) ongoal_m |= bit;
+            gstep_m |= gstep ? bit : 0u;
+            ongoal_m |= cur_on_goal ? bit : 0u;
             // ENV:581-594 lock history
             uint32_t delta16 = 0;
             if (kLock) {
@@ -600,16 +580,15 @@ __global__ void __launch_bounds__(448, 1) mapf_step_env_kernel(const KParams p, 
                 const uint32_t m2 = (qget(mvq, k) << 1) | (moves ? 1u : 0u);
                 const uint32_t f2 = (qget(fmq, k) << 1) | (failed ? 1u : 0u);
                 qset(gpq, k, g2); qset(mvq, k, m2); qset(fmq, k, f2);
-                if (ok) {
-                    if (g2 & mdw) Gd |= bit;
-                    if (m2 & mdw) Md |= bit;
-                    if (f2 & mdw) Fd |= bit;
-                    if (g2 & mlw) Gl |= bit;
-                    if (m2 & mlw) Ml |= bit;
-                }
+                const uint32_t okbit = ok ? bit : 0u;
+                Gd |= (g2 & mdw) ? okbit : 0u;
+                Md |= (m2 & mdw) ? okbit : 0u;
+                Fd |= (f2 & mdw) ? okbit : 0u;
+                Gl |= (g2 & mlw) ? okbit : 0u;
+                Ml |= (m2 & mlw) ? okbit : 0u;
                 const int dist = abs((int)(gcode >> 5) - (int)(code >> 5)) + abs((int)(gcode & 31u) - (int)(code & 31u));
                 ds[k] = (uint32_t)dist;
-                if (use_ring && ok) delta16 = (uint32_t)((int)(int16_t)hget(ringq, k) - dist) << 16;
+                delta16 = (use_ring && ok) ? (uint32_t)((int)(int16_t)hget(ringq, k) - dist) << 16 : 0u;
             }
             rec[(i0 + k) * 32] = code | (rv4[k] & 0x7800u) | delta16;
             cd[k] = code;
@@ -635,11 +614,12 @@ __global__ void __launch_bounds__(448, 1) mapf_step_env_kernel(const KParams p, 
                 if (wr == SR - 1) blk_up = blk4;
                 if (wr == SR) blk_mid = blk4;
                 if (wr == SR + 1) blk_dn = blk4;
-                if constexpr (V <= 5) {
-                    win[k][wr] = (o4 | g4) + ((agent4 | g4) << V);   // byte offset into t2: planes side by side
-                } else {
-                    win[k][wr] = lds_pure(t1_s + o4) + (lds_pure(t1_s + agent4) << 1) + (lds_pure(t1_s + g4) << 2);
-                }
+                // plane 0 = obstacle | other's goal, plane 1 = other agent | other's goal (the three sets are disjoint,
+                // ENV:730-745): spread(plane 0) + 2 * spread(plane 1) is the nibble row with codes 1 / 2 / 3, and the
+                // nibble -> byte PRMT of phase B maps 3 to OTHER_GOAL (4).  t1 has one word per bank for V <= 5: lanes that
+                // share a bank share the address, so these data-dependent look-ups never conflict (a single 4^V-entry
+                // table would: ~3.5 wavefronts per access, measured).  The loads are free to float down to phase B.
+                win[k][wr] = lds_pure(t1_s + (o4 | g4)) + (lds_pure(t1_s + (agent4 | g4)) << 1);
             }
             // ENV:761-771: a direction is valid iff its neighbour is neither obstacle nor agent
             const uint32_t am = 1u | ((~blk_up >> (2 + SR)) & 1u) << 1 | ((~blk_mid >> (2 + SR + 1)) & 1u) << 2 |
@@ -648,17 +628,16 @@ __global__ void __launch_bounds__(448, 1) mapf_step_env_kernel(const KParams p, 
             // own goal (code 3): the goal plane wrote 4 there; patched after the quad's words are stored
             {
                 const int dr = (int)(gcode >> 5) - r + SR, dc = (int)(gcode & 31u) - c + SR;
-                if ((unsigned)dr < (unsigned)V && (unsigned)dc < (unsigned)V) {
-                    const int ci = dr * V + dc;
-                    const bool occ_other = (ci != CTR) && ((occ[(gcode >> 5) * 32] >> (gcode & 31u)) & 1u);
-                    if (!((obst >> ci) & 1) && !occ_other) patch[k] = V2 * k + ci;
-                }
+                const bool in = (unsigned)dr < (unsigned)V && (unsigned)dc < (unsigned)V;
+                const int ci = in ? dr * V + dc : 0;
+                const bool occ_other = (ci != CTR) && ((occ[(gcode >> 5) * 32] >> (gcode & 31u)) & 1u);
+                // byte 4 * V2 + 20 of the stage row is padding: the harmless target of a patch that does not apply
+                patch[k] = (in && !((obst >> ci) & 1) && !occ_other) ? V2 * k + ci : 4 * V2 + 20;
             }
-            if (p.sample_mode) {
+            {   // both samplers, selected afterwards (stored only when the sampler is fused in)
                 const uint32_t x = qget(rnd, k);
-                uint32_t na;
-                if (p.sample_mode == 1) na = lds_pure_u8(kth_s + am * 8u + __umulhi(x, (uint32_t)__popc(am)));
-                else na = __umulhi(x, 5u);
+                const uint32_t na_masked = lds_pure_u8(kth_s + am * 8u + __umulhi(x, (uint32_t)__popc(am)));
+                const uint32_t na = masked_sampler ? na_masked : __umulhi(x, 5u);
                 next4 |= na << (8 * k);
             }
         }
@@ -676,14 +655,8 @@ __global__ void __launch_bounds__(448, 1) mapf_step_env_kernel(const KParams p, 
             const int4 *ew4 = p.env_words + (size_t)env * 4;
             w0 = ew4[0]; w1 = ew4[1]; w2 = ew4[2]; w3 = ew4[3];
         }
-        // Phase B -- the look-ups (immutable tables: independent of every store, all of them can be in flight at
-        // once) and the byte rows of the four agents into my stage row.
-        if constexpr (V <= 5) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-#pragma unroll
-                for (int wr = 0; wr < V; ++wr) win[k][wr] = lds_pure(t2_s + win[k][wr]);   // ENV:730-745 codes 1 / 2 / 4 as nibbles
-        }
+        // Phase B -- the byte rows of the four agents into my stage row (the table look-ups feeding it were issued in
+        // phase A and, being loads from immutable tables, are free to complete anywhere in between).
         uint32_t carry = 0;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -706,22 +679,16 @@ __global__ void __launch_bounds__(448, 1) mapf_step_env_kernel(const KParams p, 
 #pragma unroll
             for (int m = 0; m < NWMAX; ++m) {
                 if (m >= nw) continue;
-                uint32_t w = nibbles_to_bytes((m & 1) ? (acc[m >> 1] >> 16) : acc[m >> 1]);
+                uint32_t w = nibbles_to_bytes_0124((m & 1) ? (acc[m >> 1] >> 16) : acc[m >> 1]);
                 if (m == 0 && (k & 3) != 0) w |= carry;                                  // leading partial word shared with agent k-1
                 if (m == nw - 1 && (((k & 3) + V2) & 3) != 0) carry = w;                 // trailing partial word: stored by agent k+1
-                else if (ok) sts_stage(my_stage_s + (uint32_t)((j0 + m) * 4), w);
+                else sts_stage(my_stage_s + (uint32_t)((j0 + m) * 4), w);   // lanes beyond the batch fill rows nobody flushes
             }
-            if (!VEC && i0 + k == N - 1 && (((k & 3) + V2) & 3) != 0 && ok) sts_stage(my_stage_s + (uint32_t)((j0 + nw - 1) * 4), carry);
+            if (!VEC && i0 + k == N - 1 && (((k & 3) + V2) & 3) != 0) sts_stage(my_stage_s + (uint32_t)((j0 + nw - 1) * 4), carry);
         }
-        if (ok) {
+        {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (patch[k] >= 0) sts_stage_u8(my_stage_s + (uint32_t)patch[k], 3u);
-            if (ctr_other) {   // injected co-location only
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    if ((ctr_other >> k) & 1u) sts_stage_u8(my_stage_s + (uint32_t)(V2 * k + CTR), 2u);
-            }
+            for (int k = 0; k < 4; ++k) sts_stage_u8(my_stage_s + (uint32_t)patch[k], 3u);
             // action masks of the quad: 4 x 5 bytes = 5 words after the observation words
             uint32_t lo[4], hi[4];
 #pragma unroll
@@ -735,6 +702,8 @@ __global__ void __launch_bounds__(448, 1) mapf_step_env_kernel(const KParams p, 
             my_stage[OBS_W + 2] = (lo[1] >> 24) | (hi[1] << 8) | (lo[2] << 16);
             my_stage[OBS_W + 3] = (lo[2] >> 16) | (hi[2] << 16) | (lo[3] << 24);
             my_stage[OBS_W + 4] = (lo[3] >> 8) | (hi[3] << 24);
+        }
+        if (ok) {
             if (p.o_goal_delta) {
                 float2 gd[4];
 #pragma unroll
@@ -806,6 +775,36 @@ __global__ void __launch_bounds__(448, 1) mapf_step_env_kernel(const KParams p, 
     uint32_t rng_counter = (uint32_t)w2.y;
     int ep_return_x2 = w2.z, wfg_steps = w2.w;
     int episodes = w3.x;
+
+    // ---------------------------------------------------------------- injected co-location (ENV:658-666), kept off the walk
+    // Replays who owns which cell through the moves of this step (ENV:523: a leaving agent clears the owner for
+    // everybody on its cell; ENV:525: a mover owns its new cell) and marks OTHER_AGENT in the centre of the window
+    // of every agent that stood on a cell owned by somebody else when its observation was taken (ENV:737-739).
+    if (__any_sync(full, degen)) {
+        __syncwarp();   // the flush above wrote those windows
+        if (degen && ok) {
+            for (int i = 0; i < N; ++i) {
+                const uint32_t rvi = rec[i * 32], newc = rvi & REC_CODE, biti = 1u << i;
+                const bool mvd = (moved_m >> i) & 1u;
+                const uint32_t oldc = mvd ? newc - (uint32_t)action_delta((rvi >> 11) & 7u) : newc;
+                bool owned_by_other = false;
+                for (int a2 = 0; a2 < N; ++a2) {
+                    if (a2 == i) continue;
+                    const uint32_t rva = rec[a2 * 32];
+                    uint32_t ca = rva & REC_CODE;   // where a2 stands at agent i's turn: moved already only if a2 < i
+                    if (a2 > i && ((moved_m >> a2) & 1u)) ca -= (uint32_t)action_delta((rva >> 11) & 7u);
+                    if (ca == oldc) {
+                        if (mvd) solo_m &= ~(1u << a2);                       // ENV:523
+                        else if ((solo_m >> a2) & 1u) owned_by_other = true;  // the cell has an owner, and it is not me
+                    }
+                }
+                if (mvd) solo_m |= biti;                                       // ENV:525
+                else if (!(solo_m & biti) && owned_by_other && p.o_local_obs)
+                    p.o_local_obs[(ab + i) * V2 + CTR] = 2;
+            }
+        }
+        __syncwarp();
+    }
 
     // ---------------------------------------------------------------- lifelong goal reassignment (ENV:284-304, 547-556)
     if (kLock) lock_head = slot_next;
@@ -983,10 +982,12 @@ __global__ void __launch_bounds__(448, 1) mapf_step_env_kernel(const KParams p, 
         }
         // intended cell (kept even when invalid, ENV:514-515) -> who stands there.  A blocked target is an
         // obstacle or out of bounds: nobody can stand there.
+        // (needed for ENV:609-623 only while some agent has sticky-reached -- never in lifelong mode -- and for the
+        // wait-for edge of an agent whose move failed)
         uint32_t owner = here & ~bit;
         if (!(moved_m & bit)) {
             owner = 0;
-            if (!(rv & 0x4000u)) {
+            if (!(rv & 0x4000u) && (reached_m != 0u || (failed_m & bit))) {
                 const uint32_t tcode = code + (uint32_t)action_delta((rv >> 11) & 7u);
                 owner = rowm[((tcode >> 5) + PADR) * 32] & colm[((tcode & 31u) + PADR) * 32] & ~bit;
             }

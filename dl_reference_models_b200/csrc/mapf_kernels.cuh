@@ -274,7 +274,8 @@ __device__ __forceinline__ void pair_loop(const uint32_t *s_new, const uint32_t 
             const uint32_t ps = (a <= gl) ? an[k] : as[k];
             uint32_t d = ps - origin;
             uint32_t t1 = d & 1023u, t2 = d >> 10;
-            if (other && t1 < (uint32_t)V && t2 < (uint32_t)V) o.occ |= (WB)1 << (t2 * V + t1);
+            // a lower-index agent on MY cell (injected states only, ENV:658-666) does not own it (ENV:200-205): skip it
+            if (other && t1 < (uint32_t)V && t2 < (uint32_t)V && !(a < gl && ps == my_new_lin)) o.occ |= (WB)1 << (t2 * V + t1);
             d = ag[k] - origin;
             t1 = d & 1023u; t2 = d >> 10;
             if (other && t1 < (uint32_t)V && t2 < (uint32_t)V) o.xgoal |= (WB)1 << (t2 * V + t1);
@@ -1050,6 +1051,15 @@ __global__ void __launch_bounds__(256) mapf_reset_kernel(const KParams p) {
         else { st = p.positions[ai]; gg = p.goals[ai]; }
     }
 
+    if (have_override && !p.observe_only) {
+        // A layout is 2N distinct cells in the reference (rng.choice(..., replace=False), ENV:277; the tables of
+        // get_grid.py).  Two agents with one goal would need the goal-owner grid's last-index-wins rule (ENV:207-212)
+        // that the kernels do not keep, two with one start are the injected states of ENV:658-666 (set_state is the
+        // door for those): an override that repeats a cell is refused, loudly.
+        const unsigned ms = __match_any_sync(full, act ? st : (0x80000000u | (uint32_t)lane));
+        const unsigned mg = __match_any_sync(full, act ? gg : (0x80000000u | (uint32_t)lane));
+        if (act && (((ms | mg) & gmask & ~(1u << lane)) != 0)) errs |= MAPF_DEV_ERR_DUPLICATE_LAYOUT;
+    }
     const uint32_t l = act ? lin(st) : LFAR;
     s_new[gl] = l; s_snap[gl] = l; s_goal[gl] = act ? lin(gg) : LFAR;
     __syncwarp();

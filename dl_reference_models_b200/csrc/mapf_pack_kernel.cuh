@@ -26,7 +26,10 @@ __global__ void __launch_bounds__(256) mapf_pack_host_kernel(
     const float *__restrict__ reward, uint8_t *__restrict__ out, long long n_agents, int V2, float inv0, float inv1,
     const uint8_t *__restrict__ bp, uint8_t *__restrict__ out_bp, const uint8_t *__restrict__ env0,
     uint8_t *__restrict__ out_env0, const uint8_t *__restrict__ env1, uint8_t *__restrict__ out_env1,
-    const uint8_t *__restrict__ env2, uint8_t *__restrict__ out_env2, long long n_envs) {
+    const uint8_t *__restrict__ env2, uint8_t *__restrict__ out_env2, long long n_envs,
+    uint8_t *__restrict__ diff_out = nullptr, uint8_t *__restrict__ rew_out = nullptr) {
+    // diff_out / rew_out: where the slice's goal-difference and reward streams go when they do not follow the bit
+    // stream directly (the batch-wide three-stream layout of mapf_step_host_records)
     extern __shared__ uint8_t pack_stage[];  // blockDim.x * PB bytes (+3 slack)
     const int nfull = V2 >> 3, PB = nfull * 3 + 1;
     const long long first = (long long)blockIdx.x * blockDim.x;
@@ -46,10 +49,10 @@ __global__ void __launch_bounds__(256) mapf_pack_host_kernel(
         for (int i = 0; i < 5; ++i) w |= (uint32_t)(mask[a * 5 + i] != 0) << (3 + i);
         dst[k] = (uint8_t)w;
         const float2 g = gd[a];
-        uint8_t *diff = out + n_agents * PB + a * 2;  // byte stores: the stream's offset may be odd
+        uint8_t *diff = (diff_out ? diff_out : out + n_agents * PB) + a * 2;  // byte stores: the stream's offset may be odd
         diff[0] = (uint8_t)(int8_t)__float2int_rn(g.x * inv0);
         diff[1] = (uint8_t)(int8_t)__float2int_rn(g.y * inv1);
-        out[n_agents * (PB + 2) + a] = (uint8_t)(int8_t)__float2int_rn(reward[a] * 2.0f);
+        (rew_out ? rew_out : out + n_agents * (PB + 2))[a] = (uint8_t)(int8_t)__float2int_rn(reward[a] * 2.0f);
         // byte channels that ride along unchanged (one DMA per slice instead of one per channel)
         if (out_bp) out_bp[a] = bp[a];
         if (a < n_envs) {

@@ -48,6 +48,7 @@ extern "C" {
 #define MAPF_DEV_ERR_INVALID_ACTION 1u /* ENV:504-506 (ValueError in the reference) */
 #define MAPF_DEV_ERR_NO_GOAL_CELL 2u   /* ENV:296-298 (RuntimeError in the reference) */
 #define MAPF_DEV_ERR_TOO_FEW_CELLS 4u  /* ENV:270-275 (ValueError in the reference) */
+#define MAPF_DEV_ERR_DUPLICATE_LAYOUT 8u /* a starts / goals override names one cell twice (a layout is 2N distinct cells, ENV:277) */
 
 /* env_config keys that affect the transition (ENV:38-61), plus batching/sharding keys. */
 typedef struct mapf_config {
@@ -286,6 +287,17 @@ int mapf_step_host(mapf_handle *h, const int8_t *actions, const int16_t *goal_ov
  * core to this rank's chunk of the affinity mask when the node is shared (MAPF_HOST_PIN=0 / 1 overrides).
  * mapf_host_transfer_bytes: bytes that actually crossed PCIe in the last mapf_step_host call. */
 int mapf_host_transfer_bytes(const mapf_handle *h, int64_t *h2d_bytes, int64_t *d2h_bytes);
+/* Compact delivery, for callers that accept it: local_obs, action_mask, goal_delta and reward arrive as the
+ * bit-packed records themselves -- `records_host` (pinned recommended) receives, for the whole batch of BN = B * N
+ * agents, [BN x mapf_packed_record_bytes(v2) - 3 bytes: window + mask bits][BN x (int8 d_row, int8 d_col)][BN x int8
+ * 2*reward], i.e. exactly the block mapf_unpack_records expands -- and nothing is expanded inside the call: 13 B per
+ * agent cross PCIe and reach host memory instead of 42 B.  A consumer expands what it needs when it needs it (a
+ * learner, per minibatch) with mapf_unpack_records, bit for bit the arrays mapf_step_host would have delivered.
+ * `out_host_small`: the remaining channels (blocking_prev, terminated, truncated, step_flags, agent_step_flags,
+ * info) as plain host arrays, NULL members skipped; its four big members must be NULL.  This is what scales on a
+ * multi-GPU node whose host memory system, not PCIe, bounds the full-format delivery. */
+int mapf_step_host_records(mapf_handle *h, const int8_t *actions, uint8_t *records_host, const mapf_outputs *out_host_small,
+                           int32_t auto_reset);
 /* The host-side ceiling of the packed path, measured: streaming fill (write-only) and copy rate, in GB/s of bytes
  * written, of the threads mapf_step_host expands with (same count, same pinning) over `bytes` of fresh memory.
  * The expansion writes every delivered byte once: delivered bytes / fill rate bounds it from below. */

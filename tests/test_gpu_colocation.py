@@ -146,3 +146,34 @@ def test_injected_colocation_traces_of_the_live_reference(kind, lifelong):
         alive &= ~((g[f"{tag}_terminated"][sel, t] | g[f"{tag}_truncated"][sel, t]).astype(bool))
         if not alive.any():
             break
+
+
+@pytest.mark.parametrize("kind", ["lane", "env"])
+def test_layout_override_with_a_repeated_cell_is_refused(kind):
+    """A layout is 2N distinct cells (ENV:277 `replace=False`, the get_grid.py tables).  An override that names a goal
+    (or a start) twice would need the goal-owner grid's last-index-wins rule (ENV:207-212), which the kernels do not
+    keep: it fails loudly instead of silently showing OWN_GOAL where the reference shows OTHER_GOAL."""
+    import torch
+
+    from dl_reference_models_b200 import maps
+    from dl_reference_models_b200.batched_env import BatchedMapfEnv
+
+    grid = maps.get_grid("ReferenceModel-2-1")
+    free = np.argwhere(grid == 0).astype(np.int16)
+    env = BatchedMapfEnv({"num_agents": 4, "sensor_range": 2, "grid": grid, "step_kernel": kind}, 5, "cuda:0")
+    starts, goals = np.broadcast_to(free[:4], (5, 4, 2)).copy(), np.broadcast_to(free[10:14], (5, 4, 2)).copy()
+    env.reset(starts=starts, goals=goals)
+    assert env.poll_errors() == 0
+    bad = goals.copy()
+    bad[3, 2] = bad[3, 0]                      # env 3: agents 0 and 2 share a goal
+    env.reset(starts=starts, goals=bad)
+    with pytest.raises(ValueError, match="repeats a cell"):
+        env.raise_on_device_errors()
+    bad = starts.copy()
+    bad[1, 3] = bad[1, 1]                      # env 1: agents 1 and 3 share a start
+    env.reset(starts=bad, goals=goals)
+    with pytest.raises(ValueError, match="repeats a cell"):
+        env.raise_on_device_errors()
+    env.reset(starts=starts, goals=goals)
+    env.step(torch.zeros((5, 4), dtype=torch.int8))
+    assert env.poll_errors() == 0

@@ -194,3 +194,31 @@ def test_pageable_host_arrays(monkeypatch):
         nat.check(nat.lib().mapf_step_host(b._h, C.c_void_p(acts.ctypes.data), None, None, C.byref(cout), 1))
         for k in OUT_KEYS:
             assert np.array_equal(getattr(oa, k).cpu().numpy(), host[k]), f"step {s}: {k}"
+
+
+@pytest.mark.parametrize("sr,B", [(2, 8192 + 96), (1, 300), (3, 1000)])
+def test_records_delivery_expands_to_the_plain_arrays(sr, B):
+    """mapf_step_host_records: the four big channels arrive as bit-packed records (nothing expanded inside the call);
+    mapf_unpack_records turns them into exactly the arrays a device-side step produced, the small channels arrive as
+    plain arrays, and 13 B (sr 2) instead of 42 B per agent cross PCIe."""
+    import numpy as np
+    import torch
+
+    cfg = c3(sensor_range=sr, steps_per_episode=9)
+    a, b = make(cfg, B), make(cfg, B)
+    a.reset()
+    b.reset()
+    gen = torch.Generator().manual_seed(8)
+    for s in range(14):
+        acts = torch.randint(0, 5, (B, a.N), dtype=torch.int8, generator=gen)
+        oa = a.step(acts.cuda(), auto_reset=True)
+        rec, small = b.step_host_records(acts, auto_reset=True)
+        got = b.unpack_records(rec, threads=3)
+        for k in ("local_obs", "action_mask", "goal_delta", "reward"):
+            assert np.array_equal(getattr(oa, k).cpu().numpy(), got[k]), f"step {s}: {k}"
+        for k in ("blocking_prev", "terminated", "truncated", "step_flags", "agent_step_flags", "info"):
+            assert np.array_equal(getattr(oa, k).cpu().numpy(), small[k]), f"step {s}: {k}"
+    for k in a.state:
+        assert torch.equal(a.state[k], b.state[k]), f"state {k}"
+    rs = nat.lib().mapf_packed_record_bytes((2 * sr + 1) ** 2)
+    assert transfer_bytes(b)[1] == B * 16 * (rs + 2) + B * (3 + 64)

@@ -25,6 +25,7 @@ ap.add_argument("--sensor-range", type=int, default=2)
 ap.add_argument("--replicas", type=int, default=4)
 ap.add_argument("--no-stagger", action="store_true")
 ap.add_argument("--blocks", type=int, default=5)
+ap.add_argument("--episode-steps", type=int, default=None, help="override steps_per_episode (reset frequency experiments)")
 args = ap.parse_args()
 
 import torch  # noqa: E402
@@ -54,6 +55,8 @@ from dl_reference_models_b200.batched_env import BatchedMapfEnv  # noqa: E402
 bench.apply_shape(args)
 cfg, grid = bench.workload(args)
 cfg["grid"] = grid
+if args.episode_steps:
+    cfg["steps_per_episode"] = args.episode_steps
 dev = torch.device("cuda", 0)
 envs = [BatchedMapfEnv(cfg, args.envs, dev, env_id_base=r * args.envs) for r in range(args.replicas)]
 T = int(cfg["steps_per_episode"])
@@ -83,5 +86,5 @@ for e in envs:
 eps = sum(float(e.metrics_vector()[0]) for e in envs)
 kind = int(nat.lib().mapf_step_kernel_kind(envs[0]._h))
 print(json.dumps({"lib": os.path.basename(str(nat.LIB_PATH)), "shape": args.shape, "envs": args.envs, "agents": args.agents,
-                  "kernel": {1: "lane", 2: "env"}[kind], "us_per_step_median": sorted(times)[len(times) // 2],
+                  "kernel": {1: "lane", 2: "env"}[kind], "episode_steps": T, "us_per_step_median": sorted(times)[len(times) // 2],
                   "us_per_step_blocks": [round(t, 2) for t in times], "episodes": eps}))
