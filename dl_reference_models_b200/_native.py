@@ -16,7 +16,7 @@ PKG = Path(__file__).resolve().parent
 REPO = PKG.parent
 CSRC = PKG / "csrc"
 LIB_PATH = Path(os.environ.get("MAPF_B200_LIB", PKG / "libmapf_b200.so"))
-SOURCES = (CSRC / "mapf_b200.cu", CSRC / "mapf_kernels.cuh", CSRC / "mapf_env_kernel.cuh", CSRC / "mapf_cte_kernel.cuh", CSRC / "mapf_policy_kernel.cuh",
+SOURCES = (CSRC / "mapf_b200.cu", CSRC / "mapf_kernels.cuh", CSRC / "mapf_env_kernel.cuh", CSRC / "mapf_pair_kernel.cuh", CSRC / "mapf_cte_kernel.cuh", CSRC / "mapf_policy_kernel.cuh",
            CSRC / "mapf_pack_kernel.cuh", CSRC / "mapf_host_unpack.h", CSRC / "mapf_host_unpack.cpp",
            REPO / "include" / "mapf_b200.h")
 
@@ -254,5 +254,5 @@ def make_config(env_config: dict, rows: int, cols: int, num_envs: int, device: i
         env_id_base=int(env_id_base),
         seed=(int(seed) if seed is not None else int.from_bytes(os.urandom(8), "little")) & (2 ** 64 - 1),
         device=int(device),
-        step_kernel={'auto': 0, 'lane': 1, 'env': 2}[str(g('step_kernel', 'auto'))],
+        step_kernel={'auto': 0, 'lane': 1, 'env': 2, 'pair': 3}[str(g('step_kernel', 'auto'))],
     )

@@ -3,6 +3,7 @@
 // state/IO buffer management.  There is no CPU implementation of the transition in here: every
 // entry point that computes launches a kernel, and fails with MAPF_ERR_CUDA if it cannot.
 #include "mapf_env_kernel.cuh"
+#include "mapf_pair_kernel.cuh"
 #include "mapf_cte_kernel.cuh"
 #include "mapf_policy_kernel.cuh"
 #include "mapf_pack_kernel.cuh"
@@ -110,24 +111,47 @@ constexpr size_t kMaxSmem = 200 * 1024;
 constexpr size_t kMaxSmemEnv = 227 * 1024;  // opt-in limit of one sm_100 CTA
 
 using EnvKernelFn = void (*)(const mapf::KParams, const mapf::EnvLayout);
-template <bool VEC, bool FAST>
+template <bool VEC, bool FAST, bool MANY>
 EnvKernelFn env_step_for_sr(int sr) {
     switch (sr) {
 #ifndef MAPF_DEV_MINIMAL
-        case 1: return mapf::mapf_step_env_kernel<1, VEC, FAST>;
-        case 3: return mapf::mapf_step_env_kernel<3, VEC, FAST>;
+        case 1: return mapf::mapf_step_env_kernel<1, VEC, FAST, MANY>;
+        case 3: return mapf::mapf_step_env_kernel<3, VEC, FAST, MANY>;
 #endif
-        case 2: return mapf::mapf_step_env_kernel<2, VEC, FAST>;
+        case 2: return mapf::mapf_step_env_kernel<2, VEC, FAST, MANY>;
     }
     return nullptr;
 }
-EnvKernelFn pick_env_step(int sr, bool vec, bool fast) {
-    if (fast && vec) return env_step_for_sr<true, true>(sr);   // lifelong + lock metrics as compile-time constants
+template <bool FAST>
+EnvKernelFn pair_step_for_sr(int sr) {
+    switch (sr) {
 #ifndef MAPF_DEV_MINIMAL
-    return vec ? env_step_for_sr<true, false>(sr) : env_step_for_sr<false, false>(sr);
-#else
-    return vec ? env_step_for_sr<true, false>(sr) : nullptr;
+        case 1: return mapf::mapf_step_pair_kernel<1, FAST>;
+        case 3: return mapf::mapf_step_pair_kernel<3, FAST>;
 #endif
+        case 2: return mapf::mapf_step_pair_kernel<2, FAST>;
+    }
+    return nullptr;
+}
+EnvKernelFn pick_pair_step(int sr, bool fast) {
+#ifndef MAPF_DEV_MINIMAL
+    return fast ? pair_step_for_sr<true>(sr) : pair_step_for_sr<false>(sr);
+#else
+    return fast ? pair_step_for_sr<true>(sr) : nullptr;
+#endif
+}
+template <bool MANY>
+EnvKernelFn pick_env_step_m(int sr, bool vec, bool fast) {
+    if (fast && vec) return env_step_for_sr<true, true, MANY>(sr);   // lifelong + lock metrics as compile-time constants
+#ifndef MAPF_DEV_MINIMAL
+    return vec ? env_step_for_sr<true, false, MANY>(sr) : env_step_for_sr<false, false, MANY>(sr);
+#else
+    return vec ? env_step_for_sr<true, false, MANY>(sr) : nullptr;
+#endif
+}
+// many: the mapf_step_many instantiation (K env steps per launch)
+EnvKernelFn pick_env_step(int sr, bool vec, bool fast, bool many = false) {
+    return many ? pick_env_step_m<true>(sr, vec, fast) : pick_env_step_m<false>(sr, vec, fast);
 }
 
 }  // namespace
@@ -147,10 +171,12 @@ struct mapf_handle {
     uint64_t fused_counter;
     KernelFn step_fn, reset_fn;
     // env-per-thread step kernel (maps up to 32 columns wide, shared map); 0 threads = not available
-    EnvKernelFn env_fn;
+    EnvKernelFn env_fn, env_fn_many;   // env_fn_many: K steps per launch (mapf_step_many), null when not available
     mapf::EnvLayout env_layout;
     int env_threads, env_grid;
     bool use_env_kernel, env_pdl;
+    bool env_prefetch;  // MAPF_ENV_PREFETCH (default on): L2 prefetch of a warp's first tile ahead of griddepcontrol.wait
+    bool pair_kernel;   // the env kernel in use is the two-lanes-per-env one (mapf_pair_kernel.cuh)
     uint32_t *d_map_rows, *d_free_bits;
     uint32_t *d_env_tables;
     int32_t *d_num_free;
@@ -308,6 +334,7 @@ void fill_params(const mapf_handle *h, mapf::KParams &p) {
     p.L = h->layout;
     p.inner_steps = 1;
     p.out_step_stride = 0;
+    p.env_prefetch = h->env_prefetch ? 1 : 0;
 }
 
 void fill_outputs(mapf::KParams &p, const mapf_outputs *o) {
@@ -322,7 +349,7 @@ void fill_outputs(mapf::KParams &p, const mapf_outputs *o) {
 
 void note_user_stream(mapf_handle *h, cudaStream_t s);
 
-int launch_env_step(mapf_handle *h, const mapf::KParams &p, cudaStream_t s) {
+int launch_env_step(mapf_handle *h, const mapf::KParams &p, cudaStream_t s, EnvKernelFn fn = nullptr) {
     // launched with programmatic stream serialization: back-to-back steps overlap the next launch's ramp-up and
     // table copy with this launch's tail (the kernel waits with griddepcontrol.wait before it touches env state)
     cudaLaunchConfig_t cfg;
@@ -336,7 +363,7 @@ int launch_env_step(mapf_handle *h, const mapf::KParams &p, cudaStream_t s) {
     attr[0].val.programmaticStreamSerializationAllowed = h->env_pdl ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, h->env_fn, p, h->env_layout));
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, fn ? fn : h->env_fn, p, h->env_layout));
     h->launches++;
     return MAPF_OK;
 }
@@ -570,7 +597,7 @@ int mapf_create(const mapf_config *cfg, mapf_handle **out) {
     if (c.lock_nearby_manhattan < 1 || c.lock_nearby_manhattan > 255 || c.lock_min_neighbors < 1)
         return fail(MAPF_ERR_INVALID_ARG, "lock_nearby_manhattan / lock_min_neighbors must be >= 1");
     if (c.steps_per_episode < 1) return fail(MAPF_ERR_INVALID_ARG, "steps_per_episode must be >= 1");
-    if (c.step_kernel < 0 || c.step_kernel > 2) return fail(MAPF_ERR_INVALID_ARG, "step_kernel must be 0 (auto), 1 (lane) or 2 (env)");
+    if (c.step_kernel < 0 || c.step_kernel > 3) return fail(MAPF_ERR_INVALID_ARG, "step_kernel must be 0 (auto), 1 (lane), 2 (env) or 3 (pair)");
 
     int ndev = 0;
     cudaError_t ce = cudaGetDeviceCount(&ndev);
@@ -642,6 +669,8 @@ int mapf_create(const mapf_config *cfg, mapf_handle **out) {
     h->use_env_kernel = false;
     h->env_pdl = true;
     if (const char *ov = getenv("MAPF_ENV_PDL")) h->env_pdl = atoi(ov) != 0;
+    h->env_prefetch = true;
+    if (const char *ov = getenv("MAPF_ENV_PREFETCH")) h->env_prefetch = atoi(ov) != 0;
     if (e1 == cudaSuccess && c.cols <= 32 && c.rows <= mapf::ENV_MAX_ROWS && !c.per_env_maps) {
         const int max_warps = 14;   // __launch_bounds__ of mapf_step_env_kernel
         const int ntiles = (c.num_envs + 31) / 32;
@@ -661,11 +690,17 @@ int mapf_create(const mapf_config *cfg, mapf_handle **out) {
             bool fast = c.lifelong_mapf != 0 && c.enable_lock_metrics != 0;
             if (const char *ov = getenv("MAPF_ENV_FAST")) fast = fast && atoi(ov) != 0;
             h->env_fn = pick_env_step(h->SR, c.num_agents % 4 == 0, fast);
+            h->env_fn_many = pick_env_step(h->SR, c.num_agents % 4 == 0, fast, true);
             if (!h->env_fn) h->env_threads = 0;
         }
         if (h->env_threads) {
             e1 = cudaFuncSetAttribute(reinterpret_cast<const void *>(h->env_fn),
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmemEnv);
+            if (h->env_fn_many && cudaFuncSetAttribute(reinterpret_cast<const void *>(h->env_fn_many),
+                                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmemEnv) != cudaSuccess) {
+                cudaGetLastError();
+                h->env_fn_many = nullptr;
+            }
             const int w = h->env_threads / 32;
             int grid = (ntiles + w - 1) / w;
             if (nsm > 0 && grid > nsm) grid = nsm;  // persistent: every warp walks over env tiles
@@ -675,7 +710,46 @@ int mapf_create(const mapf_config *cfg, mapf_handle **out) {
     {
         int want_kernel = c.step_kernel;
         if (want_kernel == 0) {
-            if (const char *ov = getenv("MAPF_STEP_KERNEL")) want_kernel = (ov[0] == 'l') ? 1 : (ov[0] == 'e') ? 2 : 0;
+            if (const char *ov = getenv("MAPF_STEP_KERNEL"))
+                want_kernel = (ov[0] == 'l') ? 1 : (ov[0] == 'e') ? 2 : (ov[0] == 'p') ? 3 : 0;
+        }
+        // Two lanes per env (mapf_pair_kernel.cuh): same limits as the env-per-thread kernel, N a multiple of 4.  It takes
+        // the env kernel's place in the handle (function, layout, CTA shape); everything downstream is shared.
+        h->pair_kernel = false;
+        if (want_kernel == 3 && h->env_threads && c.num_agents % 4 == 0) {
+            const int max_warps = 28;   // __launch_bounds__ of mapf_step_pair_kernel
+            const int ntiles16 = (c.num_envs + mapf::PAIR_EPW - 1) / mapf::PAIR_EPW;
+            int want = (ntiles16 + (nsm > 0 ? nsm : 1) - 1) / (nsm > 0 ? nsm : 1);
+            if (want > max_warps) want = max_warps;
+            if (want < 1) want = 1;
+            if (const char *ov = getenv("MAPF_PAIR_WARPS")) { const int v = atoi(ov); if (v >= 1 && v <= max_warps) want = v; }
+            bool fast = c.lifelong_mapf != 0 && c.enable_lock_metrics != 0;
+            if (const char *ov = getenv("MAPF_ENV_FAST")) fast = fast && atoi(ov) != 0;
+            EnvKernelFn fn = pick_pair_step(h->SR, fast);
+            for (int w = want; fn && w >= 1; --w) {
+                mapf::EnvLayout E = mapf::make_pair_layout(c.num_agents, c.rows, c.cols, h->SR, h->fw, w);
+                if ((size_t)E.total_bytes > kMaxSmemEnv) continue;
+                if (cudaFuncSetAttribute(reinterpret_cast<const void *>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)kMaxSmemEnv) != cudaSuccess) { cudaGetLastError(); break; }
+                h->env_fn = fn;
+                h->env_fn_many = nullptr;
+                h->env_layout = E;
+                h->env_threads = 32 * w;
+                int grid = (ntiles16 + w - 1) / w;
+                if (nsm > 0 && grid > nsm) grid = nsm;
+                h->env_grid = grid;
+                h->pair_kernel = true;
+                break;
+            }
+        }
+        if (want_kernel == 3) {
+            if (!h->pair_kernel && c.step_kernel == 3) {
+                delete h;
+                return fail(MAPF_ERR_UNSUPPORTED,
+                            "pair step kernel needs cols <= 32, rows <= 64, a shared map and num_agents %% 4 == 0 (got %dx%d, %d agents)",
+                            c.rows, c.cols, c.num_agents);
+            }
+            want_kernel = h->pair_kernel ? 2 : 0;
         }
         if (c.step_kernel == 2 && !h->env_threads) {   // explicit request only; the environment variable is a preference
             delete h;
@@ -961,7 +1035,15 @@ int mapf_step_many(mapf_handle *h, const int8_t *actions, const mapf_outputs *ou
         p.out_step_stride = out_step_stride_envs;
         return launch(h, h->step_fn, p, s);
     }
-    // env-per-thread kernel (GPU-filling batches, where the launch rate is not the bound): K launches, same results
+    if (h->env_fn_many && steps > 1) {   // env-per-thread kernel: every warp takes its tile through the K steps in one launch
+        p.sample_counter = h->fused_counter;
+        h->fused_counter += (uint64_t)steps;
+        p.inner_steps = steps;
+        p.out_step_stride = out_step_stride_envs;
+        note_user_stream(h, s);
+        return launch_env_step(h, p, s, h->env_fn_many);
+    }
+    // two-lanes-per-env kernel: K launches, same results
     const int64_t N = h->cfg.num_agents;
     for (int t = 0; t < steps; ++t) {
         mapf::KParams q = p;
@@ -1548,6 +1630,6 @@ int mapf_gae(const float *rewards, const float *values, const uint8_t *dones, co
 
 int64_t mapf_launch_count(const mapf_handle *h) { return h ? h->launches : 0; }
 
-int mapf_step_kernel_kind(const mapf_handle *h) { return h ? (h->use_env_kernel ? 2 : 1) : 0; }
+int mapf_step_kernel_kind(const mapf_handle *h) { return h ? (h->use_env_kernel ? (h->pair_kernel ? 3 : 2) : 1) : 0; }
 
 }  // extern "C"

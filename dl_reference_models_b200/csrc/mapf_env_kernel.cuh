@@ -287,7 +287,11 @@ constexpr uint32_t REC_CODE = 0x7FFu;
 // One CTA of 14 warps per SM (shared memory allows no more).  The register file is split four ways (16 K registers per
 // scheduler) and two of the schedulers hold 4 of the 14 warps: 4 x 32 x 128 registers is all there is, so 128 it is
 // (144 would fit the 64 K total but not the partitions: "too many resources requested for launch").
-template <int SR, bool VEC, bool FAST = false>
+// MANY: mapf_step_many -- `p.inner_steps` consecutive env steps in ONE launch, every warp on its own tile from the first step
+// to the last (no grid-wide dependency between steps: the tail of the one-wave launch is paid once, and what a step
+// reads is what the step before just wrote, in L2).  Step it > 0 takes the actions the fused sampler drew in step
+// it - 1 and writes its outputs `p.out_step_stride` envs further into the caller's [K, B, ...] buffers.
+template <int SR, bool VEC, bool FAST = false, bool MANY = false>
 __global__ void __launch_bounds__(448, 1) mapf_step_env_kernel(const KParams p, const EnvLayout E) {
     const bool kLifelong = FAST ? true : p.lifelong;
     const bool kLock = FAST ? true : p.lock_enabled;
@@ -315,6 +319,34 @@ __global__ void __launch_bounds__(448, 1) mapf_step_env_kernel(const KParams p, 
     // table copy above (the tables are immutable between launches) while the slowest CTAs of this launch finish;
     // everything that touches env state waits here for the previous launch to complete and flush.
     asm volatile("griddepcontrol.launch_dependents;");
+    // While the previous launch drains: ask L2 for the state rows of my first tile (a hint -- L2 is the coherence point,
+    // whatever the previous launch still writes there is what the loads behind the wait will see).  With a working set
+    // beyond L2 (several env batches stepped in turn) the first loads of a warp would otherwise all miss to HBM at the
+    // same moment, with nothing to overlap them with.
+    if (p.env_prefetch) {
+        const int tile0 = blockIdx.x * (blockDim.x >> 5) + (tid >> 5);
+        const int left = p.B - tile0 * 32;
+        if (left > 0) {
+            const size_t a0 = (size_t)tile0 * 32 * (size_t)p.N;
+            const uint32_t agents = (uint32_t)(left < 32 ? left : 32) * (uint32_t)p.N;
+            const void *ptr = nullptr;
+            uint32_t bytes = agents * 4u;
+            switch (tid & 31) {
+                case 0: ptr = p.positions + a0; break;
+                case 1: ptr = p.goals + a0; break;
+                case 2: ptr = p.lock_gp + a0; break;
+                case 3: ptr = p.lock_mv + a0; break;
+                case 4: ptr = p.lock_fm + a0; break;
+                case 5: ptr = p.actions ? p.actions + a0 : nullptr; bytes = agents; break;
+                case 6: ptr = p.agent_flags + a0; bytes = agents; break;
+                case 7: ptr = p.env_words + (size_t)tile0 * 32 * 4; bytes = (uint32_t)(left < 32 ? left : 32) * 64u; break;
+                default: break;
+            }
+            bytes &= ~15u;
+            if (ptr && bytes && (reinterpret_cast<uintptr_t>(ptr) & 15) == 0)
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr), "r"(bytes) : "memory");
+        }
+    }
     asm volatile("griddepcontrol.wait;" ::: "memory");
     __syncthreads();
     const char *t1b = reinterpret_cast<const char *>(esm + ENV_T1_OFF);
@@ -355,8 +387,8 @@ __global__ void __launch_bounds__(448, 1) mapf_step_env_kernel(const KParams p, 
     // Final-state observation of agent `lane` of ONE env, the whole warp on that env (ENV:565-575 after a goal
     // reassignment, ENV:459-468 after a reset): window, mask, goal delta, pressure flag, next action -- straight to
     // global memory.  occ_e / goal_e: the env's boards (row r at [r * 32]); ctr2: my own cell belongs to another agent.
-    auto emit_final = [&](size_t abe, long long eg, const uint32_t *occ_e, const uint32_t *goal_e, uint32_t code,
-                          uint32_t gcode, uint32_t bp_bit, bool ctr2) {
+    auto emit_final = [&](size_t abe, size_t oo, unsigned long long sctr, long long eg, const uint32_t *occ_e,
+                          const uint32_t *goal_e, uint32_t code, uint32_t gcode, uint32_t bp_bit, bool ctr2) {
         if (lane >= N) return;
         const int r = (int)(code >> 5), c = (int)(code & 31u);
         const WB obst = lut[code];
@@ -387,7 +419,7 @@ __global__ void __launch_bounds__(448, 1) mapf_step_env_kernel(const KParams p, 
         const uint32_t am = 1u | ((~blk_up >> (2 + SR)) & 1u) << 1 | ((~blk_mid >> (2 + SR + 1)) & 1u) << 2 |
                             ((~blk_dn >> (2 + SR)) & 1u) << 3 | ((~blk_mid >> (2 + SR - 1)) & 1u) << 4;
         if (p.o_local_obs) {
-            uint8_t *ob = p.o_local_obs + (abe + lane) * V2;
+            uint8_t *ob = p.o_local_obs + (abe + oo + lane) * V2;
 #pragma unroll
             for (int n = 0; n < V2; ++n) ob[n] = (uint8_t)((acc[n >> 3] >> (4 * (n & 7))) & 0xFu);
             const int dr = (int)(gcode >> 5) - r + SR, dc = (int)(gcode & 31u) - c + SR;
@@ -400,15 +432,15 @@ __global__ void __launch_bounds__(448, 1) mapf_step_env_kernel(const KParams p, 
         }
         if (p.o_action_mask) {
 #pragma unroll
-            for (int k = 0; k < 5; ++k) p.o_action_mask[(abe + lane) * 5 + k] = (int8_t)((am >> k) & 1u);
+            for (int k = 0; k < 5; ++k) p.o_action_mask[(abe + oo + lane) * 5 + k] = (int8_t)((am >> k) & 1u);
         }
         if (p.o_goal_delta) {
             const int gi0 = (int)(gcode >> 5) - r + (R - 1), gi1 = (int)(gcode & 31u) - c + (C - 1) + 2 * R - 1;
-            p.o_goal_delta[abe + lane] = make_float2(gdt[gi0], gdt[gi1]);
+            p.o_goal_delta[abe + oo + lane] = make_float2(gdt[gi0], gdt[gi1]);
         }
-        if (p.o_blocking_prev) p.o_blocking_prev[abe + lane] = (uint8_t)bp_bit;
+        if (p.o_blocking_prev) p.o_blocking_prev[abe + oo + lane] = (uint8_t)bp_bit;
         if (p.sample_mode) {
-            const uint4 rnd = sample_quad(p.seed, eg, lane >> 2, p.sample_counter);
+            const uint4 rnd = sample_quad(p.seed, eg, lane >> 2, sctr);
             const uint32_t x = qget(rnd, lane & 3);
             const uint32_t na = p.sample_mode == 1 ? kth[am * 8 + __umulhi(x, (uint32_t)__popc(am))] : __umulhi(x, 5u);
             p.o_next_actions[abe + lane] = (int8_t)na;
@@ -421,6 +453,10 @@ __global__ void __launch_bounds__(448, 1) mapf_step_env_kernel(const KParams p, 
     const size_t ab = (size_t)(ok ? env : 0) * N;
     const long long env_global = p.env_id_base + env;
     const size_t env0 = (size_t)tile * 32;
+    for (int it = 0; it < (MANY ? p.inner_steps : 1); ++it) {
+    const size_t so = MANY ? (size_t)it * (size_t)p.out_step_stride : 0, oo = so * (size_t)N;   // this step's output rows
+    const unsigned long long sctr = p.sample_counter + (MANY ? (unsigned long long)it : 0ull);
+    const int8_t *acts_in = (MANY && it > 0) ? p.o_next_actions : p.actions;
 
     // ---------------------------------------------------------------- the two env words the walk needs (the rest: epilogue)
     int lock_count = 0, lock_head = 0;
@@ -478,11 +514,11 @@ __global__ void __launch_bounds__(448, 1) mapf_step_env_kernel(const KParams p, 
         const bool two = q + 1 < NQ;
         const uint4 pq0 = ldq32<VEC>(p.positions, ab + i0, i0, N, ok, 0u);
         const uint4 gq0 = ldq32<VEC>(p.goals, ab + i0, i0, N, ok, 0u);
-        const uint32_t ac0 = p.actions ? ldq8<VEC>(reinterpret_cast<const uint8_t *>(p.actions), ab + i0, i0, N, ok) : 0u;
+        const uint32_t ac0 = acts_in ? ldq8<VEC>(reinterpret_cast<const uint8_t *>(acts_in), ab + i0, i0, N, ok) : 0u;
         const uint32_t fl0 = ldq8<VEC>(p.agent_flags, ab + i0, i0, N, ok);
         const uint4 pq1 = ldq32<VEC>(p.positions, ab + i1, i1, N, ok && two, 0u);
         const uint4 gq1 = ldq32<VEC>(p.goals, ab + i1, i1, N, ok && two, 0u);
-        const uint32_t ac1 = p.actions ? ldq8<VEC>(reinterpret_cast<const uint8_t *>(p.actions), ab + i1, i1, N, ok && two) : 0u;
+        const uint32_t ac1 = acts_in ? ldq8<VEC>(reinterpret_cast<const uint8_t *>(acts_in), ab + i1, i1, N, ok && two) : 0u;
         const uint32_t fl1 = ldq8<VEC>(p.agent_flags, ab + i1, i1, N, ok && two);
         prepass_quad(i0, pq0, gq0, ac0, fl0);
         if (two) prepass_quad(i1, pq1, gq1, ac1, fl1);
@@ -522,7 +558,7 @@ __global__ void __launch_bounds__(448, 1) mapf_step_env_kernel(const KParams p, 
         uint4 gpq = gp_n, mvq = mv_n, fmq = fm_n;
         const uint2 ringq = ring_n;
         uint4 rnd = make_uint4(0, 0, 0, 0);
-        if (p.sample_mode) rnd = sample_quad(p.seed, env_global, q, p.sample_counter);
+        if (p.sample_mode) rnd = sample_quad(p.seed, env_global, q, sctr);
         uint32_t ds[4] = {0, 0, 0, 0}, cd[4] = {0, 0, 0, 0}, gc[4] = {0, 0, 0, 0};
         uint32_t masks4 = 0, next4 = 0;
         int patch[4];
@@ -713,22 +749,22 @@ __global__ void __launch_bounds__(448, 1) mapf_step_env_kernel(const KParams p, 
                     gd[k] = (VEC || i0 + k < N) ? make_float2(gdt[gi0], gdt[gi1]) : make_float2(0.f, 0.f);
                 }
                 if (VEC) {   // one 256-bit store per quad (sm_100 STG.256): half the L1 tag look-ups of two 128-bit stores
-                    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p.o_goal_delta + ab + i0),
+                    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p.o_goal_delta + ab + oo + i0),
                                  "f"(gd[0].x), "f"(gd[0].y), "f"(gd[1].x), "f"(gd[1].y), "f"(gd[2].x), "f"(gd[2].y),
                                  "f"(gd[3].x), "f"(gd[3].y) : "memory");
                 } else {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) if (i0 + k < N) p.o_goal_delta[ab + i0 + k] = gd[k];
+                    for (int k = 0; k < 4; ++k) if (i0 + k < N) p.o_goal_delta[ab + oo + i0 + k] = gd[k];
                 }
             }
-            if (p.o_blocking_prev) stq8<VEC>(p.o_blocking_prev, ab + i0, i0, N, true, spread4(bprev_m >> i0));
+            if (p.o_blocking_prev) stq8<VEC>(p.o_blocking_prev, ab + oo + i0, i0, N, true, spread4(bprev_m >> i0));
             if (p.sample_mode) stq8<VEC>(reinterpret_cast<uint8_t *>(p.o_next_actions), ab + i0, i0, N, true, next4);
         }
         // ------------------------------------------------ coalesced flush of the stage rows (one per lane)
         // row `e` holds quad q of env env0 + e: agent index (env0 + e) * N + 4 * q
         __syncwarp();
         if (VEC) {
-            const size_t agent0 = env0 * N + (size_t)i0;
+            const size_t agent0 = env0 * N + oo + (size_t)i0;
             for (int w = lane; w < OBS_W + 5; w += 32) {
                 const bool is_obs = w < OBS_W;
                 unsigned char *gp = is_obs ? (p.o_local_obs ? p.o_local_obs + agent0 * V2 + 4 * w : nullptr)
@@ -755,11 +791,11 @@ __global__ void __launch_bounds__(448, 1) mapf_step_env_kernel(const KParams p, 
                 if (!((act_w >> e) & 1u)) continue;
                 const uint8_t *src = reinterpret_cast<const uint8_t *>(stage_w + e * STRIDE);
                 if (p.o_local_obs) {
-                    uint8_t *dst = p.o_local_obs + ((env0 + e) * N + i0) * V2;
+                    uint8_t *dst = p.o_local_obs + ((env0 + e) * N + oo + i0) * V2;
                     for (int b = lane; b < na * V2; b += 32) dst[b] = src[b];
                 }
                 if (p.o_action_mask) {
-                    uint8_t *dst = reinterpret_cast<uint8_t *>(p.o_action_mask) + ((env0 + e) * N + i0) * 5;
+                    uint8_t *dst = reinterpret_cast<uint8_t *>(p.o_action_mask) + ((env0 + e) * N + oo + i0) * 5;
                     for (int b = lane; b < na * 5; b += 32) dst[b] = src[4 * OBS_W + b];
                 }
             }
@@ -800,7 +836,7 @@ __global__ void __launch_bounds__(448, 1) mapf_step_env_kernel(const KParams p, 
                 }
                 if (mvd) solo_m |= biti;                                       // ENV:525
                 else if (!(solo_m & biti) && owned_by_other && p.o_local_obs)
-                    p.o_local_obs[(ab + i) * V2 + CTR] = 2;
+                    p.o_local_obs[(ab + oo + i) * V2 + CTR] = 2;
             }
         }
         __syncwarp();
@@ -910,7 +946,7 @@ __global__ void __launch_bounds__(448, 1) mapf_step_env_kernel(const KParams p, 
                 const uint32_t code = lane < N ? (rec_e[lane * 32] & REC_CODE) : 0u;
                 const uint32_t gcode = lane < N ? code_of(p.goals[abe + lane]) : 0u;
                 const bool ctr2 = !((solo_e >> lane) & 1u) && ((occ_e[(code >> 5) * 32] >> (code & 31u)) & 1u);
-                emit_final(abe, eg, occ_e, goal_e, code, gcode, (bp_e >> lane) & 1u, ctr2);
+                emit_final(abe, oo, sctr, eg, occ_e, goal_e, code, gcode, (bp_e >> lane) & 1u, ctr2);
             }
             if (lane == e) { rng_counter += rng_inc; errs |= err_e; ongoal_m |= ongoal_fix; }
             __syncwarp();
@@ -1072,13 +1108,13 @@ __global__ void __launch_bounds__(448, 1) mapf_step_env_kernel(const KParams p, 
         }
         if (ok) {
             if (p.o_reward) {
-                if (VEC) *reinterpret_cast<float4 *>(p.o_reward + ab + i0) = make_float4(rw[0], rw[1], rw[2], rw[3]);
+                if (VEC) *reinterpret_cast<float4 *>(p.o_reward + ab + oo + i0) = make_float4(rw[0], rw[1], rw[2], rw[3]);
                 else {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) if (i0 + k < N) p.o_reward[ab + i0 + k] = rw[k];
+                    for (int k = 0; k < 4; ++k) if (i0 + k < N) p.o_reward[ab + oo + i0 + k] = rw[k];
                 }
             }
-            if (p.o_agent_step_flags) stq8<VEC>(p.o_agent_step_flags, ab + i0, i0, N, true, asf4);
+            if (p.o_agent_step_flags) stq8<VEC>(p.o_agent_step_flags, ab + oo + i0, i0, N, true, asf4);
             stq8<VEC>(p.agent_flags, ab + i0, i0, N, true, af4);
         }
     }
@@ -1087,16 +1123,16 @@ __global__ void __launch_bounds__(448, 1) mapf_step_env_kernel(const KParams p, 
     const int n_comp = __popc(completed_m), n_reach = __popc(reached_m);
     if (ok) {
         if (p.o_info) {  // integer sources of info["__all__"], ENV:639-656
-            int4 *io = p.o_info + (size_t)env * 4;
+            int4 *io = p.o_info + ((size_t)env + so) * 4;
             io[0] = make_int4(arrivals, kLifelong ? goals_total : n_reach, blocking_step, blocking_total);
             io[1] = make_int4(dl_step, ll_step, dl_event, ll_event);
             io[2] = make_int4(dl_events, ll_events, dl_steps, ll_steps);
             io[3] = make_int4(n_comp, step_count, n_reach, wfg_steps);
         }
-        if (p.o_terminated) p.o_terminated[env] = terminated;
-        if (p.o_truncated) p.o_truncated[env] = truncated;
+        if (p.o_terminated) p.o_terminated[env + so] = terminated;
+        if (p.o_truncated) p.o_truncated[env + so] = truncated;
         if (p.o_step_flags)
-            p.o_step_flags[env] = (uint8_t)((terminated ? MAPF_SF_TERMINATED : 0) | (truncated ? MAPF_SF_TRUNCATED : 0) |
+            p.o_step_flags[env + so] = (uint8_t)((terminated ? MAPF_SF_TERMINATED : 0) | (truncated ? MAPF_SF_TRUNCATED : 0) |
                                             (dl_step ? MAPF_SF_DEADLOCK_STEP : 0) | (ll_step ? MAPF_SF_LIVELOCK_STEP : 0) |
                                             (dl_event ? MAPF_SF_DEADLOCK_EVENT : 0) | (ll_event ? MAPF_SF_LIVELOCK_EVENT : 0) |
                                             (reassigned ? MAPF_SF_GOAL_REASSIGNED : 0) | (wf_any ? MAPF_SF_WFG_CYCLE : 0));
@@ -1198,7 +1234,7 @@ __global__ void __launch_bounds__(448, 1) mapf_step_env_kernel(const KParams p, 
                 atomicOr(&goal_e[(gg >> 5) * 32], 1u << (gg & 31u));
             }
             __syncwarp();
-            emit_final(abe, eg, occ_e, goal_e, st, gg, 0u, false);
+            emit_final(abe, oo, sctr, eg, occ_e, goal_e, st, gg, 0u, false);
             if (lane == e) {
                 rng_counter += rounds; errs |= err_e;
                 step_count = 0; lock_count = 0; lock_head = 0; lock_prev = 0; goals_total = 0; blocking_total = 0;
@@ -1217,6 +1253,7 @@ __global__ void __launch_bounds__(448, 1) mapf_step_env_kernel(const KParams p, 
         ew4[3] = make_int4(episodes, lock_head, w3.z, w3.w);
     }
     __syncwarp();
+    }  // inner steps
     }  // tile loop
     errs = __reduce_or_sync(full, errs);
     if (errs && lane == 0) atomicOr(p.err_bits, errs);

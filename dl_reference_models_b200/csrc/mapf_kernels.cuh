@@ -142,6 +142,7 @@ struct KParams {
     int4 *o_info;  // [B, 4] int4 = MAPF_INFO_WORDS int32
     int8_t *o_next_actions;  // fused benchmark sampler (scripts/benchmark_multi_agent_env.py:38-57)
     int sample_mode;         // 0 off, 1 uniform over the new action mask, 2 uniform over 0..4
+    int env_prefetch;        // env-per-thread step kernel: L2 prefetch of the first tile's state ahead of griddepcontrol.wait
     int inner_steps;         // lane-per-agent step kernel: env steps per launch (mapf_step_many), >= 1
     long long out_step_stride;   // ... and how many envs further each of them writes its outputs
     unsigned long long sample_counter;

@@ -70,7 +70,7 @@ typedef struct mapf_config {
     int64_t env_id_base;     /* global id of env 0 (Philox key => results independent of sharding) */
     uint64_t seed;           /* ENV:74 */
     int32_t device;          /* CUDA device ordinal */
-    int32_t step_kernel;     /* 0 auto, 1 lane-per-agent kernel, 2 env-per-thread kernel (cols <= 32, shared map) */
+    int32_t step_kernel;     /* 0 auto, 1 lane-per-agent kernel, 2 env-per-thread kernel (cols <= 32, shared map), 3 two lanes per env (same limits, num_agents % 4 == 0) */
 } mapf_config;
 
 /* Words of the per-env int32 state block env_words[B, MAPF_ENV_WORDS]. */

@@ -79,7 +79,7 @@ def _replay(cfg, grid, B, steps, kind, fast, env_id_base=0, masked=True):
     return episodes, arrivals
 
 
-@pytest.mark.parametrize("kind", ["env", "lane"])
+@pytest.mark.parametrize("kind", ["env", "lane", "pair"])
 @pytest.mark.parametrize("fast", [True, False])
 def test_c3_philox_autoreset_fused_sampler(kind, fast):
     """BASELINE config 3 as benchmarked (32x32, 16 agents, lifelong, lock metrics, masked sampler), 4 096 envs x 320

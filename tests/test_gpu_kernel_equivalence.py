@@ -17,7 +17,7 @@ def make(cfg, B, kind, **kw):
     from dl_reference_models_b200.batched_env import BatchedMapfEnv
 
     env = BatchedMapfEnv(dict(cfg, step_kernel=kind), B, "cuda:0", **kw)
-    assert nat.lib().mapf_step_kernel_kind(env._h) == {"lane": 1, "env": 2}[kind]
+    assert nat.lib().mapf_step_kernel_kind(env._h) == {"lane": 1, "env": 2, "pair": 3}[kind]
     return env
 
 
@@ -34,10 +34,10 @@ def assert_same(a, b, oa, ob, ctx):
         assert torch.equal(x, y), f"{ctx}: output {k} differs at {torch.nonzero(x != y)[:4].tolist()}"
 
 
-def run_pair(cfg, B, steps, masked=True, auto_reset=True, fused=True):
+def run_pair(cfg, B, steps, masked=True, auto_reset=True, fused=True, kinds=("lane", "env")):
     import torch
 
-    a, b = make(cfg, B, "lane"), make(cfg, B, "env")
+    a, b = make(cfg, B, kinds[0]), make(cfg, B, kinds[1])
     oa, ob = a.reset(), b.reset()
     assert_same(a, b, oa, ob, "reset")
     acts_a = a.sample_actions(masked=masked)
@@ -190,11 +190,95 @@ def test_full_quads_other_agent_counts(n):
     run_pair(c3(num_agents=n, steps_per_episode=30, lifelong_mapf=False), 512 + 3, 70, masked=False)
 
 
-@pytest.mark.parametrize("kind,B,n", [("lane", 4096, 4), ("lane", 300, 16), ("env", 2048, 8)])
+def test_two_lanes_per_env_kernel_equals_the_other_two():
+    """step_kernel="pair" (mapf_pair_kernel.cuh: two lanes per env, the moves of a quad serialised half by half, shared
+    64-bit owner boards): the same function as the env-per-thread and the lane-per-agent kernels -- lifelong and
+    episodic, 1 to 8 quads per env, every sensor range, both instantiations, corridors with lock events, injected
+    invalid / NULL actions on a tall map."""
+    import torch
+
+    from dl_reference_models_b200 import maps
+
+    a, _ = run_pair(c3(), 4096 + 7, 100, kinds=("env", "pair"))
+    assert int(a.state["env_words"][:, nat.W_EPISODES].min()) == 2
+    for n in (4, 8, 12):
+        run_pair(c3(num_agents=n, steps_per_episode=30), 1024 + 9, 70, kinds=("env", "pair"))
+        run_pair(c3(num_agents=n, steps_per_episode=30, lifelong_mapf=False), 512 + 3, 70, masked=False, kinds=("lane", "pair"))
+    for sr in (1, 3):
+        run_pair(c3(sensor_range=sr, steps_per_episode=25), 700, 60, kinds=("env", "pair"))
+    cfg = {"num_agents": 32, "sensor_range": 2, "steps_per_episode": 256, "lifelong_mapf": False, "seed": 77,
+           "deadlock_window_steps": 8, "livelock_window_steps": 16, "grid": maps.corridor_grid(32, 32)}
+    run_pair(cfg, 256, 300, masked=False, kinds=("lane", "pair"))
+    cfg = c3(num_agents=32, grid=maps.random_obstacle_grid(12, 12, 0.15, 7, min_free=80), steps_per_episode=50)
+    run_pair(cfg, 1000, 120, masked=False, kinds=("env", "pair"))
+    for name, n in (("ReferenceModel-1-4", 4), ("ReferenceModel-3-1", 8)):
+        cfg = {"env_name": name, "num_agents": n, "sensor_range": 2, "steps_per_episode": 60, "lifelong_mapf": True,
+               "deadlock_window_steps": 2, "livelock_window_steps": 4, "lock_nearby_manhattan": 3, "seed": 5}
+        run_pair(cfg, 200, 150, masked=False, kinds=("lane", "pair"))
+    grid = maps.random_obstacle_grid(48, 32, 0.25, 11, min_free=200)
+    cfg = {"num_agents": 32, "sensor_range": 3, "steps_per_episode": 20, "lifelong_mapf": True, "seed": 3, "grid": grid}
+    a, b = make(cfg, 257, "env"), make(cfg, 257, "pair")
+    oa, ob = a.reset(), b.reset()
+    gen = torch.Generator().manual_seed(0)
+    for s in range(40):
+        if s % 7 == 3:
+            oa, ob = a.step(None, auto_reset=True), b.step(None, auto_reset=True)
+        else:
+            acts = torch.randint(-2 if s % 11 == 5 else 0, 7 if s % 11 == 5 else 5, (257, 32), dtype=torch.int8, generator=gen)
+            oa, ob = a.step(acts, auto_reset=True), b.step(acts, auto_reset=True)
+        assert_same(a, b, oa, ob, f"step {s}")
+    assert a.poll_errors() == b.poll_errors()
+
+
+@pytest.mark.parametrize("lifelong", [False, True])
+def test_pair_kernel_injected_colocation_equals_env_kernel(lifelong):
+    """States no legal step produces (several agents on one cell, ENV:658-666): the env-per-thread kernel replays the
+    live reference's traces of such states (tests/test_gpu_colocation.py); the two-lanes-per-env kernel keeps the same
+    owner-grid semantics -- same penalties, same centre cells, same NOT_OWNER flags, moving co-located agents included."""
+    import torch
+
+    from dl_reference_models_b200 import maps
+
+    B, n = 300, 8
+    cfg = {"num_agents": n, "sensor_range": 2, "steps_per_episode": 12, "lifelong_mapf": lifelong, "seed": 9,
+           "deadlock_window_steps": 2, "livelock_window_steps": 4, "grid": maps.random_obstacle_grid(9, 11, 0.2, 3, min_free=40)}
+    a, b = make(cfg, B, "env"), make(cfg, B, "pair")
+    a.reset(); b.reset()
+    gen = torch.Generator().manual_seed(1)
+    st = a.get_state()
+    pos = st["positions"].cpu().clone()
+    src = torch.randint(0, n, (B, 3), generator=gen)
+    dst = torch.randint(0, n, (B, 3), generator=gen)
+    for j in range(3):   # agent dst[b, j] is put on the cell of agent src[b, j]: pairs, triples and chains across both halves
+        idx = torch.arange(B)
+        pos[idx, dst[:, j]] = pos[idx, src[:, j]].clone()
+    st["positions"] = pos
+    a.set_state(st)
+    b.set_state({k: v.clone() for k, v in st.items()})
+    for s in range(10):
+        acts = torch.randint(0, 5, (B, n), dtype=torch.int8, generator=gen)
+        oa, ob = a.step(acts, auto_reset=False), b.step(acts, auto_reset=False)
+        assert_same(a, b, oa, ob, f"step {s}")
+    assert float(oa.reward.min()) <= 0.0
+
+
+def test_pair_kernel_generic_instantiation(monkeypatch):
+    monkeypatch.setenv("MAPF_ENV_FAST", "0")
+    run_pair(c3(steps_per_episode=25), 2048 + 5, 60, kinds=("env", "pair"))
+
+
+def test_pair_kernel_needs_full_quads():
+    with pytest.raises(Exception):
+        make(c3(num_agents=5), 64, "pair")
+
+
+@pytest.mark.parametrize("kind,B,n", [("lane", 4096, 4), ("lane", 300, 16), ("env", 2048, 8), ("env", 4096 + 33, 16),
+                                      ("env", 515, 5), ("pair", 1024, 16)])
 def test_step_many_equals_single_steps(kind, B, n):
-    """mapf_step_many: K env steps with the fused sampler's actions in ONE launch (lane-per-agent kernel; K launches
-    behind the same call for the env-per-thread kernel) -- every output row of every step and the state afterwards
-    equal K single mapf_step calls, bit for bit, across in-launch resets."""
+    """mapf_step_many: K env steps with the fused sampler's actions in ONE launch (both the lane-per-agent and the
+    env-per-thread kernel -- every warp takes its tile through the K steps; K launches behind the same call for the
+    two-lanes-per-env kernel) -- every output row of every step and the state afterwards equal K single mapf_step
+    calls, bit for bit, across in-launch resets."""
     import torch
 
     K = 24

@@ -25,6 +25,7 @@ ap.add_argument("--sensor-range", type=int, default=2)
 ap.add_argument("--replicas", type=int, default=4)
 ap.add_argument("--no-stagger", action="store_true")
 ap.add_argument("--blocks", type=int, default=5)
+ap.add_argument("--inner", type=int, default=1, help="env steps per launch (mapf_step_many, rollout buffers [K, ...])")
 ap.add_argument("--episode-steps", type=int, default=None, help="override steps_per_episode (reset frequency experiments)")
 args = ap.parse_args()
 
@@ -70,21 +71,30 @@ for e in envs:
 for i in range(args.burn * len(envs)):
     e = envs[i % len(envs)]
     e.step(e._next, auto_reset=True)
+if args.inner > 1:
+    for e in envs:
+        e._roll = e.rollout_buffers(args.inner)
 torch.cuda.synchronize()
 times = []
 for b in range(args.blocks):
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
-    for i in range(args.steps):
-        e = envs[i % len(envs)]
-        e.step(e._next, auto_reset=True)
+    if args.inner > 1:
+        for i in range(max(1, args.steps // args.inner)):
+            e = envs[i % len(envs)]
+            e.step_many(args.inner, out=e._roll)
+    else:
+        for i in range(args.steps):
+            e = envs[i % len(envs)]
+            e.step(e._next, auto_reset=True)
     t1.record()
     torch.cuda.synchronize()
-    times.append(t0.elapsed_time(t1) * 1e3 / args.steps)
+    nsteps = max(1, args.steps // args.inner) * args.inner if args.inner > 1 else args.steps
+    times.append(t0.elapsed_time(t1) * 1e3 / nsteps)
 for e in envs:
     e.raise_on_device_errors()
 eps = sum(float(e.metrics_vector()[0]) for e in envs)
 kind = int(nat.lib().mapf_step_kernel_kind(envs[0]._h))
 print(json.dumps({"lib": os.path.basename(str(nat.LIB_PATH)), "shape": args.shape, "envs": args.envs, "agents": args.agents,
-                  "kernel": {1: "lane", 2: "env"}[kind], "episode_steps": T, "us_per_step_median": sorted(times)[len(times) // 2],
+                  "kernel": {1: "lane", 2: "env", 3: "pair"}[kind], "episode_steps": T, "inner": args.inner, "us_per_step_median": sorted(times)[len(times) // 2],
                   "us_per_step_blocks": [round(t, 2) for t in times], "episodes": eps}))
