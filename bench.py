@@ -41,6 +41,8 @@ UNIT = "agent-steps/s"
 def kernel_name(kind: int, num_agents: int, sensor_range: int) -> str:
     if kind == 2:
         return f"mapf_step_env_kernel<{sensor_range},...> (env-per-thread)"
+    if kind == 3:
+        return f"mapf_step_pair_kernel<{sensor_range},...> (two lanes per env)"
     g = 4 if num_agents <= 4 else 8 if num_agents <= 8 else 16 if num_agents <= 16 else 32
     return f"mapf_step_kernel<{g},{sensor_range},...> (lane-per-agent)"
 
@@ -258,7 +260,7 @@ def committed_traffic(shape: str, kind: int):
         t = json.loads(f.read_text())
     except Exception as exc:
         return None, f"profiles/traffic.json unreadable: {exc}"
-    key = f"{shape}_{ {1: 'lane', 2: 'env'}.get(kind) }"
+    key = f"{shape}_{ {1: 'lane', 2: 'env', 3: 'pair'}.get(kind) }"
     ent = t.get(key)
     if not ent:
         return None, f"no capture for {key} in profiles/traffic.json"
@@ -471,6 +473,32 @@ def run_b200(args, rank: int, local_rank: int, world: int):
     kernel_ms = block_ms_max / K
     metrics, allreduce_check = reduced_metrics(sb)
 
+    # ------------------------------------------------------------------ the same batches through mapf_step_many: K steps per launch
+    # (fused-sampler rollouts: every warp takes its tile through the K steps, each step's outputs go to its own rows
+    # of a [K, B, ...] rollout buffer -- K x 45 MB of outputs per launch and replica, nothing kept in L2 between launches)
+    many = None
+    if not args.no_extra_shapes and sb.kind == 2:
+        Km = 16
+        for e in sb.envs:
+            e._roll = e.rollout_buffers(Km)
+        mi = [0]
+
+        def many_step():
+            e = sb.envs[mi[0] % len(sb.envs)]
+            mi[0] += 1
+            e.step_many(Km, out=e._roll)
+
+        for _ in range(len(sb.envs)):
+            many_step()
+        mblocks, _, _ = timed_blocks(many_step, 4, min(args.min_seconds, 0.2), barrier, torch)
+        sb.check()
+        many_ms = reduce_max(float(np.median(mblocks))) / (4 * Km)
+        many = {"steps_per_launch": Km, "ms_per_step": many_ms, "value": world * B * N / (many_ms * 1e-3), "unit": UNIT,
+                "api": "mapf_step_many (K env steps per kernel launch, fused masked sampler, [K, B, ...] rollout buffers)"}
+        for e in sb.envs:
+            del e._roll
+        torch.cuda.empty_cache()
+
     # ------------------------------------------------------------------ e2e: the C ABI's host-buffer entry point
     e2e_env = sb.envs[0]
     e2e_env.fuse_sampler(None)
@@ -590,8 +618,13 @@ def run_b200(args, rank: int, local_rank: int, world: int):
                             "pcie_floor_ms": (rec_d2h / 1e9) / max(ceil["d2h_gbs"] / world, 1e-9) * 1e3 +
                                              (rec_h2d / 1e9) / max(ceil["h2d_gbs"] / world, 1e-9) * 1e3,
                             "checksum": rec_checksum},
+            "step_many": (dict(many, roofline={"bound": "hbm", "achieved": alg_bytes / (many["ms_per_step"] * 1e-3) / 1e9,
+                                                "peak": peak, "unit": "GB/s",
+                                                "frac": alg_bytes / (many["ms_per_step"] * 1e-3) / 1e9 / peak,
+                                                "kernel": kernel_name(sb.kind, N, args.sensor_range) + " (K steps per launch)"})
+                          if many else None),
             "gpu_launches": int(reduce_sum(launches) if world > 1 else launches), "clocks": clocks,
-            "step_kernel": {1: "lane", 2: "env"}.get(sb.kind),
+            "step_kernel": {1: "lane", 2: "env", 3: "pair"}.get(sb.kind),
             "episode_metrics": {k: metrics[k] for k in ("episodes", "goals_reached_mean", "deadlock_steps_mean",
                                                         "livelock_steps_mean", "throughput_mean", "length_mean")},
             "allreduce_check": allreduce_check,
@@ -643,7 +676,7 @@ def extra_shapes(args, dev, rank, world, barrier, reduce_max, torch, dist) -> di
     if rank == 0:
         ach = bpa * sb.B * sb.N / (ms / steps * 1e-3) / 1e9
         out["c4"] = {"workload": config_dict(sb.args, world)["workload"], "value": world * sb.B * sb.N * steps / (ms * 1e-3),
-                     "unit": UNIT, "ms_per_step": ms / steps, "steps": steps, "step_kernel": {1: "lane", 2: "env"}.get(sb.kind),
+                     "unit": UNIT, "ms_per_step": ms / steps, "steps": steps, "step_kernel": {1: "lane", 2: "env", 3: "pair"}.get(sb.kind),
                      "metric_allreduces_during_stepping": len(reports), "allreduce_every_steps": every,
                      "episodes_reported": [r["episodes"] for r in reports],
                      "deadlock_steps_mean": reports[-1]["deadlock_steps_mean"], "livelock_steps_mean": reports[-1]["livelock_steps_mean"],
@@ -675,7 +708,7 @@ def extra_shapes(args, dev, rank, world, barrier, reduce_max, torch, dist) -> di
                      "value": world * sb.B * sb.N / (res["many"] * 1e-3), "ms_per_step": res["many"],
                      "one_launch_per_step": world * sb.B * sb.N / (res["single"] * 1e-3), "ms_per_step_one_launch_per_step": res["single"],
                      "steps_per_launch": Kc, "api": "mapf_step_many (K env steps per kernel launch, fused masked sampler)",
-                     "step_kernel": {1: "lane", 2: "env"}.get(sb.kind),
+                     "step_kernel": {1: "lane", 2: "env", 3: "pair"}.get(sb.kind),
                      "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                                   "bytes_per_agent_step": bpa, "kernel": kernel_name(sb.kind, sb.N, args.sensor_range),
                                   "note": "4 096 envs x 4 agents: 1.6 MB per step, launch-latency bound, not bandwidth bound"}}
