@@ -687,7 +687,9 @@ int mapf_create(const mapf_config *cfg, mapf_handle **out) {
             }
         }
         if (h->env_threads) {
-            bool fast = c.lifelong_mapf != 0 && c.enable_lock_metrics != 0;
+            // FAST: lifelong + lock metrics as compile-time constants, and at most 16 agents (its epilogue keeps the row and
+            // the column owner masks in the two halves of one word)
+            bool fast = c.lifelong_mapf != 0 && c.enable_lock_metrics != 0 && c.num_agents <= 16;
             if (const char *ov = getenv("MAPF_ENV_FAST")) fast = fast && atoi(ov) != 0;
             h->env_fn = pick_env_step(h->SR, c.num_agents % 4 == 0, fast);
             h->env_fn_many = pick_env_step(h->SR, c.num_agents % 4 == 0, fast, true);

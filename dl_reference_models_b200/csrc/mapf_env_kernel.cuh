@@ -957,46 +957,78 @@ __global__ void __launch_bounds__(448, 1) mapf_step_env_kernel(const KParams p, 
     // The boards are dead: rowm[r + PADR] / colm[c + PADR] get bit a for agent a's final row / column
     // (PADR zero rows on both sides).
     __syncwarp();
-    for (int r = 0; r < E.board_rows; ++r) { occ[r * 32] = 0u; goalb[r * 32] = 0u; }
-    if (ok) {
+    // PK (the FAST instantiation, N <= 16): both masks share one word -- low half rows, high half columns -- in the goal
+    // board's memory, and the occupancy board stays alive for a cheap pre-test: an agent with nobody within Manhattan
+    // distance 2 on the final board and no failed move has nothing to do below (no neighbour set, no owner to look
+    // up), and that is most agents -- the loop then runs over the few that do, not over all N.
+    constexpr bool PK = FAST;
+    uint32_t todo = ok ? allN : 0u;
+    if (PK) {
+        for (int r = 0; r < E.board_rows; ++r) goalb[r * 32] = 0u;
+        uint32_t near_m = 0;
+        if (ok) {
 #pragma unroll 1
-        for (int i = 0; i < N; ++i) {
-            const uint32_t code = rec[i * 32] & REC_CODE;
-            atomicOr(&rowm[((code >> 5) + PADR) * 32], 1u << i);   // reductions without a return value: no dependent chain
-            atomicOr(&colm[((code & 31u) + PADR) * 32], 1u << i);
+            for (int i = 0; i < N; ++i) {
+                const uint32_t code = rec[i * 32] & REC_CODE;
+                const int r = (int)(code >> 5);
+                atomicOr(&goalb[(r + PADR) * 32], 1u << i);
+                atomicOr(&goalb[((code & 31u) + PADR) * 32], 0x10000u << i);
+                // rows above the map read neighbouring shared memory: a false "near" costs a look below, never a result
+                const uint32_t *orow = &occ[(r - 2) * 32];
+                const uint32_t b = 1u << (code & 31u);
+                const uint32_t m1 = (b << 1) | (b >> 1), mB = m1 | b, mA = m1 | (b << 2) | (b >> 2);
+                const uint32_t nr = (orow[64] & mA) | ((orow[32] | orow[96]) & mB) | ((orow[0] | orow[128]) & b);
+                near_m |= nr ? (1u << i) : 0u;
+            }
+        }
+        todo = (p.nearby == 2 && !degen && reached_m == 0u) ? (near_m | failed_m) & todo : todo;
+    } else {
+        for (int r = 0; r < E.board_rows; ++r) { occ[r * 32] = 0u; goalb[r * 32] = 0u; }
+        if (ok) {
+#pragma unroll 1
+            for (int i = 0; i < N; ++i) {
+                const uint32_t code = rec[i * 32] & REC_CODE;
+                atomicOr(&rowm[((code >> 5) + PADR) * 32], 1u << i);   // reductions without a return value: no dependent chain
+                atomicOr(&colm[((code & 31u) + PADR) * 32], 1u << i);
+            }
         }
     }
+    // agents of row / column idx (idx already padded)
+    auto rowset = [&](int idx) -> uint32_t { return PK ? (goalb[idx * 32] & 0xFFFFu) : rowm[idx * 32]; };
+    auto colset = [&](int idx) -> uint32_t { return PK ? (goalb[idx * 32] >> 16) : colm[idx * 32]; };
     uint32_t coloc_any = 0, wf_alive = 0, flags_any = 0;   // flags_any: bit 0 deadlock, bit 1 livelock participant set found
     uint32_t wf_m = 0, blocking_m = 0;
     const uint32_t intent_m = allN & ~reached_m;  // ENV:619-621: only agents that have not (sticky-)reached press
     // a rolled loop on purpose: the launch is one pass over the code per warp, the instruction cache is a
     // contended resource (stall_no_inst was 18 % with this loop unrolled by four)
 #pragma unroll 1
-    for (int i = 0; i < (ok ? N : 0); ++i) {
+    while (todo) {
+        const int i = __ffs(todo) - 1;
+        todo &= todo - 1;
         const uint32_t bit = 1u << i;
         const uint32_t rv = rec[i * 32];
         const uint32_t code = rv & REC_CODE;
         const int r = (int)(code >> 5), c = (int)(code & 31u);
-        const uint32_t *prow_ = &rowm[(r + PADR) * 32], *pcol_ = &colm[(c + PADR) * 32];
-        const uint32_t here = *prow_ & *pcol_;   // agents on my cell (me included)
+        const int pr = r + PADR, pc = c + PADR;
+        const uint32_t row0 = rowset(pr), col0 = colset(pc);
+        const uint32_t here = row0 & col0;   // agents on my cell (me included)
         if (here & ~bit) coloc_any |= bit;
         // ENV:389-438 neighbours within Manhattan distance `nearby`, via the row / column masks
         if (kLock && !(ongoal_m & bit)) {
             uint32_t nb = 0;
             if (p.nearby == 2) {
-                const uint32_t c0 = *pcol_;
-                const uint32_t c1 = c0 | pcol_[-32] | pcol_[32];
-                const uint32_t c2 = c1 | pcol_[-64] | pcol_[64];
-                nb = (*prow_ & c2) | ((prow_[-32] | prow_[32]) & c1) | ((prow_[-64] | prow_[64]) & c0);
+                const uint32_t c1 = col0 | colset(pc - 1) | colset(pc + 1);
+                const uint32_t c2 = c1 | colset(pc - 2) | colset(pc + 2);
+                nb = (row0 & c2) | ((rowset(pr - 1) | rowset(pr + 1)) & c1) | ((rowset(pr - 2) | rowset(pr + 2)) & col0);
             } else {
                 uint32_t u = 0;
                 for (int w = 0; w <= p.nearby; ++w) {
                     const int dd = p.nearby - w;
-                    if (c - w >= 0) u |= pcol_[-w * 32];
-                    if (c + w < C) u |= pcol_[w * 32];
+                    if (c - w >= 0) u |= colset(pc - w);
+                    if (c + w < C) u |= colset(pc + w);
                     uint32_t rm = 0;
-                    if (r - dd >= 0) rm |= prow_[-dd * 32];
-                    if (r + dd < R) rm |= prow_[dd * 32];
+                    if (r - dd >= 0) rm |= rowset(pr - dd);
+                    if (r + dd < R) rm |= rowset(pr + dd);
                     nb |= rm & u;
                 }
             }
@@ -1025,7 +1057,7 @@ __global__ void __launch_bounds__(448, 1) mapf_step_env_kernel(const KParams p, 
             owner = 0;
             if (!(rv & 0x4000u) && (reached_m != 0u || (failed_m & bit))) {
                 const uint32_t tcode = code + (uint32_t)action_delta((rv >> 11) & 7u);
-                owner = rowm[((tcode >> 5) + PADR) * 32] & colm[((tcode & 31u) + PADR) * 32] & ~bit;
+                owner = rowset((int)(tcode >> 5) + PADR) & colset((int)(tcode & 31u) + PADR) & ~bit;
             }
         }
         if (intent_m & bit) blocking_m |= owner;   // ENV:609-623 (filtered below)
@@ -1100,7 +1132,7 @@ __global__ void __launch_bounds__(448, 1) mapf_step_env_kernel(const KParams p, 
             int rx2 = (int)((pos4 >> (8 * k)) & 0xFFu) - (int)((neg4 >> (8 * k)) & 0xFFu);
             if ((coloc_any >> (i0 + k)) & 1u) {   // ENV:658-666, -1 per co-located pair member (injected states only)
                 const uint32_t code = rec[(i0 + k) * 32] & REC_CODE;
-                const int others = __popc(rowm[((code >> 5) + PADR) * 32] & colm[((code & 31u) + PADR) * 32]) - 1;
+                const int others = __popc(rowset((int)(code >> 5) + PADR) & colset((int)(code & 31u) + PADR)) - 1;
                 rx2 -= 2 * others;
                 coloc_pairs2 += 2u * (uint32_t)others;
             }

@@ -19,7 +19,7 @@ OUT_KEYS = ("local_obs", "action_mask", "goal_delta", "blocking_prev", "reward",
 cfg = {"num_agents": NA, "sensor_range": 2, "steps_per_episode": 20, "lifelong_mapf": True, "seed": 4242,
        "grid": maps.random_obstacle_grid(32, 32, 0.30, 2026, min_free=32)}
 a = BatchedMapfEnv(dict(cfg, step_kernel=REF), B, "cuda:0")
-b = BatchedMapfEnv(dict(cfg, step_kernel="pair"), B, "cuda:0")
+b = BatchedMapfEnv(dict(cfg, step_kernel=__import__("os").environ.get("DBG_KIND", "pair")), B, "cuda:0")
 print("kinds", nat.lib().mapf_step_kernel_kind(a._h), nat.lib().mapf_step_kernel_kind(b._h))
 oa, ob = a.reset(), b.reset()
 acts_a = a.sample_actions(masked=True)
