@@ -11,8 +11,11 @@ the blocking / move-after-goal penalties (CTE:92-93).
   four counters), same attributes (``positions`` / ``starts`` / ``goals`` dicts of arrays, ``step_count``,
   ``goal_reached_once``, ``grid``, ``seed``, ``rng``, ``_obs_slices`` ...).
 
-Layout draws (CTE:155-185) stay on the host with a ``numpy.random.Generator`` exactly like the reference, so a seeded
-B = 1 env reproduces the reference's episodes bit for bit.  The transition always runs on the GPU (no CPU fallback).
+Layout draws (CTE:155-185): ``rng_backend="numpy"`` (the default of a B = 1 env) keeps them on the host with a
+``numpy.random.Generator`` exactly like the reference, so a seeded B = 1 env reproduces the reference's episodes bit
+for bit; ``rng_backend="device"`` (the default for B > 1) draws them on the GPU -- the multi-agent reset kernel's Philox
+layout draw, distributionally the same 2N distinct free cells -- so that resets, and ``step(..., auto_reset=True)``,
+of a big batch never touch the host.  The transition always runs on the GPU (no CPU fallback).
 """
 from __future__ import annotations
 
@@ -64,6 +67,10 @@ class BatchedCteEnv:
         self.steps_per_episode = int(g("steps_per_episode", 100))
         self.deterministic = bool(g("deterministic", False))
         self.seed = g("seed", None)
+        self.rng_backend = str(g("rng_backend", "numpy" if int(num_envs) == 1 else "device"))
+        if self.rng_backend not in ("numpy", "device"):
+            raise ValueError("rng_backend must be 'numpy' or 'device'")
+        self._layout_env = None
         self.D = self.R * self.C + 5 * self.N
         dev = self.device
         z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=dev)  # noqa: E731
@@ -85,9 +92,18 @@ class BatchedCteEnv:
             action_mask=self.action_mask.data_ptr(), flat_obs=self.flat_obs.data_ptr(), reward=self.reward.data_ptr(),
             terminated=self.terminated.data_ptr(), truncated=self.truncated.data_ptr(), info=self.info.data_ptr(),
             err_bits=self._err.data_ptr(), reset_mask=None)
-        # one numpy Generator per env: env 0 is seeded like the reference (default_rng(seed), CTE:97-101)
+        # numpy backend: one Generator per env, env 0 seeded like the reference (default_rng(seed), CTE:97-101)
+        nrng = B if self.rng_backend == "numpy" else 1
         self._rngs = [np.random.default_rng(None if self.seed is None else (self.seed if e == 0 else [int(self.seed), e]))
-                      for e in range(B)]
+                      for e in range(nrng)]
+        if self.rng_backend == "device" and not self.deterministic:
+            # the layout source: a multi-agent handle of the same map / agent count whose masked reset draws 2N distinct
+            # free cells per env with Philox (mapf_reset_kernel); only its starts / goals tensors are used
+            from .batched_env import BatchedMapfEnv
+
+            self._layout_env = BatchedMapfEnv({"grid": self.grid, "num_agents": N, "sensor_range": 1,
+                                               "seed": 0 if self.seed is None else int(self.seed),
+                                               "enable_lock_metrics": False}, B, dev)
         if self.deterministic:
             name = self.env_config["env_name"]
             sp, gp = maps.get_start_positions(name, N), maps.get_goal_positions(name, N)
@@ -96,13 +112,26 @@ class BatchedCteEnv:
             self.starts.copy_(torch.from_numpy(np.broadcast_to(st, (B, N, 2)).copy()))
             self.goals.copy_(torch.from_numpy(np.broadcast_to(gl, (B, N, 2)).copy()))
         else:
-            self._draw(np.arange(B))   # the reference draws once in the constructor (CTE:112) ...
+            self._draw(None)   # the reference draws once in the constructor (CTE:112) ...
         self.positions.copy_(self.starts)
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
-    def _draw(self, env_ids):
+    def _draw(self, mask):
+        """New layouts for the envs of ``mask`` (uint8 [B] device tensor; None = all)."""
+        if self._layout_env is not None:
+            le = self._layout_env
+            le.reset(mask=mask)
+            if mask is None:
+                self.starts.copy_(le.state["starts"])
+                self.goals.copy_(le.state["goals"])
+            else:
+                m = mask.bool().view(self.B, 1, 1)
+                torch.where(m, le.state["starts"], self.starts, out=self.starts)
+                torch.where(m, le.state["goals"], self.goals, out=self.goals)
+            return
+        env_ids = np.arange(self.B) if mask is None else np.flatnonzero(mask.cpu().numpy())
         st = self.starts.cpu().numpy()
         gl = self.goals.cpu().numpy()
         for e in env_ids:
@@ -113,28 +142,32 @@ class BatchedCteEnv:
     def reset(self, mask=None, starts=None, goals=None):
         """CTE:218-235 for the selected envs (uint8 [B] mask, None = all).  Deterministic envs go back to their
         starts, the others draw a fresh layout (... and again on every reset, CTE:227); ``starts`` / ``goals``
-        (int16 [B,N,2]) install a given layout instead."""
-        sel = np.arange(self.B) if mask is None else np.flatnonzero(torch.as_tensor(mask).cpu().numpy())
+        (int16 [B,N,2]) install a given layout instead.  With the device RNG backend nothing here waits for the GPU."""
+        m = (torch.ones(self.B, dtype=torch.uint8, device=self.device) if mask is None
+             else torch.as_tensor(mask).to(device=self.device, dtype=torch.uint8).reshape(self.B).contiguous())
         if starts is not None:
             self.starts.copy_(torch.as_tensor(np.asarray(starts), dtype=torch.int16).reshape(self.B, self.N, 2))
             self.goals.copy_(torch.as_tensor(np.asarray(goals), dtype=torch.int16).reshape(self.B, self.N, 2))
         elif not self.deterministic:
-            self._draw(sel)
-        m = torch.zeros(self.B, dtype=torch.uint8, device=self.device)
-        m[torch.as_tensor(sel, device=self.device)] = 1
-        self.positions[m.bool()] = self.starts[m.bool()]
+            self._draw(None if mask is None else m)
+        torch.where(m.bool().view(self.B, 1, 1), self.starts, self.positions, out=self.positions)
+        self._reset_mask = m   # outlives the launch (replaced by the next reset, stream-ordered)
         self._args.reset_mask = m.data_ptr()
         nat.check(self._lib.mapf_cte_reset(C.byref(self._args), self._stream()))
-        torch.cuda.current_stream(self.device).synchronize()   # `m` must outlive the launch
         self._args.reset_mask = None
         return self.flat_obs
 
-    def step(self, actions):
-        """CTE:237-346 for every env.  ``actions``: int8 [B,N] joint actions."""
+    def step(self, actions, auto_reset: bool = False):
+        """CTE:237-346 for every env.  ``actions``: int8 [B,N] joint actions.  ``auto_reset`` (no reference counterpart,
+        the vector-env convention of the multi-agent batch API): envs whose episode ended in this step are reset behind
+        it -- ``flat_obs`` then holds the first observation of their next episode, ``reward`` / ``terminated`` /
+        ``truncated`` / ``info`` still describe the step that ended the episode."""
         a = torch.as_tensor(actions).to(device=self.device, dtype=torch.int8).reshape(self.B, self.N).contiguous()
         self._actions = a
         self._args.actions = a.data_ptr()
         nat.check(self._lib.mapf_cte_step(C.byref(self._args), self._stream()))
+        if auto_reset:
+            self.reset(mask=self.terminated | self.truncated)
         return self.flat_obs, self.reward, self.terminated, self.truncated, self.info
 
     def poll_errors(self) -> int:

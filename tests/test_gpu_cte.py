@@ -94,3 +94,57 @@ def test_cte_wrapper_reproduces_seeded_reference_run():
         assert [info[k] for k in ("blocking_count_step", "goals_reached_step", "goals_reached_total", "blocking_count_total")] == list(z["info"][t])
     with pytest.raises(ValueError):
         env.step([0, 0, 0, 7])
+
+
+def test_cte_device_layout_draws_and_auto_reset_at_batch_scale():
+    """B > 1 defaults to the device RNG backend: layouts come from the reset kernel's Philox draw (valid, different per
+    env, redrawn at every reset) and ``step(..., auto_reset=True)`` resets finished envs behind the step without a host
+    round trip; a sample of the batch is checked against the C oracle across several episodes."""
+    import torch
+
+    from dl_reference_models_b200 import maps
+    from dl_reference_models_b200.single_agent import BatchedCteEnv
+    from oracle.cte_oracle import CteOracleEnv
+
+    grid = maps.get_grid("ReferenceModel-2-1")
+    cfg = {"grid": grid, "num_agents": 4, "steps_per_episode": 12, "seed": 5}
+    B, S = 4096, 48
+    env = BatchedCteEnv(cfg, B)
+    assert env.rng_backend == "device"
+    env.reset()
+
+    def check_layouts():
+        st, gl = env.starts.cpu().numpy().astype(np.int64), env.goals.cpu().numpy().astype(np.int64)
+        assert (grid[st[..., 0], st[..., 1]] == 0).all() and (grid[gl[..., 0], gl[..., 1]] == 0).all()
+        cells = np.concatenate([st[..., 0] * grid.shape[1] + st[..., 1], gl[..., 0] * grid.shape[1] + gl[..., 1]], axis=1)
+        assert all(len(set(r)) == len(r) for r in cells.tolist()), "2N distinct cells per env"
+        return st, gl
+
+    st, gl = check_layouts()
+    assert len({tuple(r) for r in st.reshape(B, -1).tolist()}) > B // 2, "layouts differ between envs"
+    orcs = [CteOracleEnv(cfg, grid) for _ in range(S)]
+    ref = np.stack([o.reset(st[e].astype(np.int16), gl[e].astype(np.int16)) for e, o in enumerate(orcs)])
+    assert np.array_equal(env.flat_obs[:S].cpu().numpy(), ref)
+    gen = torch.Generator().manual_seed(3)
+    episodes = 0
+    for t in range(40):
+        acts = torch.randint(0, 5, (B, 4), dtype=torch.int8, generator=gen)
+        obs, reward, term, trunc, info = env.step(acts, auto_reset=True)
+        a = acts.numpy()
+        outs = [o.step(a[e]) for e, o in enumerate(orcs)]
+        done = (term.cpu().numpy() | trunc.cpu().numpy()).astype(bool)
+        assert np.array_equal(reward[:S].cpu().numpy(), np.array([o[1] for o in outs])), f"reward step {t}"
+        assert np.array_equal(done[:S], np.array([o[2] or o[3] for o in outs])), f"done step {t}"
+        assert np.array_equal(info[:S].cpu().numpy(), np.stack([o[4] for o in outs]))
+        if done.any():
+            episodes += int(done.sum())
+            st, gl = check_layouts()
+        got = obs[:S].cpu().numpy()
+        for e, o in enumerate(orcs):
+            want = o.reset(st[e].astype(np.int16), gl[e].astype(np.int16)) if done[e] else outs[e][0]
+            assert np.array_equal(got[e], want), f"obs env {e} step {t}"
+    assert episodes >= 3 * B and env.poll_errors() == 0
+    # the numpy backend stays available for batches (seed-compatible env 0)
+    env2 = BatchedCteEnv(dict(cfg, rng_backend="numpy"), 3)
+    env2.reset()
+    assert env2.rng_backend == "numpy" and len(env2._rngs) == 3
