@@ -497,29 +497,29 @@ class ReferenceModel(MultiAgentEnv):
         return self._results(acts[0], prev)
 
     def _draw_goal_overrides(self, acts: np.ndarray, prev: np.ndarray):
-        """Probe launch to learn who arrives (moves do not depend on goals), roll the device back,
-        let the host RNG hook pick the cells in the reference's order, return them as overrides."""
+        """Who arrives this step is decided by the moves alone (ENV:502-563: they depend on the owner grid, not on
+        anybody's goal), so the wrapper replays the move loop on its host mirrors -- no probe launch, no roll-back --
+        lets the host RNG hook pick the new cells in the reference's order and hands them to the one real launch as
+        overrides."""
         N = self._num_agents
-        all_keys = nat.STATE_FIELDS
-        saved = {k: None for k in all_keys}
-        st = self._state_struct(all_keys)
-        nat.check(self._lib.mapf_get_state_host(self._h, C.byref(st)))
-        saved = {k: self._hs[k].copy() for k in all_keys}
+        R, Cc = self.grid.shape
         mirrors = (self._reached_arr.copy(), self._completed_once_arr.copy(), self._blocking_pressure_prev_arr.copy(),
                    self._episode_goals_reached_total)
-        probe = nat.MapfOutputs(agent_step_flags=self._ho["agent_step_flags"].ctypes.data,
-                                step_flags=self._ho["step_flags"].ctypes.data)
-        nat.check(self._lib.mapf_step_host(self._h, _vp(acts), None, None, C.byref(probe), 0))
-        bits = C.c_uint32(0)
-        nat.check(self._lib.mapf_poll_errors(self._h, C.byref(bits), None))
-        arrived = (self._ho["agent_step_flags"][0] & nat.ASF_GOAL_REACHED) != 0
-        pst = self._state_struct(("positions",))
-        nat.check(self._lib.mapf_get_state_host(self._h, C.byref(pst)))
-        new_pos = self._hs["positions"][0].copy()
-        for k in all_keys:  # roll back: host images and device
-            np.copyto(self._hs[k], saved[k])
-        st = self._state_struct(all_keys)
-        nat.check(self._lib.mapf_set_state_host(self._h, C.byref(st)))
+        saved = {"positions": self._positions_arr.copy(), "goals": self._goals_arr.copy(),
+                 "owner": self._occupancy_owner.copy()}
+        owner = self._occupancy_owner.copy()
+        new_pos = prev.copy()
+        for i in range(N):   # ENV:512-526
+            a = int(acts[0, i])
+            if a == NO_OP:
+                continue
+            tr, tc = (int(v) for v in prev[i] + self._action_deltas[a])
+            if not (0 <= tr < R and 0 <= tc < Cc) or self.grid[tr, tc] != 0 or owner[tr, tc] != self.UNASSIGNED_OWNER:
+                continue
+            owner[int(prev[i, 0]), int(prev[i, 1])] = self.UNASSIGNED_OWNER
+            owner[tr, tc] = i
+            new_pos[i] = (tr, tc)
+        arrived = (new_pos == self._goals_arr).all(axis=1)
         if not arrived.any():
             return None
         override = np.full((1, N, 2), -1, np.int16)
@@ -534,8 +534,10 @@ class ReferenceModel(MultiAgentEnv):
             self.goal_reached_once[self.agents[idx]] = True
             self._assign_new_goal(int(idx))
             override[0, idx] = self._goals_arr[idx]
-        for k in ("positions", "goals"):
-            np.copyto(self._hs[k], saved[k])
+        self._positions_arr[:] = saved["positions"]
+        self._goals_arr[:] = saved["goals"]
+        self._occupancy_owner[:] = saved["owner"]
+        self._rebuild_goal_owner()
         self._reached_arr[:], self._completed_once_arr[:], self._blocking_pressure_prev_arr[:] = mirrors[:3]
         self._episode_goals_reached_total = mirrors[3]
         return override
