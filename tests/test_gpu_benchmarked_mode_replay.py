@@ -123,3 +123,17 @@ def test_c2_small_map_unmasked_sampler(kind):
 
     cfg = {"num_agents": 4, "sensor_range": 2, "steps_per_episode": 40, "lifelong_mapf": False, "seed": 7}
     _replay(cfg, maps.get_grid("ReferenceModel-2-1"), 2048, 130, kind, True, env_id_base=17, masked=False)
+
+
+def test_c3_full_baseline_batch_65536_envs():
+    """BASELINE configs[2] at its FULL size -- 65 536 envs x 16 agents, the batch bench.py times, with the kernel "auto"
+    picks for it (env-per-thread, FAST) -- compared with the oracle on every channel of every env: 20 steps with
+    8-step episodes, so every env is reset twice inside a launch and the Philox goal / layout / action draws of a
+    million agents are replayed."""
+    from dl_reference_models_b200 import maps
+
+    grid = maps.random_obstacle_grid(32, 32, 0.30, 2026, min_free=32)
+    cfg = {"num_agents": 16, "sensor_range": 2, "steps_per_episode": 8, "lifelong_mapf": True, "seed": 999,
+           "enable_lock_metrics": True, "deadlock_window_steps": 3, "livelock_window_steps": 6}
+    episodes, arrivals = _replay(cfg, grid, 65536, 20, "auto", True)
+    assert episodes == 2 * 65536 and arrivals > 10000
