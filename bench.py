@@ -230,8 +230,9 @@ def run_reference(args, rank: int, world: int):
           "sample": f"mean of {len(vals)} samples ({wall:.0f} s in total), the last one: " + last["sample"]}
     line = {
         "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16/u8",
-        "data": "synthetic", "impl": "reference", "config": config_dict(args, args.gpus), "cpu_baseline": cb,
+        # one step = one pass over the batch of the b200 arm's step (envs x agents agent-steps), at the measured CPU rate
+        "ms_per_step": args.envs * args.agents / v * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int16/u8", "data": "synthetic", "impl": "reference", "config": config_dict(args, args.gpus), "cpu_baseline": cb,
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
         "cpu_baseline_python": python_reference_run(args, seconds=10.0),
