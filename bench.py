@@ -517,7 +517,7 @@ def run_b200(args, rank: int, local_rank: int, world: int):
     host_actions = [torch.randint(0, 5, (B, N), dtype=torch.int8, generator=gen).pin_memory() for _ in range(4)]
     delivered = sum(v.numel() * v.element_size() for v in host_out.values())
     lib = nat.lib()
-    Ke, We = max(3, min(K, 50)), 8   # the first six calls are the library's packed-vs-plain calibration
+    Ke, We = max(3, min(K, 50)), 12   # the first nine calls are the library's packed / packed + NT / plain calibration
     torch.cuda.synchronize(dev)
     for i in range(We):
         nat.check(lib.mapf_step_host(e2e_env._h, C.c_void_p(host_actions[i % 4].data_ptr()), None, None,
@@ -602,6 +602,7 @@ def run_b200(args, rank: int, local_rank: int, world: int):
                     "ms_per_step": e2e_ms / Ke,
                     "api": "mapf_step_host (C ABI, pinned host buffers)",
                     "transfer": ("bit-packed agent records over PCIe, expanded into the host arrays inside the call"
+                                 + (" (non-temporal stores)" if int(lib.mapf_host_transfer_mode(e2e_env._h)) == 2 else "")
                                  if d2h < delivered else "plain copies"),
                     "actions": "uniform random from pinned host buffers", "checksum": checksum,
                     "roofline": {"bound": "host DMA (PCIe on one GPU; the node's host memory system when several ranks share it)",

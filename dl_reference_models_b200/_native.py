@@ -177,6 +177,7 @@ def lib():
     L.mapf_step_host.argtypes = [vp, vp, vp, vp, C.POINTER(MapfOutputs), i32]
     L.mapf_step_many.argtypes = [vp, vp, C.POINTER(MapfOutputs), i32, C.c_int64, i32, vp]
     L.mapf_host_transfer_bytes.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    L.mapf_host_transfer_mode.argtypes = [vp]
     L.mapf_host_wait_stream.argtypes = [vp, vp]
     L.mapf_step_host_records.argtypes = [vp, vp, vp, C.POINTER(MapfOutputs), i32]
     L.mapf_host_memory_probe.argtypes = [vp, C.c_int64, C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_double)]
@@ -213,7 +214,7 @@ EXPORTS = (
     "mapf_version", "mapf_last_error", "mapf_create", "mapf_destroy", "mapf_set_map",
     "mapf_state_nbytes", "mapf_bind_state", "mapf_alloc_state", "mapf_get_state_host",
     "mapf_set_state_host", "mapf_reset", "mapf_step", "mapf_step_many", "mapf_reset_host", "mapf_step_host",
-    "mapf_host_transfer_bytes", "mapf_host_wait_stream", "mapf_host_memory_probe", "mapf_step_host_records", "mapf_packed_record_bytes", "mapf_unpack_records",
+    "mapf_host_transfer_bytes", "mapf_host_transfer_mode", "mapf_host_wait_stream", "mapf_host_memory_probe", "mapf_step_host_records", "mapf_packed_record_bytes", "mapf_unpack_records",
     "mapf_observe", "mapf_observe_host",
     "mapf_flat_obs_dim", "mapf_pack_flat_obs", "mapf_sample_masked_actions",
     "mapf_sample_random_actions", "mapf_set_fused_sampler", "mapf_metrics_reduce", "mapf_poll_errors", "mapf_launch_count",

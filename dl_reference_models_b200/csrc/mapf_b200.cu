@@ -213,8 +213,9 @@ struct mapf_handle {
     int knob_host_pin;          // MAPF_HOST_PIN: -1 unset (pin when the node is shared), 0 off, 1 on
     // packed-or-plain, decided by measurement: calls 0-2 go packed, 3-5 plain (the first of each untimed), then the
     // faster one stays -- on THIS host, with whatever else (the other ranks of the node) is running beside it
-    int auto_calls, auto_choice;          // auto_choice: -1 undecided, 0 plain, 1 packed
-    int64_t auto_ns[2];                   // summed call time of the timed calls: [plain, packed]
+    int auto_calls, auto_choice;          // auto_choice: -1 undecided, 0 plain, 1 packed, 2 packed + non-temporal expansion
+    int64_t auto_ns[3];                   // summed call time of the timed calls: [plain, packed, packed + NT]
+    int knob_host_nt;                     // MAPF_HOST_NT: -1 unset (measured with the rest), 0 off, 1 on
     // ordering of the *_host entry points (private streams) against work the caller queued on ITS stream
     cudaEvent_t ev_user;
     cudaStream_t last_user_stream;
@@ -488,7 +489,9 @@ void read_knobs(mapf_handle *h) {
     if (const char *lr = getenv("LOCAL_RANK")) { const int r = atoi(lr); if (r >= 0 && r < h->local_world) h->local_rank = r; }
     h->knob_host_pin = -1;
     if (const char *ov = getenv("MAPF_HOST_PIN")) h->knob_host_pin = atoi(ov) != 0 ? 1 : 0;
-    h->auto_calls = 0; h->auto_choice = -1; h->auto_ns[0] = h->auto_ns[1] = 0;
+    h->auto_calls = 0; h->auto_choice = -1; h->auto_ns[0] = h->auto_ns[1] = h->auto_ns[2] = 0;
+    h->knob_host_nt = -1;
+    if (const char *ov = getenv("MAPF_HOST_NT")) h->knob_host_nt = atoi(ov) != 0 ? 1 : 0;
 }
 
 // This rank's share of the cores the process may run on: a contiguous chunk of the affinity mask per local rank.
@@ -1122,23 +1125,34 @@ static int step_host_impl(mapf_handle *h, const int8_t *actions, const int16_t *
     // into the caller's arrays while slice c + 1 is in flight (and while this thread is still enqueueing).
     // MAPF_HOST_RAW_32NDS=k sends the last k/32 of the batch as plain copies behind the packed slices (for hosts
     // with too few cores to keep up with PCIe; measured no gain on the 16-core B200 hosts, so 0 by default).
-    // packed or plain: forced by MAPF_HOST_PACK, else measured on the first six eligible calls (see mapf_handle)
-    bool packed = false;
+    // packed or plain: forced by MAPF_HOST_PACK, else measured on the first nine eligible calls (see mapf_handle)
+    // ... three candidates: packed, packed with the expansion going through non-temporal stores (hosts whose memory
+    // system is the bound: no read-for-ownership of the 45 MB it writes), plain; three calls each, the first untimed
+    bool packed = false, nt = h->knob_host_nt > 0;
     int auto_phase = -1;   // >= 0: this call is a timed calibration call for mode auto_phase
     const bool records = records_host != nullptr;
     if (records) packed = true;   // same kernels and slicing as the packed path; nothing is expanded on the host
     else if (host_pack_eligible(h, out_host)) {
         if (h->knob_host_pack >= 0) packed = h->knob_host_pack != 0;
-        else if (h->auto_choice >= 0) packed = h->auto_choice != 0;
+        else if (h->auto_choice >= 0) { packed = h->auto_choice != 0; nt = h->auto_choice == 2; }
         else {
+            // candidate modes in calibration order; a forced MAPF_HOST_NT leaves two of them
+            int modes[3], nm = 0;
+            if (h->knob_host_nt != 1) modes[nm++] = 1;
+            if (h->knob_host_nt != 0) modes[nm++] = 2;
+            modes[nm++] = 0;
             const int c = h->auto_calls++;
-            packed = c < 3;
-            if (c != 0 && c != 3) auto_phase = packed ? 1 : 0;
+            const int mode = modes[(c / 3) < nm ? c / 3 : nm - 1];
+            packed = mode != 0; nt = mode == 2;
+            if (c % 3 != 0) auto_phase = mode;
+            if (c + 1 >= 3 * nm) auto_phase |= 0x100;   // last calibration call: decide behind it
         }
     }
+
     if (packed) {
         rc = ensure_pack(h);
         if (rc) return rc;
+        if (!records) mapf::host_pool_set_nt(h->pool, nt);
     }
     // slice sizes as weights: uniform by default; the packed path tapers them (small first slice: its records are
     // on the wire early; small last slice: the expansion nobody overlaps is short).  MAPF_HOST_SLICES=n -> n
@@ -1325,8 +1339,16 @@ static int step_host_impl(mapf_handle *h, const int8_t *actions, const int16_t *
     h->last_h2d_bytes = h2d;
     h->last_d2h_bytes = d2h;
     if (auto_phase >= 0) {
-        h->auto_ns[auto_phase] += std::chrono::steady_clock::now().time_since_epoch().count() - t_begin;
-        if (h->auto_calls >= 6) h->auto_choice = h->auto_ns[1] <= h->auto_ns[0] ? 1 : 0;
+        h->auto_ns[auto_phase & 0xFF] += std::chrono::steady_clock::now().time_since_epoch().count() - t_begin;
+        if (auto_phase & 0x100) {   // every candidate has two timed calls: the fastest stays (ties: packed, then NT)
+            int best = -1;
+            const int order[3] = {1, 2, 0};
+            for (int i = 0; i < 3; ++i) {
+                const int m = order[i];
+                if (h->auto_ns[m] > 0 && (best < 0 || h->auto_ns[m] < h->auto_ns[best])) best = m;
+            }
+            h->auto_choice = best < 0 ? 1 : best;
+        }
     }
     return MAPF_OK;
 }
@@ -1372,6 +1394,13 @@ int mapf_host_transfer_bytes(const mapf_handle *h, int64_t *h2d_bytes, int64_t *
     if (h2d_bytes) *h2d_bytes = h->last_h2d_bytes;
     if (d2h_bytes) *d2h_bytes = h->last_d2h_bytes;
     return MAPF_OK;
+}
+
+int mapf_host_transfer_mode(const mapf_handle *h) {
+    if (!h) return fail(MAPF_ERR_INVALID_ARG, "null handle");
+    if (h->knob_host_pack == 0) return 0;
+    if (h->knob_host_pack > 0) return h->knob_host_nt > 0 ? 2 : 1;
+    return h->auto_choice;
 }
 
 int mapf_packed_record_bytes(int32_t v2) { return v2 >= 1 ? mapf::pack_record_bytes(v2) : 0; }

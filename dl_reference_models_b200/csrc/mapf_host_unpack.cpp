@@ -185,9 +185,58 @@ constexpr int kBlock = 64;  // chunk boundaries fall on whole 64-agent blocks
 
 enum { ISA_GENERIC = 0, ISA_BMI2 = 1, ISA_VBMI = 2 };
 
-// Agents [b0, b1) of the job.  (Expanding into an L1-resident block and streaming it out with non-temporal
-// stores was measured too: slower than plain stores on the B200 hosts, 1.77e9 vs 2.08e9 agent-steps/s end to end.)
-void unpack_agents(const UnpackJob &j, int64_t b0, int64_t b1, int isa) {
+#if MAPF_X86
+// bytes [src, src + n) -> dst with non-temporal 64-byte stores (unaligned head / tail: plain copies)
+__attribute__((target("avx512f")))
+inline void stream_out(void *dst_, const void *src_, size_t n) {
+    uint8_t *dst = static_cast<uint8_t *>(dst_);
+    const uint8_t *src = static_cast<const uint8_t *>(src_);
+    size_t head = (size_t)(-(intptr_t)reinterpret_cast<uintptr_t>(dst)) & 63u;
+    if (head > n) head = n;
+    if (head) { memcpy(dst, src, head); dst += head; src += head; n -= head; }
+    for (; n >= 64; n -= 64, dst += 64, src += 64)
+        _mm512_stream_si512(reinterpret_cast<__m512i *>(dst), _mm512_loadu_si512(src));
+    if (n) memcpy(dst, src, n);
+}
+
+void unpack_vbmi(int V2, Cursor c, int64_t n, const float *gr, const float *gc, float den_row, float den_col);
+
+// MAPF_HOST_NT=1: expand kNtBlock agents into a cache-resident block, then stream whole lines out with non-temporal
+// stores.  Plain stores read every line of the output arrays before they overwrite it (read for ownership); where the
+// host's memory system is what bounds mapf_step_host -- many ranks on one node -- that read is a third of the traffic.
+// (On a single-GPU host the call is PCIe-paced and the staged copy only costs: 1.77e9 vs 2.08e9 agent-steps/s.)
+constexpr int kNtBlock = 512;
+__attribute__((target("avx512f,avx512bw,avx512vl,avx512vbmi,bmi2")))
+void unpack_agents_nt(const UnpackJob &j, int64_t b0, int64_t b1) {
+    alignas(64) static thread_local uint8_t s_obs[kNtBlock * 49];
+    alignas(64) static thread_local int8_t s_mask[kNtBlock * 5];
+    alignas(64) static thread_local float s_gd[kNtBlock * 2], s_rw[kNtBlock];
+    const int V2 = j.V2, PB = pack_obs_bytes(V2);
+    const int64_t na = j.a1 - j.a0;
+    const float *gr = j.gdt_row + 128, *gc = j.gdt_col + 128;
+    if (j.bytes_src) memcpy(j.bytes_dst + b0, j.bytes_src + (b0 - j.a0), (size_t)(b1 - b0));
+    for (int64_t blk = b0; blk < b1; blk += kNtBlock) {
+        const int64_t n = (b1 - blk < kNtBlock) ? b1 - blk : kNtBlock, off = blk - j.a0;
+        Cursor c;
+        c.bits = j.packed + off * PB;
+        c.diff = reinterpret_cast<const int8_t *>(j.packed + na * PB) + off * 2;
+        c.rew2 = reinterpret_cast<const int8_t *>(j.packed + na * (PB + 2)) + off;
+        c.obs = s_obs; c.mask = s_mask; c.gd = s_gd; c.rw = s_rw;
+        unpack_vbmi(V2, c, n, gr, gc, j.den_row, j.den_col);
+        stream_out(j.obs + blk * V2, s_obs, (size_t)n * V2);
+        stream_out(j.mask + blk * 5, s_mask, (size_t)n * 5);
+        stream_out(j.goal_delta + blk * 2, s_gd, (size_t)n * 8);
+        stream_out(j.reward + blk, s_rw, (size_t)n * 4);
+    }
+    _mm_sfence();
+}
+#endif
+
+// Agents [b0, b1) of the job.
+void unpack_agents(const UnpackJob &j, int64_t b0, int64_t b1, int isa, bool nt = false) {
+#if MAPF_X86
+    if (nt && isa == ISA_VBMI) return unpack_agents_nt(j, b0, b1);
+#endif
     const int V2 = j.V2, PB = pack_obs_bytes(V2);
     const int64_t na = j.a1 - j.a0, off = b0 - j.a0;
     Cursor c;
@@ -227,6 +276,7 @@ struct QueuedJob {
 struct HostPool {
     int nthreads = 1, nchunks = 1;
     int isa = ISA_GENERIC;
+    std::atomic<bool> nt{false};   // staged expansion with non-temporal stores (hosts bound by their memory system)
     std::vector<std::thread> workers;
     std::mutex mu;
     std::condition_variable cv;
@@ -269,7 +319,7 @@ struct HostPool {
             const int64_t n = job.a1 - job.a0, nblk = (n + kBlock - 1) / kBlock;
             int64_t b0 = job.a0 + kBlock * (nblk * c / nchunks), b1 = job.a0 + kBlock * (nblk * (c + 1) / nchunks);
             if (b1 > job.a1) b1 = job.a1;
-            if (b0 < b1) unpack_agents(job, b0, b1, isa);
+            if (b0 < b1) unpack_agents(job, b0, b1, isa, nt.load(std::memory_order_relaxed));
             if (q.done.fetch_add(1, std::memory_order_acq_rel) + 1 == nchunks)
                 q.t_last.store(std::chrono::steady_clock::now().time_since_epoch().count(), std::memory_order_relaxed);
         }
@@ -321,6 +371,7 @@ HostPool *host_pool_create(int threads, const int *cpus, int ncpus) {
     if (p->isa == ISA_BMI2 && __builtin_cpu_supports("avx512vbmi") && __builtin_cpu_supports("avx512bw") &&
         __builtin_cpu_supports("avx512vl"))
         p->isa = ISA_VBMI;
+    if (const char *ov = getenv("MAPF_HOST_NT")) p->nt.store(atoi(ov) != 0);
     if (const char *ov = getenv("MAPF_HOST_ISA")) {  // generic | bmi2 | vbmi: cap the instruction set (tests)
         const int cap = ov[0] == 'g' ? ISA_GENERIC : ov[0] == 'b' ? ISA_BMI2 : ISA_VBMI;
         if (cap < p->isa) p->isa = cap;
@@ -350,6 +401,8 @@ void host_pool_destroy(HostPool *p) {
     for (auto &t : p->workers) t.join();
     delete p;
 }
+
+void host_pool_set_nt(HostPool *p, bool on) { if (p) p->nt.store(on, std::memory_order_release); }
 
 int host_pool_threads(const HostPool *p) { return p ? p->nthreads : 0; }
 

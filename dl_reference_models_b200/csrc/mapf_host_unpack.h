@@ -34,6 +34,9 @@ struct HostPool;
 HostPool *host_pool_create(int threads, const int *cpus = nullptr, int ncpus = 0);
 void host_pool_destroy(HostPool *p);
 int host_pool_threads(const HostPool *p);
+// expansion through cache-resident blocks and non-temporal whole-line stores (AVX-512 hosts; a no-op elsewhere); set
+// between steps.  Default: MAPF_HOST_NT at pool creation, else off.
+void host_pool_set_nt(HostPool *p, bool on);
 // One step = begin, submit (non-blocking, at most 32 jobs; a job starts once *ticket == ticket_value, or at once
 // if ticket is null), finish (the caller's thread joins in and returns when every job is done).  Single caller.
 void host_pool_begin(HostPool *p);

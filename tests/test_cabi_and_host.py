@@ -184,12 +184,14 @@ def _pack_block_numpy(obs, mask, drow, dcol, reward2):
     return np.concatenate([bits.reshape(-1), diff.reshape(-1), reward2.astype(np.int8).view(np.uint8)])
 
 
-@pytest.mark.parametrize("isa", ["generic", "bmi2", "vbmi"])
+@pytest.mark.parametrize("isa", ["generic", "bmi2", "vbmi", "vbmi+nt"])
 @pytest.mark.parametrize("v2,threads,n", [(9, 1, 10007), (25, 1, 10007), (25, 5, 70001), (49, 3, 10007), (25, 2, 3), (9, 4, 64)])
 def test_host_expansion_of_packed_block(monkeypatch, isa, v2, threads, n):
     """Every instruction-set variant of the expansion (capped by MAPF_HOST_ISA; a CPU without the extension falls
-    back to the next one) reproduces the arrays exactly."""
-    monkeypatch.setenv("MAPF_HOST_ISA", isa)
+    back to the next one) reproduces the arrays exactly -- also the staged one with non-temporal whole-line stores
+    (MAPF_HOST_NT=1, for hosts bound by their memory system), unaligned heads / tails and guard rows included."""
+    monkeypatch.setenv("MAPF_HOST_ISA", isa.split("+")[0])
+    monkeypatch.setenv("MAPF_HOST_NT", "1" if isa.endswith("+nt") else "0")
     L = nat.lib()
     rng = np.random.default_rng(v2 * 10 + threads)
     obs = rng.integers(0, 5, (n, v2), dtype=np.uint8)

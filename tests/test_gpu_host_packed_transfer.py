@@ -222,3 +222,20 @@ def test_records_delivery_expands_to_the_plain_arrays(sr, B):
         assert torch.equal(a.state[k], b.state[k]), f"state {k}"
     rs = nat.lib().mapf_packed_record_bytes((2 * sr + 1) ** 2)
     assert transfer_bytes(b)[1] == B * 16 * (rs + 2) + B * (3 + 64)
+
+
+def test_non_temporal_expansion_and_measured_mode_are_exact(monkeypatch):
+    """The packed delivery with the expansion going through cache-resident blocks and non-temporal stores
+    (MAPF_HOST_NT=1), and the handle's own choice -- packed / packed + NT / plain, measured on its first nine calls --
+    deliver the arrays of the device-side step, whatever mode a call happens to run in."""
+    monkeypatch.setenv("MAPF_HOST_PACK", "1")
+    monkeypatch.setenv("MAPF_HOST_NT", "1")
+    _, b = run_host_vs_device(c3(), 8192 + 96, 12)
+    assert nat.lib().mapf_host_transfer_mode(b._h) == 2
+    monkeypatch.delenv("MAPF_HOST_PACK", raising=False)
+    monkeypatch.delenv("MAPF_HOST_NT", raising=False)
+    _, b = run_host_vs_device(c3(), 8192 + 96, 14)      # calls 0-8 calibrate, 9.. run in the mode that won
+    assert nat.lib().mapf_host_transfer_mode(b._h) in (0, 1, 2)
+    monkeypatch.setenv("MAPF_HOST_NT", "0")             # NT ruled out: two candidates, six calibration calls
+    _, b = run_host_vs_device(c3(), 8192 + 96, 8)
+    assert nat.lib().mapf_host_transfer_mode(b._h) in (0, 1)

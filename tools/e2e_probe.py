@@ -84,6 +84,7 @@ SETTINGS = [
     ("auto", {}),
     ("plain", {"MAPF_HOST_PACK": "0"}),
     ("packed", {"MAPF_HOST_PACK": "1"}),
+    ("packed_nt", {"MAPF_HOST_PACK": "1", "MAPF_HOST_NT": "1"}),
     ("packed_nopin", {"MAPF_HOST_PACK": "1", "MAPF_HOST_PIN": "0"}),
     ("packed_t2", {"MAPF_HOST_PACK": "1", "MAPF_HOST_THREADS": "2"}),
     ("packed_t3", {"MAPF_HOST_PACK": "1", "MAPF_HOST_THREADS": "3"}),
@@ -93,7 +94,7 @@ SETTINGS = [
 if os.environ.get("E2E_SETTINGS"):
     want = os.environ["E2E_SETTINGS"].split(",")
     SETTINGS = [x for x in SETTINGS if x[0] in want]
-KNOBS = ("MAPF_HOST_PACK", "MAPF_HOST_PIN", "MAPF_HOST_THREADS", "MAPF_HOST_SLICES", "MAPF_HOST_PLAN")
+KNOBS = ("MAPF_HOST_PACK", "MAPF_HOST_PIN", "MAPF_HOST_THREADS", "MAPF_HOST_SLICES", "MAPF_HOST_PLAN", "MAPF_HOST_NT")
 for name, envv in SETTINGS:
     for k in KNOBS:
         os.environ.pop(k, None)
