@@ -48,6 +48,19 @@ def main():
     res["policy_act"] = {"us_per_launch": s * 1e6, "agents": B * N, "GBps": bytes_per_agent * B * N / s / 1e9,
                          "agent_steps_per_s": B * N / s, "flops": 2 * (28 * 64 + 64 * 64 + 64 * 6) * B * N,
                          "TFLOPs": 2 * (28 * 64 + 64 * 64 + 64 * 6) * B * N / s / 1e12}
+    # the MLP runs on mma.sync (K <= 64 per layer, the channels it reads and writes bound it, not the tensor pipe):
+    # reported against the measured dense bf16 peak so that nobody has to guess
+    try:
+        import json as _json
+        from pathlib import Path as _Path
+
+        _pk = _json.loads((_Path(__file__).resolve().parents[1] / "MEASURED_PEAKS.json").read_text())
+        res["policy_act"]["bf16_peak_TFLOPs"] = float(_pk["bf16_tflops"])
+        res["policy_act"]["frac_of_bf16_peak"] = res["policy_act"]["TFLOPs"] / float(_pk["bf16_tflops"])
+        res["policy_act"]["frac_of_hbm_peak"] = res["policy_act"]["GBps"] / float(_pk["hbm_gbs"])
+    except Exception as exc:   # no peaks file on this box
+        res["policy_act"]["bf16_peak_TFLOPs"] = None
+        res["policy_act"]["frac_note"] = f"MEASURED_PEAKS.json not readable: {exc}"
     T = 64
     rewards, values = torch.randn(T, B, N, device="cuda"), torch.randn(T, B, N, device="cuda")
     dones = torch.rand(T, B, device="cuda") < 0.01
