@@ -520,6 +520,7 @@ def run_b200(args, rank: int, local_rank: int, world: int):
     Ke, We = max(3, min(K, 50)), 12   # the first nine calls are the library's packed / packed + NT / plain calibration
     torch.cuda.synchronize(dev)
     for i in range(We):
+        barrier()   # the ranks of a node calibrate their delivery mode in step, like workers that step in step
         nat.check(lib.mapf_step_host(e2e_env._h, C.c_void_p(host_actions[i % 4].data_ptr()), None, None,
                                      C.byref(cout), 1))
     e2e_blocks = []
@@ -583,6 +584,9 @@ def run_b200(args, rank: int, local_rank: int, world: int):
         # a fill probe over fresh memory does not see): reported beside the PCIe floor, not folded into it
         host_fill_ms = (delivered / 1e9) / max(ceil["host_fill_gbs"] / world, 1e-9) * 1e3 if d2h < delivered else 0.0
         floor_ms = pcie_floor_ms
+        e2e_mode = int(lib.mapf_host_transfer_mode(e2e_env._h))
+        if e2e_mode == 2:   # non-temporal expansion: every byte of the arrays goes to DRAM, the fill rate IS a floor
+            floor_ms = max(pcie_floor_ms, host_fill_ms)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": block_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -602,16 +606,18 @@ def run_b200(args, rank: int, local_rank: int, world: int):
                     "ms_per_step": e2e_ms / Ke,
                     "api": "mapf_step_host (C ABI, pinned host buffers)",
                     "transfer": ("bit-packed agent records over PCIe, expanded into the host arrays inside the call"
-                                 + (" (non-temporal stores)" if int(lib.mapf_host_transfer_mode(e2e_env._h)) == 2 else "")
+                                 + (" (non-temporal stores)" if e2e_mode == 2 else "")
                                  if d2h < delivered else "plain copies"),
                     "actions": "uniform random from pinned host buffers", "checksum": checksum,
                     "roofline": {"bound": "host DMA (PCIe on one GPU; the node's host memory system when several ranks share it)",
                                  "floor_ms_per_step": floor_ms, "pcie_floor_ms": pcie_floor_ms,
                                  "host_fill_time_ms": host_fill_ms, "frac": floor_ms / (e2e_ms / Ke),
-                                 "measured_ceilings_aggregate": ceil, "host_cores": ncores,
+                                 "measured_ceilings_aggregate": ceil, "host_cores": ncores, "delivery_mode": e2e_mode,
                                  "note": "ceilings probed in this job with all ranks at once: pinned D2H / H2D DMA, and the "
                                          "streaming fill / copy rate of the host threads the call expands with; floor = the "
-                                         "bytes this step moves over PCIe / the rank's share of the measured DMA rates"}},
+                                         "bytes this step moves over PCIe / the rank's share of the measured DMA rates, and "
+                                         "-- when the expansion uses non-temporal stores (delivery_mode 2) -- at least the "
+                                         "time the same threads need to stream the delivered arrays to DRAM"}},
             "e2e_compact": {"value": world * B * N * Ke / (rec_ms * 1e-3), "unit": UNIT, "ms_per_step": rec_ms / Ke,
                             "h2d_bytes_per_step": rec_h2d, "d2h_bytes_per_step": rec_d2h, "steps": Ke,
                             "api": "mapf_step_host_records (C ABI, pinned host buffers): the observation / mask / goal-delta / "

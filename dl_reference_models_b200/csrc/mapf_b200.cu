@@ -1127,7 +1127,9 @@ static int step_host_impl(mapf_handle *h, const int8_t *actions, const int16_t *
     // with too few cores to keep up with PCIe; measured no gain on the 16-core B200 hosts, so 0 by default).
     // packed or plain: forced by MAPF_HOST_PACK, else measured on the first nine eligible calls (see mapf_handle)
     // ... three candidates: packed, packed with the expansion going through non-temporal stores (hosts whose memory
-    // system is the bound: no read-for-ownership of the 45 MB it writes), plain; three calls each, the first untimed
+    // system is the bound: no read-for-ownership of the 45 MB it writes), plain; three calls each, the first untimed.
+    // Ranks that share a node should make these calls in step (they do when they step their envs in step): a rank
+    // that calibrates while the others idle sees a host that is not the one it will run on.
     bool packed = false, nt = h->knob_host_nt > 0;
     int auto_phase = -1;   // >= 0: this call is a timed calibration call for mode auto_phase
     const bool records = records_host != nullptr;
@@ -1141,10 +1143,12 @@ static int step_host_impl(mapf_handle *h, const int8_t *actions, const int16_t *
             if (h->knob_host_nt != 1) modes[nm++] = 1;
             if (h->knob_host_nt != 0) modes[nm++] = 2;
             modes[nm++] = 0;
+            // round robin (each mode once untimed, then twice timed): whatever else loads the host while this handle
+            // calibrates -- the other ranks of the node, calibrating too -- weighs on every candidate alike
             const int c = h->auto_calls++;
-            const int mode = modes[(c / 3) < nm ? c / 3 : nm - 1];
+            const int mode = modes[c % nm];
             packed = mode != 0; nt = mode == 2;
-            if (c % 3 != 0) auto_phase = mode;
+            if (c >= nm) auto_phase = mode;
             if (c + 1 >= 3 * nm) auto_phase |= 0x100;   // last calibration call: decide behind it
         }
     }

@@ -281,9 +281,10 @@ int mapf_step_host(mapf_handle *h, const int8_t *actions, const int16_t *goal_ov
  * inside the call expand them into the caller's arrays -- the delivered arrays are bit for bit the same.
  * Whether it pays depends on the host (PCIe rate against what its cores and memory system can expand, with
  * whatever else -- the other ranks of a multi-GPU node -- runs beside it), so the handle measures: its first nine
- * eligible calls go packed x3, packed with a non-temporal expansion x3 (cache-resident blocks streamed out as whole
- * lines: no read-for-ownership of the arrays, which is what counts on a host bound by its memory system), plain x3
- * (the first of each untimed) and the fastest mode stays.  MAPF_HOST_PACK=0 / 1 and MAPF_HOST_NT=0 / 1 force the
+ * eligible calls take turns -- packed, packed with a non-temporal expansion (cache-resident blocks streamed out as whole
+ * lines: no read-for-ownership of the arrays, which is what counts on a host bound by its memory system), plain, three
+ * times round (the first round untimed) -- and the fastest mode stays; ranks that share a node should make these calls
+ * in step, so that each of them measures the host it will run on.  MAPF_HOST_PACK=0 / 1 and MAPF_HOST_NT=0 / 1 force the
  * choices, MAPF_HOST_THREADS / MAPF_HOST_SLICES tune it.  The expansion
  * threads (cores of this process / LOCAL_WORLD_SIZE, at most 16, the caller's thread included) are pinned one per
  * core to this rank's chunk of the affinity mask when the node is shared (MAPF_HOST_PIN=0 / 1 overrides).
