@@ -214,7 +214,7 @@ struct mapf_handle {
     // packed-or-plain, decided by measurement: calls 0-2 go packed, 3-5 plain (the first of each untimed), then the
     // faster one stays -- on THIS host, with whatever else (the other ranks of the node) is running beside it
     int auto_calls, auto_choice;          // auto_choice: -1 undecided, 0 plain, 1 packed, 2 packed + non-temporal expansion
-    int64_t auto_ns[3];                   // summed call time of the timed calls: [plain, packed, packed + NT]
+    int64_t auto_ns[3];                   // best call time of the timed calls: [plain, packed, packed + NT]
     int knob_host_nt;                     // MAPF_HOST_NT: -1 unset (measured with the rest), 0 off, 1 on
     // ordering of the *_host entry points (private streams) against work the caller queued on ITS stream
     cudaEvent_t ev_user;
@@ -1125,7 +1125,7 @@ static int step_host_impl(mapf_handle *h, const int8_t *actions, const int16_t *
     // into the caller's arrays while slice c + 1 is in flight (and while this thread is still enqueueing).
     // MAPF_HOST_RAW_32NDS=k sends the last k/32 of the batch as plain copies behind the packed slices (for hosts
     // with too few cores to keep up with PCIe; measured no gain on the 16-core B200 hosts, so 0 by default).
-    // packed or plain: forced by MAPF_HOST_PACK, else measured on the first nine eligible calls (see mapf_handle)
+    // packed or plain: forced by MAPF_HOST_PACK, else measured on the first sixteen eligible calls (see mapf_handle)
     // ... three candidates: packed, packed with the expansion going through non-temporal stores (hosts whose memory
     // system is the bound: no read-for-ownership of the 45 MB it writes), plain; three calls each, the first untimed.
     // Ranks that share a node should make these calls in step (they do when they step their envs in step): a rank
@@ -1143,13 +1143,16 @@ static int step_host_impl(mapf_handle *h, const int8_t *actions, const int16_t *
             if (h->knob_host_nt != 1) modes[nm++] = 1;
             if (h->knob_host_nt != 0) modes[nm++] = 2;
             modes[nm++] = 0;
-            // round robin (each mode once untimed, then twice timed): whatever else loads the host while this handle
-            // calibrates -- the other ranks of the node, calibrating too -- weighs on every candidate alike
-            const int c = h->auto_calls++;
-            const int mode = modes[c % nm];
+            // four calls per candidate in a row: the first untimed (it follows a call of another mode: the expansion
+            // threads may be asleep behind a plain call, the staging cold), the best of the other three counts -- one
+            // hiccup (a page fault, a late worker) must not decide
+            // (and four untimed calls in front of it all: kernels loaded, expansion threads created, staging touched,
+            // clocks up -- none of that may count against the candidate that happens to go first)
+            const int c = h->auto_calls++ - 4;
+            const int mode = c < 0 ? modes[0] : modes[(c / 4) < nm ? c / 4 : nm - 1];
             packed = mode != 0; nt = mode == 2;
-            if (c >= nm) auto_phase = mode;
-            if (c + 1 >= 3 * nm) auto_phase |= 0x100;   // last calibration call: decide behind it
+            if (c >= 0 && c % 4 != 0) auto_phase = mode;
+            if (c + 1 >= 4 * nm) auto_phase |= 0x100;   // last calibration call: decide behind it
         }
     }
 
@@ -1343,13 +1346,21 @@ static int step_host_impl(mapf_handle *h, const int8_t *actions, const int16_t *
     h->last_h2d_bytes = h2d;
     h->last_d2h_bytes = d2h;
     if (auto_phase >= 0) {
-        h->auto_ns[auto_phase & 0xFF] += std::chrono::steady_clock::now().time_since_epoch().count() - t_begin;
-        if (auto_phase & 0x100) {   // every candidate has two timed calls: the fastest stays (ties: packed, then NT)
+        {   // the best of a mode's timed calls: one hiccup (a page fault, a late worker) must not decide
+            const int64_t dt = std::chrono::steady_clock::now().time_since_epoch().count() - t_begin;
+            int64_t &slot = h->auto_ns[auto_phase & 0xFF];
+            if (slot == 0 || dt < slot) slot = dt;
+        }
+        if (auto_phase & 0x100) {
+            // every candidate has its best of three timed calls.  In order of preference -- packed, packed + NT, plain:
+            // fewest PCIe bytes, least host memory traffic per byte -- a later one has to win by 10 % (single calls
+            // are not timed better than that; where the host decides the margin is 30 % and more)
             int best = -1;
             const int order[3] = {1, 2, 0};
             for (int i = 0; i < 3; ++i) {
                 const int m = order[i];
-                if (h->auto_ns[m] > 0 && (best < 0 || h->auto_ns[m] < h->auto_ns[best])) best = m;
+                if (h->auto_ns[m] <= 0) continue;
+                if (best < 0 || h->auto_ns[m] * 10 < h->auto_ns[best] * 9) best = m;
             }
             h->auto_choice = best < 0 ? 1 : best;
         }

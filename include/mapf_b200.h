@@ -280,17 +280,18 @@ int mapf_step_host(mapf_handle *h, const int8_t *actions, const int16_t *goal_ov
  * agent (3 bits per window cell, 1 bit per mask entry, the integer goal difference, 2*reward) and host threads
  * inside the call expand them into the caller's arrays -- the delivered arrays are bit for bit the same.
  * Whether it pays depends on the host (PCIe rate against what its cores and memory system can expand, with
- * whatever else -- the other ranks of a multi-GPU node -- runs beside it), so the handle measures: its first nine
- * eligible calls take turns -- packed, packed with a non-temporal expansion (cache-resident blocks streamed out as whole
- * lines: no read-for-ownership of the arrays, which is what counts on a host bound by its memory system), plain, three
- * times round (the first round untimed) -- and the fastest mode stays; ranks that share a node should make these calls
+ * whatever else -- the other ranks of a multi-GPU node -- runs beside it), so the handle measures: its first sixteen
+ * eligible calls go four at a time -- a warm-up, then packed, packed with a non-temporal expansion (cache-resident blocks streamed out as
+ * whole lines: no read-for-ownership of the arrays, which is what counts on a host bound by its memory system), plain;
+ * the first of each four untimed, the best of the other three counts -- and the fastest mode stays (in that order of
+ * preference: a later one has to win by 10 %); ranks that share a node should make these calls
  * in step, so that each of them measures the host it will run on.  MAPF_HOST_PACK=0 / 1 and MAPF_HOST_NT=0 / 1 force the
  * choices, MAPF_HOST_THREADS / MAPF_HOST_SLICES tune it.  The expansion
  * threads (cores of this process / LOCAL_WORLD_SIZE, at most 16, the caller's thread included) are pinned one per
  * core to this rank's chunk of the affinity mask when the node is shared (MAPF_HOST_PIN=0 / 1 overrides).
  * mapf_host_transfer_bytes: bytes that actually crossed PCIe in the last mapf_step_host call. */
 int mapf_host_transfer_bytes(const mapf_handle *h, int64_t *h2d_bytes, int64_t *d2h_bytes);
-/* How mapf_step_host delivers the four big channels on this handle: -1 still measuring (its first nine eligible calls
+/* How mapf_step_host delivers the four big channels on this handle: -1 still measuring (its first sixteen eligible calls
  * try each mode), 0 plain copies, 1 bit-packed + expansion by host threads, 2 the same with the expansion going through
  * cache-resident blocks and non-temporal stores (hosts bound by their memory system).  MAPF_HOST_PACK / MAPF_HOST_NT
  * force a mode. */

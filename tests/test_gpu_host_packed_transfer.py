@@ -226,7 +226,7 @@ def test_records_delivery_expands_to_the_plain_arrays(sr, B):
 
 def test_non_temporal_expansion_and_measured_mode_are_exact(monkeypatch):
     """The packed delivery with the expansion going through cache-resident blocks and non-temporal stores
-    (MAPF_HOST_NT=1), and the handle's own choice -- packed / packed + NT / plain, measured on its first nine calls --
+    (MAPF_HOST_NT=1), and the handle's own choice -- packed / packed + NT / plain, measured on its first sixteen calls --
     deliver the arrays of the device-side step, whatever mode a call happens to run in."""
     monkeypatch.setenv("MAPF_HOST_PACK", "1")
     monkeypatch.setenv("MAPF_HOST_NT", "1")
@@ -234,8 +234,8 @@ def test_non_temporal_expansion_and_measured_mode_are_exact(monkeypatch):
     assert nat.lib().mapf_host_transfer_mode(b._h) == 2
     monkeypatch.delenv("MAPF_HOST_PACK", raising=False)
     monkeypatch.delenv("MAPF_HOST_NT", raising=False)
-    _, b = run_host_vs_device(c3(), 8192 + 96, 14)      # calls 0-8 calibrate, 9.. run in the mode that won
+    _, b = run_host_vs_device(c3(), 8192 + 96, 19)      # calls 0-15 calibrate, 16.. run in the mode that won
     assert nat.lib().mapf_host_transfer_mode(b._h) in (0, 1, 2)
-    monkeypatch.setenv("MAPF_HOST_NT", "0")             # NT ruled out: two candidates, six calibration calls
-    _, b = run_host_vs_device(c3(), 8192 + 96, 8)
+    monkeypatch.setenv("MAPF_HOST_NT", "0")             # NT ruled out: two candidates, twelve calibration calls
+    _, b = run_host_vs_device(c3(), 8192 + 96, 14)
     assert nat.lib().mapf_host_transfer_mode(b._h) in (0, 1)

@@ -102,7 +102,7 @@ for name, envv in SETTINGS:
     env = BatchedMapfEnv(cfg, B, dev, env_id_base=rank * B)
     env.reset()
     torch.cuda.synchronize(dev)
-    for i in range(12):
+    for i in range(18):
         barrier()
         nat.check(lib.mapf_step_host(env._h, C.c_void_p(acts[i % 4].data_ptr()), None, None, C.byref(cout), 1))
     reps = []
