@@ -248,8 +248,10 @@ int mapf_step(mapf_handle *h, const int8_t *actions, const int16_t *goal_overrid
 
 /* `steps` consecutive env steps in one call, for rollouts whose actions come from the fused benchmark sampler
  * (mapf_set_fused_sampler; scripts/benchmark_multi_agent_env.py:38-57): step 1 takes `actions`, step t + 1 the
- * actions drawn at the end of step t -- exactly what `steps` calls of mapf_step would do, bit for bit, but small
- * batches (launch-rate bound: ~10 us per launch for 4 096 x 4) run all of them inside ONE kernel launch.
+ * actions drawn at the end of step t -- exactly what `steps` calls of mapf_step would do, bit for bit, but inside ONE
+ * kernel launch (lane-per-agent and env-per-thread kernels; the two-lanes-per-env kernel launches `steps` times): small
+ * batches stop being launch-rate bound (~10 us per launch for 4 096 x 4), GPU-filling ones pay ramp-up and tail once
+ * and read each step's state from L2 -- every warp takes its envs from the first step to the last.
  * Step t writes its outputs t * out_step_stride_envs envs further into `out` (pass [steps, B, ...] buffers and
  * stride B for a rollout, or 0 to keep only the last step's).  The sampler's action buffer holds the actions for
  * the step after the last.  No replay hooks (goal_override / goal_rank) on this entry point. */
