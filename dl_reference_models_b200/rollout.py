@@ -61,6 +61,42 @@ class Batch:
     last_value: torch.Tensor  # [B,N] bootstrap value of the observation after the last step
 
 
+@dataclass
+class CompactBatch:
+    """A rollout kept the way the env emits it -- uint8 window, float32 goal delta, uint8 pressure flag: V^2 + 9 bytes per
+    agent-step instead of 4 (V^2 + 3) of float32 features -- and expanded per minibatch (:meth:`features_of`).  The other
+    fields are those of :class:`Batch`; the observation tensors hold T + 1 rows (row T: the observation after the
+    last step)."""
+    local_obs: torch.Tensor      # [T+1,B,N,V,V] uint8
+    goal_delta: torch.Tensor     # [T+1,B,N,2] float32
+    blocking_prev: torch.Tensor  # [T+1,B,N] uint8 (None when the flat observation has no pressure flag)
+    masks: torch.Tensor          # [T,B,N,5] int8 (a view of the first T rows of the collector's [T+1,...] buffer)
+    actions: torch.Tensor
+    logp: torch.Tensor
+    values: torch.Tensor
+    rewards: torch.Tensor
+    dones: torch.Tensor
+    last_value: torch.Tensor
+
+    def features_of(self, idx: torch.Tensor) -> torch.Tensor:
+        """Float32 feature rows (ENV:306-328 order: window, goal delta, pressure) of the flat agent-step indices ``idx``
+        into the first T rows."""
+        T1, B, N = self.local_obs.shape[:3]
+        V2 = self.local_obs.shape[-1] * self.local_obs.shape[-2]
+        t, r = idx // (B * N), idx % (B * N)   # the rows may be padded apart: index (step, agent), never reshape the block
+        parts = [self.local_obs.view(T1, B * N, V2)[t, r].float(), self.goal_delta.view(T1, B * N, 2)[t, r]]
+        if self.blocking_prev is not None:
+            parts.append(self.blocking_prev.view(T1, B * N)[t, r].float().unsqueeze(-1))
+        return torch.cat(parts, dim=-1)
+
+    @property
+    def features(self) -> torch.Tensor:
+        """The whole [T,B,N,F] float32 block (what :class:`Batch` stores), materialised on demand."""
+        T, B, N = self.actions.shape
+        n = T * B * N
+        return self.features_of(torch.arange(n, device=self.actions.device)).reshape(T, B, N, -1)
+
+
 def sample_categorical(logits: torch.Tensor):
     """Gumbel-max draw from softmax(logits) and its log-probability (no multinomial kernel)."""
     logp_all = torch.log_softmax(logits, dim=-1)
@@ -77,16 +113,31 @@ class FusedCollector:
     of a step is two ctypes calls.  The buffers are reused: the :class:`Batch` of one :meth:`collect` is overwritten
     by the next."""
 
-    def __init__(self, env, fused, steps: int):
+    def __init__(self, env, fused, steps: int, compact: bool = False):
         import ctypes as C
 
         from . import _native as nat
 
-        self.env, self.fused, self.T = env, fused, int(steps)
+        self.env, self.fused, self.T, self.compact = env, fused, int(steps), bool(compact)
         B, N, T, dev = env.B, env.N, self.T, env.device
         F = env.flat_obs_dim(include_action_mask=False)
-        self.feats = torch.empty((T, B, N, F), device=dev)
-        self.masks = torch.empty((T, B, N, 5), dtype=torch.int8, device=dev)
+        if self.compact:
+            # compact rollout: the env step writes the observation channels of step t straight into row t + 1 of
+            # [T + 1, ...] buffers, the policy kernel reads row t and stores no feature block at all
+            o = env.out
+
+            def rows_of(t):   # [T + 1, *t.shape] with every row 256-byte aligned (the kernels store 128-bit words)
+                n, es = t.numel(), t.element_size()
+                stride = -(-(n * es) // 256) * 256 // es
+                buf = torch.empty((T + 1, stride), dtype=t.dtype, device=dev)
+                return buf[:, :n].view((T + 1,) + tuple(t.shape))
+
+            self.obs_rows = {k: rows_of(o[k]) for k in ("local_obs", "goal_delta", "blocking_prev", "action_mask")}
+            self.feats = None
+            self.masks = self.obs_rows["action_mask"][:T]
+        else:
+            self.feats = torch.empty((T, B, N, F), device=dev)
+            self.masks = torch.empty((T, B, N, 5), dtype=torch.int8, device=dev)
         self.actions = torch.empty((T, B, N), dtype=torch.int64, device=dev)
         self.logp = torch.empty((T, B, N), device=dev)
         self.values = torch.empty((T, B, N), device=dev)
@@ -98,22 +149,38 @@ class FusedCollector:
         vp = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
         o = env.out
 
+        rows = self.obs_rows if self.compact else None
+
+        def src(k, t):   # where the policy kernel of step t reads channel k
+            return vp(rows[k][t]) if rows is not None else vp(o[k])
+
         def policy_args(t):
             last = t == T
             return nat.MapfPolicyArgs(
                 num_envs=B, num_agents=N, v2=env.V * env.V, feature_dim=fused.F,
                 no_masking=int(bool(fused.policy.no_masking)), reserved=0, seed=fused.seed, counter=0,
-                env_id_base=int(env.cfg.env_id_base), local_obs=vp(o["local_obs"]), goal_delta=vp(o["goal_delta"]),
-                blocking_prev=vp(o["blocking_prev"]) if fused.with_bp else None, action_mask=vp(o["action_mask"]),
+                env_id_base=int(env.cfg.env_id_base), local_obs=src("local_obs", t), goal_delta=src("goal_delta", t),
+                blocking_prev=src("blocking_prev", t) if fused.with_bp else None, action_mask=src("action_mask", t),
                 weights=vp(fused._dev), actions=vp(fused.actions),
                 actions64=vp(fused.actions64 if last else self.actions[t]), logp=vp(fused.logp if last else self.logp[t]),
                 value=vp(self.last_value if last else self.values[t]), logits_out=None,
-                features_out=None if last else vp(self.feats[t]), action_mask_out=None if last else vp(self.masks[t]))
+                features_out=None if (last or self.compact) else vp(self.feats[t]),
+                action_mask_out=None if (last or self.compact) else vp(self.masks[t]))
 
         self._pargs = [policy_args(t) for t in range(T + 1)]   # the last one: bootstrap value of the final observation
-        self._couts = [nat.MapfOutputs(**{k: ((self.rewards[t] if k == "reward" else self.term[t] if k == "terminated"
-                                               else self.trunc[t] if k == "truncated" else o[k]).data_ptr())
-                                          for k in nat.OUTPUT_FIELDS}) for t in range(T)]
+
+        def dst(k, t):   # where the env step t writes channel k
+            if k == "reward":
+                return self.rewards[t]
+            if k == "terminated":
+                return self.term[t]
+            if k == "truncated":
+                return self.trunc[t]
+            if rows is not None and k in rows:
+                return rows[k][t + 1]
+            return o[k]
+
+        self._couts = [nat.MapfOutputs(**{k: dst(k, t).data_ptr() for k in nat.OUTPUT_FIELDS}) for t in range(T)]
         self._actions_ptr = vp(fused.actions)
 
     @torch.no_grad()
@@ -123,6 +190,9 @@ class FusedCollector:
         if getattr(env, "_fused", 0):
             raise RuntimeError("turn the env's fused uniform sampler off (fuse_sampler(None)) before a policy rollout")
         stream, h, check = env._stream(), env._h, self._nat.check
+        if self.compact:   # row 0 = the env's current observation
+            for k, r in self.obs_rows.items():
+                r[0].copy_(env.out[k])
         for t in range(self.T):
             fused.counter += 1
             a = self._pargs[t]
@@ -134,6 +204,12 @@ class FusedCollector:
         a.counter = fused.counter
         check(lib.mapf_policy_act(C.byref(a), stream))
         dones = (self.term | self.trunc).bool()
+        if self.compact:
+            for k, r in self.obs_rows.items():   # the env's own buffers show the latest observation again
+                env.out[k].copy_(r[self.T])
+            return CompactBatch(self.obs_rows["local_obs"], self.obs_rows["goal_delta"],
+                                self.obs_rows["blocking_prev"] if fused.with_bp else None, self.masks, self.actions,
+                                self.logp, self.values, self.rewards, dones, self.last_value)
         return Batch(self.feats, self.masks, self.actions, self.logp, self.values, self.rewards, dones, self.last_value)
 
 
@@ -195,19 +271,19 @@ def ppo_update(policy, optimizer, batch: Batch, *, clip: float = 0.05, vf_coeff:
                entropy_coeff: float = 0.001, epochs: int = 12, minibatch: int = 1024, gamma: float = 0.99,
                lam: float = 0.95, max_minibatches: int | None = None) -> dict:
     adv, ret = gae(batch.rewards, batch.values, batch.dones, batch.last_value, gamma, lam)
-    F = batch.features.shape[-1]
-    feats = batch.features.reshape(-1, F)
+    compact = isinstance(batch, CompactBatch)
+    feats = None if compact else batch.features.reshape(-1, batch.features.shape[-1])
     masks = batch.masks.reshape(-1, batch.masks.shape[-1])
     acts, old_logp = batch.actions.reshape(-1), batch.logp.reshape(-1)
     adv, ret = adv.reshape(-1), ret.reshape(-1)
     adv = (adv - adv.mean()) / (adv.std() + 1e-8)
-    n = feats.shape[0]
+    n = acts.shape[0]
     stats, done_mb = {}, 0
     for _ in range(epochs):
-        perm = torch.randperm(n, device=feats.device)
+        perm = torch.randperm(n, device=acts.device)
         for i in range(0, n, minibatch):
             idx = perm[i:i + minibatch]
-            lg, v = policy(feats[idx], masks[idx])
+            lg, v = policy(batch.features_of(idx) if compact else feats[idx], masks[idx])
             dist = torch.distributions.Categorical(logits=lg)
             lp = dist.log_prob(acts[idx])
             ratio = torch.exp(lp - old_logp[idx])
@@ -256,16 +332,20 @@ def benchmark(num_envs: int = 65536, steps: int = 64, device: str = "cuda:0") ->
 
     env.fuse_sampler(None)
     fused = FusedPolicy(policy, env)
-    collector = FusedCollector(env, fused, steps)
-    collector.collect()
-    torch.cuda.synchronize(env.device)
-    t0 = time.perf_counter()
-    collector.collect()
-    torch.cuda.synchronize(env.device)
-    fused_s = time.perf_counter() - t0
+    res = {}
+    for name, compact in (("fused_policy_loop", False), ("fused_policy_loop_compact", True)):
+        collector = FusedCollector(env, fused, steps, compact=compact)
+        collector.collect()
+        torch.cuda.synchronize(env.device)
+        t0 = time.perf_counter()
+        collector.collect()
+        torch.cuda.synchronize(env.device)
+        res[name] = time.perf_counter() - t0
+        del collector
     n = num_envs * env.N * steps
     return {"envs": num_envs, "agents": env.N, "steps": steps, "env_only_agent_steps_per_s": n / env_s,
-            "policy_loop_agent_steps_per_s": n / loop_s, "fused_policy_loop_agent_steps_per_s": n / fused_s}
+            "policy_loop_agent_steps_per_s": n / loop_s, "fused_policy_loop_agent_steps_per_s": n / res["fused_policy_loop"],
+            "fused_policy_loop_compact_agent_steps_per_s": n / res["fused_policy_loop_compact"]}
 
 
 if __name__ == "__main__":

@@ -162,3 +162,39 @@ def test_fused_collect_rows_are_what_a_manual_loop_sees():
         assert torch.equal(ea.state[k], eb.state[k]), k
     with pytest.raises(ValueError):
         ea.step(None, reward_out=torch.zeros(3, device=ea.device))
+
+
+def test_compact_fused_collector_equals_the_feature_storing_one():
+    """FusedCollector(compact=True): the env step writes the observation channels of step t into row t + 1 of
+    [T + 1, ...] buffers, the policy kernel reads row t and stores no float32 feature block (V^2 + 9 instead of
+    4 (V^2 + 3) bytes per agent-step).  Same actions, log-probabilities, values, rewards, episode ends and env state as
+    the feature-storing collector; the features expanded from the compact rows are its features; it trains; a second
+    collect continues from the first."""
+    import torch
+
+    from dl_reference_models_b200.policy_kernels import FusedPolicy
+    from dl_reference_models_b200.rollout import ActionMaskPolicy, CompactBatch, FusedCollector, ppo_update
+
+    T = 40
+    ea, _ = make_env(B=203, n=7)
+    eb, _ = make_env(B=203, n=7)
+    torch.manual_seed(0)
+    policy = ActionMaskPolicy(ea.flat_obs_dim(include_action_mask=False)).to(ea.device)
+    fa, fb = FusedPolicy(policy, ea, seed=5), FusedPolicy(policy, eb, seed=5)
+    ca, cb = FusedCollector(ea, fa, T), FusedCollector(eb, fb, T, compact=True)
+    for rnd in range(2):
+        a, b = ca.collect(), cb.collect()
+        assert isinstance(b, CompactBatch)
+        for k in ("actions", "logp", "values", "rewards", "dones", "last_value", "masks"):
+            assert torch.equal(getattr(a, k), getattr(b, k)), f"round {rnd}: {k}"
+        assert torch.equal(a.features, b.features), f"round {rnd}: features"
+        idx = torch.tensor([0, 5, 203 * 7 * 3 + 11, T * 203 * 7 - 1], device=ea.device)
+        assert torch.equal(a.features.reshape(-1, a.features.shape[-1])[idx], b.features_of(idx))
+        for k in ea.state:
+            assert torch.equal(ea.state[k], eb.state[k]), k
+        for k in ("local_obs", "goal_delta", "blocking_prev", "action_mask"):
+            assert torch.equal(ea.out[k], eb.out[k]), f"round {rnd}: env buffer {k}"
+    assert bool(b.dones.any())
+    opt = torch.optim.Adam(policy.parameters(), lr=1e-3)
+    stats = ppo_update(policy, opt, b, epochs=1, max_minibatches=3)
+    assert all(np.isfinite(v) for v in stats.values())
