@@ -80,3 +80,36 @@ def test_policy_env_loop_and_ppo_update_on_device():
     stats = ppo_update(pol, opt, batch, epochs=1, minibatch=1024, max_minibatches=8)
     assert all(np.isfinite(v) for v in stats.values())
     assert any(not torch.equal(a, b) for a, b in zip(before, pol.parameters()))
+
+
+def test_compact_batch_expands_features_from_padded_rows():
+    """CompactBatch.features_of: float32 feature rows (window, goal delta, pressure) of arbitrary agent-steps out of
+    uint8 / float32 rows that are padded apart (256-byte aligned rows), without ever reshaping the whole block."""
+    import torch
+
+    from dl_reference_models_b200.rollout import CompactBatch
+
+    T, B, N, V = 3, 5, 7, 5
+    gen = torch.Generator().manual_seed(0)
+
+    def rows(shape, dtype):
+        n = int(np.prod(shape))
+        es = torch.empty((), dtype=dtype).element_size()
+        stride = -(-(n * es) // 256) * 256 // es
+        buf = torch.zeros((T + 1, stride), dtype=dtype)
+        return buf[:, :n].view((T + 1,) + shape)
+
+    lo, gd, bp = rows((B, N, V, V), torch.uint8), rows((B, N, 2), torch.float32), rows((B, N), torch.uint8)
+    lo.copy_(torch.randint(0, 5, lo.shape, generator=gen).to(torch.uint8))
+    gd.copy_(torch.rand(gd.shape, generator=gen))
+    bp.copy_(torch.randint(0, 2, bp.shape, generator=gen).to(torch.uint8))
+    assert not lo.is_contiguous()
+    z = torch.zeros((T, B, N))
+    b = CompactBatch(lo, gd, bp, torch.zeros((T, B, N, 5), dtype=torch.int8), z.long(), z, z, z, torch.zeros((T, B), dtype=torch.bool),
+                     torch.zeros((B, N)))
+    want = torch.cat([lo[:T].reshape(T, B, N, V * V).float(), gd[:T], bp[:T].float().unsqueeze(-1)], dim=-1)
+    assert torch.equal(b.features, want)
+    idx = torch.tensor([0, 1, B * N, T * B * N - 1, 17])
+    assert torch.equal(b.features_of(idx), want.reshape(-1, V * V + 3)[idx])
+    b2 = CompactBatch(lo, gd, None, b.masks, b.actions, z, z, z, b.dones, b.last_value)
+    assert b2.features.shape[-1] == V * V + 2
