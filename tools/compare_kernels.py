@@ -1,6 +1,7 @@
-"""First-contact check of the two-lanes-per-env step kernel against the env-per-thread kernel: runs both on the same
-configuration and prints, per step, which state / output tensors differ (count and first indices) instead of stopping
-at the first difference.  usage: python tools/debug_pair.py [B] [steps] [agents] [ref_kind]"""
+"""Two step kernels side by side on the same configuration (C3-like, 20-step episodes, Philox draws, in-launch resets,
+fused masked sampler): prints, per step, which state / output tensors differ (count and first indices) instead of
+stopping at the first difference -- the first-contact check of a new or changed kernel.
+usage: [DBG_KIND=pair|env|lane] python tools/compare_kernels.py [B] [steps] [agents] [ref_kind]"""
 import sys
 
 import torch
